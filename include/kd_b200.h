@@ -1,0 +1,150 @@
+/* kd_b200.h - C ABI of libkd_b200.so, the B200 (sm_100a) implementation of the
+ * speech-distill knowledge-distillation hot path.
+ *
+ * The reference (indiejoseph/speech-distill) is pure Python and has no FFI of its own; the
+ * entry points below are what a binding for its one arithmetic module would call.  Each one
+ * cites the reference code it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - tensors are row-major, last dimension contiguous; strides are in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every call is asynchronous on `stream`, never synchronises the host and never allocates;
+ *   - return value 0 = success, non-zero = error, text via kd_last_error() (thread local);
+ *   - dtype codes: KD_DTYPE_F32 / KD_DTYPE_BF16 / KD_DTYPE_F16.
+ *
+ * Row convention (distillation_loss.py:31-45): with logits [B,T,V] and labels [B,T], row (b,t)
+ * is scored against labels[b,t+1]; it is VALID iff t < T-1, labels[b,t+1] != ignore_index and
+ * (mask == NULL or mask[b,t+1] != 0).  N = number of valid rows.
+ *
+ * Sums record (float[8], written by the *_fwd* calls):
+ *   [0] sum over valid rows of CE_r  = LSE(z) - z[label]                    (distillation_loss.py:123)
+ *   [1] sum over valid rows of KL_r  (temperature tau, WITHOUT the tau^2)   (:66-68 dense, :94-106 sparse)
+ *   [2] dense : sum of teacher CE_r = LSE(y) - y[label]                     (:71)
+ *       sparse: sum of v[r,k] over hits (i[r,k] == label)                   (:110-116)
+ *   [3] N (valid rows seen by this call)
+ *   [4] sparse: number of hits; dense: 0
+ *   [5..7] reserved (0)
+ * Normalisation (/N, *tau^2, alpha mix) is a separate call so that a data-parallel caller can
+ * all-reduce the record first.
+ */
+#ifndef KD_B200_H_
+#define KD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KD_DTYPE_F32 0
+#define KD_DTYPE_BF16 1
+#define KD_DTYPE_F16 2
+
+#define KD_ABI_VERSION 1
+
+/* Teacher kinds for the fused LM-head entry points. */
+#define KD_TEACHER_NONE 0   /* CE only (stage1 warm-up, stage1.py:298-340) */
+#define KD_TEACHER_DENSE 1  /* full-vocab teacher logits (distillation_loss.py:56-71) */
+#define KD_TEACHER_SPARSE 2 /* top-k log-probs + indices (distillation_loss.py:73-118) */
+
+int kd_version(void);
+const char* kd_last_error(void); /* host string, valid until the next failing call on this thread */
+
+/* Number of SMs / compute capability of the current device (host helper for callers that size work). */
+int kd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- row bookkeeping -------------------------------------------------------------------
+ * distillation_loss.py:34-45: builds, for every row r = b*T + t, row_target[r] = labels[b,t+1]
+ * if the row is valid else -1, and counts the valid rows.  labels int64 [B,T] contiguous;
+ * mask uint8 [B,T] (non-zero = keep) or NULL.  row_target may be NULL (count only). */
+int kd_prepare_rows(const int64_t* labels, const uint8_t* mask, int B, int T, int64_t ignore_index,
+                    int32_t* row_target, int32_t* n_valid, void* stream);
+
+/* distillation_loss.py:68 (*tau^2, batchmean /N), :116-118, :123, :126.
+ * sums float[8] as above -> losses float[4] = (total, task, distill, teacher_task).
+ * N == 0 gives four zeros (:47-53). */
+int kd_finalize_losses(const float* sums, float tau, float alpha, int sparse, float* losses, void* stream);
+
+/* ---- K2: streaming KD on materialised logits --------------------------------------------
+ * Replaces DistillationLoss.forward + its autograd (distillation_loss.py:14-128) for the dense
+ * teacher.  z = student logits, y = teacher logits, both [B,T,V] with arbitrary b/t strides.
+ * n_norm: device int32 holding the normaliser N used in the gradient (this rank's N from
+ * kd_prepare_rows, or the all-reduced global N).  grad_scale: host scalar folded into dlogits.
+ * dlogits: NULL (forward only: one sweep, 4 B/element for bf16) or a contiguous [B,T,V] buffer of
+ * z's dtype that receives d(total)/dz * grad_scale for EVERY row (zeros on invalid rows).
+ * workspace: kd_stream_workspace_bytes() bytes, 16-byte aligned. */
+size_t kd_stream_workspace_bytes(void);
+int kd_dense_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b, int64_t z_stride_t,
+                     const void* y, int y_dtype, int64_t y_stride_b, int64_t y_stride_t,
+                     const int32_t* row_target, int B, int T, int V, float tau, float alpha,
+                     const int32_t* n_norm, float grad_scale, float* sums, void* dlogits,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sparse teacher (distillation_loss.py:73-118): topk_v float32 [B,T,K] teacher log-probs at
+ * tau = 1, topk_i int32 [B,T,K] vocabulary indices (both contiguous).  K <= 1024. */
+int kd_sparse_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b, int64_t z_stride_t,
+                      const float* topk_v, const int32_t* topk_i, int K,
+                      const int32_t* row_target, int B, int T, int V, float tau, float alpha,
+                      const int32_t* n_norm, float grad_scale, float* sums, void* dlogits,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* x[i] *= *scale for i < n, skipped on device when *scale == 1 (upstream grad_output of the
+ * scalar loss; accelerate divides the loss by the accumulation steps, train.py:349). */
+int kd_scale_inplace(void* x, int dtype, int64_t n, const float* scale, void* stream);
+
+/* ---- K3: teacher top-k log-prob compaction -----------------------------------------------
+ * train.py:82-91 and extract_teacher_logits.py:114-129: log_softmax over V, top-k, values to
+ * fp16, indices to int32.  logits [R,V] (row stride in elements), out_v fp16 [R,k], out_i
+ * int32 [R,k].  Output order: logit descending, ties by ascending index.  k <= 512. */
+int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k,
+                     void* out_v, int32_t* out_i, void* stream);
+
+/* ---- stage1 frozen-vocabulary row mask -----------------------------------------------------
+ * stage1.py:53-57 / 67-71: grad[:old_vocab] = 0, in place on a [V,H] gradient. */
+int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stream);
+
+/* ---- K1: fused LM head + KD (logits never materialised) ------------------------------------
+ * Replaces lm_head (transformers Qwen3ForCausalLM.lm_head, called at train.py:54) followed by
+ * DistillationLoss.forward, and their backward.  h [R,H] bf16 (R = B*T rows, row stride
+ * h_stride), W [V,H] bf16 (row stride w_stride), row_target from kd_prepare_rows.
+ * Teacher: dense y [R,V] (y_dtype bf16/f16/f32, row stride y_stride), sparse (topk_v, topk_i, K)
+ * or none (alpha is forced to 1: plain causal-LM CE, stage1).
+ *
+ * kd_fused_linear_fwd  : sums[8] and row_stats float[R,4] = (LSE1, LSEtau, LSEteacher_tau, valid).
+ * kd_fused_linear_bwd  : dH [R,H] bf16 and dW [V,H] bf16 (rows < dw_row_begin are NOT written:
+ *                        stage1 passes old_vocab and zero-fills once, stage1.py:46-57);
+ *                        grad_coef: device float[2] = (w_ce, w_kl); the gradient returned is
+ *                        d[(w_ce * sum CE + w_kl * tau^2 * sum KL) / N]; the usual call passes
+ *                        (alpha * g, (1 - alpha) * g) with g the upstream grad of the total loss
+ *                        (distillation_loss.py:126); n_norm as above.
+ * v_chunk: vocabulary columns per backward chunk (0 = library default); the gradient scratch is
+ * R x v_chunk bf16, independent of V.  workspace sized by kd_fused_workspace_bytes(). */
+size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk);
+int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                        int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
+                        const float* topk_v, const int32_t* topk_i, int K,
+                        const int32_t* row_target, int R, int H, int V, float tau, float alpha,
+                        float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
+                        void* stream);
+int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                        int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
+                        const float* topk_v, const int32_t* topk_i, int K,
+                        const int32_t* row_target, const float* row_stats, int R, int H, int V,
+                        float tau, const int32_t* n_norm, const float* grad_coef,
+                        void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
+                        int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Plain bf16 GEMM on the same tcgen05 pipeline (test hook for the K1 building block), fp32 out:
+ *   C[M,N] (ldc) = op(A) * op(B)^T with
+ *   a_mn_major = 0: A is [M][K] (K contiguous, lda)   | 1: A is [K][M] (M contiguous, lda)
+ *   b_mn_major = 0: B is [N][K] (K contiguous, ldb)   | 1: B is [K][N] (N contiguous, ldb)
+ * (a_mn_major = 1, b_mn_major = 0) is not instantiated. */
+int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                 float* C, int64_t ldc, int M, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KD_B200_H_ */

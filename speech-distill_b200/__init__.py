@@ -1,0 +1,19 @@
+"""speech_distill_b200 - B200 (sm_100a) implementation of the speech-distill KD hot path.
+
+Host-side mirror of the reference interface over libkd_b200.so (C ABI: include/kd_b200.h):
+
+* ``DistillationLoss``            - reference ``distillation_loss.py`` (drop-in module)
+* ``kd_loss_on_logits``           - functional form, with data-parallel hooks
+* ``fused_linear_kd_loss``        - LM head + KD without materialising logits (K1)
+* ``teacher_topk_logprobs``       - reference ``extract_teacher_logits.py:114-129`` / ``train.py:82-91``
+* ``freeze_model_weights`` / ``fused_linear_cross_entropy`` / ``mask_old_rows_`` - reference ``stage1.py:29-93``
+"""
+from ._lib import KdError, LIB_PATH, load as load_library  # noqa: F401
+from .loss import DistillationLoss, fused_linear_kd_loss, kd_loss_on_logits  # noqa: F401
+from .stage1 import freeze_model_weights, fused_linear_cross_entropy, mask_old_rows_  # noqa: F401
+from .topk import extract_batch, teacher_topk_logprobs  # noqa: F401
+
+__all__ = [
+    "DistillationLoss", "kd_loss_on_logits", "fused_linear_kd_loss", "teacher_topk_logprobs", "extract_batch",
+    "freeze_model_weights", "fused_linear_cross_entropy", "mask_old_rows_", "KdError", "load_library", "LIB_PATH",
+]

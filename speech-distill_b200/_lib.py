@@ -1,0 +1,100 @@
+"""ctypes binding of libkd_b200.so (the C ABI declared in include/kd_b200.h).
+
+There is no CPU fallback: if the library is missing, or a call is made without a CUDA device,
+the caller gets an exception, never a silently slower path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkd_b200.so")
+
+KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
+KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
+
+_c = ctypes
+_vp, _i32, _i64, _f32, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/kd_b200.h one to one
+SIGNATURES = {
+    "kd_version": (_i32, []),
+    "kd_last_error": (_c.c_char_p, []),
+    "kd_device_info": (_i32, [_c.POINTER(_i32)] * 3),
+    "kd_prepare_rows": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
+    "kd_finalize_losses": (_i32, [_vp, _f32, _f32, _i32, _vp, _vp]),
+    "kd_stream_workspace_bytes": (_sz, []),
+    "kd_dense_fwd_bwd": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i64, _vp, _i32, _i32, _i32, _f32, _f32,
+                                _vp, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_sparse_fwd_bwd": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
+                                 _vp, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "kd_topk_logprobs": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "kd_mask_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
+    "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "kd_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _i32,
+                                   _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32,
+                                   _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz,
+                                   _vp]),
+    "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+class KdError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KdError(
+            f"{LIB_PATH} not found: build it with `python speech-distill_b200/build.py` "
+            "(the KD kernels have no CPU or PyTorch fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.kd_version() != 1:
+        raise KdError(f"libkd_b200 ABI version {lib.kd_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().kd_last_error().decode("utf-8", "replace")
+        raise KdError(f"{what} failed (code {rc}): {msg}")
+
+
+def dtype_code(t):
+    import torch
+
+    if t == torch.float32:
+        return KD_DTYPE_F32
+    if t == torch.bfloat16:
+        return KD_DTYPE_BF16
+    if t == torch.float16:
+        return KD_DTYPE_F16
+    raise TypeError(f"unsupported dtype {t}; the KD kernels take float32, bfloat16 or float16")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise KdError(
+                "speech_distill_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                f"got a tensor on {t.device}"
+            )
+
+
+def stream_ptr(device):
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

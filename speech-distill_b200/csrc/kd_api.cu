@@ -1,0 +1,39 @@
+// C-ABI plumbing shared by all kernels: error text, version, device info.
+#include <cstdarg>
+#include <cstdio>
+
+#include "kd_common.cuh"
+
+namespace kd {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return 2;
+}
+
+}  // namespace kd
+
+extern "C" int kd_version(void) { return KD_ABI_VERSION; }
+
+extern "C" const char* kd_last_error(void) { return kd::g_error; }
+
+extern "C" int kd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  if (kd::check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 2;
+  cudaDeviceProp prop;
+  if (kd::check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return 2;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}

@@ -1,0 +1,994 @@
+// K1: fused LM head + KD loss on the Blackwell tensor pipeline (tcgen05 / TMEM / TMA).
+//
+// Replaces `logits = lm_head(hidden)` (transformers Qwen3ForCausalLM, called at train.py:54)
+// followed by DistillationLoss.forward (distillation_loss.py:14-128) and their autograd, without
+// ever materialising the [rows, V] logits.
+//
+// One persistent, warp-specialised kernel template serves every GEMM on the path:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 4-stage smem ring, SWIZZLE_128B)
+//   warp 1      : MMA issuer    (one thread, tcgen05.mma kind::f16, 128 x 256 x 16, fp32 in TMEM)
+//   warp 2      : TMEM allocator (2 accumulator buffers x 256 columns = all 512 columns)
+//   warps 4..11 : epilogue      (tcgen05.ld 32x32b: one thread per accumulator row)
+// and the epilogue is a policy:
+//   FwdEpi  : online soft-max statistics of the student tile + streamed teacher tile (forward)
+//   GradEpi : recomputed tile -> gradient tile G (bf16) into a V-independent scratch (backward)
+//   StoreEpi: dW chunk = G^T h (final rows, bf16) and dH += G W_chunk (fp32 accumulate -> bf16)
+//
+// Algorithmic FLOPs: 2 R H V (forward) + 2 R H V (dH) + 2 R H V (dW); executed: + 2 R H V
+// (tile recompute in the backward, the price of not storing logits).
+#include <cuda.h>
+
+#include "kd_common.cuh"
+#include "kd_umma.cuh"
+
+namespace kd {
+namespace fused {
+
+using namespace umma;
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;  // 384
+constexpr uint32_t kABytes = BM * BK * 2;       // 16 KB
+constexpr uint32_t kBBytes = BN * BK * 2;       // 32 KB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kBoxMnBytes = 64 * BK * 2;   // one 64(mn) x 64(k) MN-major box = 8 KB
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
+
+struct Geom {
+  int num_m_blk, num_n_blk, num_k_blk;
+  int a_m0, a_k0, b_n0, b_k0;  // element offsets added to the TMA coordinates
+  int n_per_unit;              // consecutive n blocks handled by one work unit (same m block)
+  int num_units;
+};
+
+__host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, int& range, int& n_begin, int& n_end) {
+  range = u / g.num_m_blk;
+  m_blk = u - range * g.num_m_blk;
+  n_begin = range * g.n_per_unit;
+  n_end = n_begin + g.n_per_unit < g.num_n_blk ? n_begin + g.n_per_unit : g.num_n_blk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue policies.  Each epilogue thread owns accumulator row `row_in_tile` and the column half
+// `half` (128 columns) of every 128 x 256 tile, visited in four 32-column chunks.
+// ---------------------------------------------------------------------------------------------
+struct EpiThread {
+  int row_in_tile;  // 0..127 (TMEM lane)
+  int half;         // 0/1
+  uint32_t tmem_lane_off;  // lane field of the TMEM address
+};
+
+template <typename TY>
+__device__ __forceinline__ void load_row32(const TY* __restrict__ p, bool vec_ok, int ncols, float (&f)[32]) {
+  // ncols = number of in-range columns (<= 32); out-of-range columns read as -inf
+  if (vec_ok && ncols == 32) {
+    if constexpr (sizeof(TY) == 2) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        Vec8<TY> v;
+        v.load_global(p + 8 * q);
+        float t[8];
+        v.unpack(t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[8 * q + j] = t[j];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        Vec8<float> v;
+        v.load_global(reinterpret_cast<const float*>(p) + 8 * q);
+        float t[8];
+        v.unpack(t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[8 * q + j] = t[j];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = j < ncols ? Elem<TY>::to_f(p[j]) : -CUDART_INF_F;
+  }
+}
+
+// ---- forward: online statistics -------------------------------------------------------------
+struct FwdParams {
+  const int32_t* row_target;
+  const void* y;
+  int64_t y_stride;
+  int y_vec_ok;
+  int R, V;
+  float inv_tau;
+  float* partials;  // [num_ranges * 2][R][kRecFloats]
+};
+
+template <typename TY, bool DENSE, bool TAU2>
+struct FwdEpi {
+  using Params = FwdParams;
+  const Params& p;
+  EpiThread t;
+  int row, target, range;
+  float m, s1, st, mt, t1, tt, a, zl;
+
+  __device__ FwdEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {}
+
+  __device__ void begin_unit(const Geom&, int m_blk, int range_) {
+    row = m_blk * BM + t.row_in_tile;
+    range = range_;
+    target = row < p.R ? p.row_target[row] : -1;
+    m = mt = -CUDART_INF_F;
+    s1 = st = t1 = tt = a = zl = 0.f;
+  }
+
+  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc) {
+    const int col_base = g.b_n0 + n_blk * BN + t.half * (BN / 2);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
+      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(t.half * (BN / 2) + c * 32), raw);
+      tmem_ld_wait();
+      const int col0 = col_base + c * 32;
+      const int ncols = p.V - col0 < 32 ? p.V - col0 : 32;
+      if (target < 0 || ncols <= 0) continue;
+      float fz[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) fz[j] = j < ncols ? __uint_as_float(raw[j]) : -CUDART_INF_F;
+      const unsigned d = (unsigned)(target - col0);
+      if (d < 32u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j == (int)d) zl = fz[j];
+      }
+      student_update<TAU2, 32>(fz, 32, p.inv_tau, m, s1, st);
+      if (DENSE) {
+        float fy[32];
+        const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
+        load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
+        teacher_update<TAU2, 32>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
+      }
+    }
+  }
+
+  __device__ void end_unit(const Geom&) {
+    if (row < p.R) {
+      float* rec = p.partials + ((size_t)(range * 2 + t.half) * p.R + row) * kRecFloats;
+      *reinterpret_cast<float4*>(rec) = make_float4(m, s1, st, mt);
+      *reinterpret_cast<float4*>(rec + 4) = make_float4(t1, tt, a, zl);
+    }
+  }
+};
+
+// ---- backward: gradient tile ------------------------------------------------------------------
+struct GradParams {
+  const int32_t* row_target;
+  const float* row_stats;  // [R][4] = LSE1, LSE_tau, LSEteacher_tau, valid
+  const void* y;
+  int64_t y_stride;
+  int y_vec_ok;
+  int R, V;
+  float tau;
+  int use_kl;  // 0: CE only (no teacher)
+  const int32_t* n_norm;
+  const float* coef;  // device float[2]: weight of d(sum CE) and of tau^2 d(sum KL) in the returned gradient
+  __nv_bfloat16* G;  // [R][ldg], column j <-> vocabulary index v0 + j
+  int64_t ldg;
+  int v0;
+};
+
+template <typename TY, bool DENSE, bool TAU2>
+struct GradEpi {
+  using Params = GradParams;
+  const Params& p;
+  EpiThread t;
+  int row, target;
+  float c1, c2, c_tau, off1, offt, offy, half_off1, k_tau;
+
+  __device__ GradEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {
+    const int nn = *p.n_norm;
+    const float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
+    c1 = p.coef[0] * inv_n;
+    c2 = p.use_kl ? p.coef[1] * p.tau * inv_n : 0.f;
+    c_tau = kLog2e / p.tau;
+  }
+
+  __device__ void begin_unit(const Geom&, int m_blk, int) {
+    row = m_blk * BM + t.row_in_tile;
+    target = row < p.R ? p.row_target[row] : -1;
+    if (target >= 0) {
+      const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
+      off1 = rs.x * kLog2e;
+      offt = rs.y * kLog2e;
+      offy = rs.z * kLog2e;
+      half_off1 = 0.5f * off1;
+      k_tau = c2 * ex2(half_off1 - offt);
+    }
+  }
+
+  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc) {
+    const int jbase = n_blk * BN + t.half * (BN / 2);  // column inside the chunk scratch
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
+      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(t.half * (BN / 2) + c * 32), raw);
+      tmem_ld_wait();
+      if (row >= p.R) continue;
+      const int j0 = jbase + c * 32;
+      const int col0 = p.v0 + j0;
+      const int ncols = p.V - col0 < 32 ? p.V - col0 : 32;
+      float gq[32];
+      if (target < 0 || ncols <= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gq[j] = 0.f;
+      } else {
+        float fy[32];
+        if (DENSE) {
+          const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
+          load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float z = __uint_as_float(raw[j]);
+          float gi;
+          if (TAU2) {
+            const float e = ex2(fmaf(z, c_tau, -half_off1));
+            gi = e * fmaf(e, c1, k_tau);
+          } else {
+            gi = c1 * ex2(fmaf(z, kLog2e, -off1)) + c2 * ex2(fmaf(z, c_tau, -offt));
+          }
+          if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[j], c_tau, -offy)), gi);
+          gq[j] = j < ncols ? gi : 0.f;
+        }
+        const unsigned d = (unsigned)(target - col0);
+        if (d < 32u) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j == (int)d) gq[j] -= c1;
+        }
+      }
+      __nv_bfloat16* out = p.G + (int64_t)row * p.ldg + j0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float t8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t8[j] = gq[8 * q + j];
+        Vec8<__nv_bfloat16> v;
+        v.pack(t8);
+        *reinterpret_cast<uint4*>(out + 8 * q) = v.a;  // stays in L2 for the dW / dH GEMMs
+      }
+    }
+  }
+
+  __device__ void end_unit(const Geom&) {}
+};
+
+// ---- plain stores: dW rows (bf16), dH accumulation (fp32 -> bf16), test hook (fp32) ------------
+enum StoreMode { kStoreF32 = 0, kAccumF32 = 1, kFinalBf16 = 2, kStoreBf16 = 3 };
+struct StoreParams {
+  int mode;
+  int m_total, n_total;    // valid extent of the logical C (rows, cols)
+  int m_begin;             // rows below this are not written (stage1: old vocabulary)
+  float* c32;              // fp32 C / accumulator, row stride ld32
+  int64_t ld32;
+  __nv_bfloat16* c16;      // bf16 output, row stride ld16
+  int64_t ld16;
+  int64_t row0_32, row0_16;  // row offsets of tile row 0 inside c32 / c16
+};
+
+struct StoreEpi {
+  using Params = StoreParams;
+  const Params& p;
+  EpiThread t;
+  int row;
+
+  __device__ StoreEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {}
+  __device__ void begin_unit(const Geom&, int m_blk, int) { row = m_blk * BM + t.row_in_tile; }
+
+  __device__ void tile(const Geom&, int n_blk, uint32_t tmem_acc) {
+    const int col_base = n_blk * BN + t.half * (BN / 2);
+    const bool row_ok = row < p.m_total && row >= p.m_begin;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t raw[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
+      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(t.half * (BN / 2) + c * 32), raw);
+      tmem_ld_wait();
+      const int col0 = col_base + c * 32;
+      const int ncols = p.n_total - col0 < 32 ? p.n_total - col0 : 32;
+      if (!row_ok || ncols <= 0) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (p.mode == kAccumF32 || p.mode == kFinalBf16) {
+        const float* acc = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
+        if (ncols == 32 && (p.ld32 & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 o = *reinterpret_cast<const float4*>(acc + 4 * q);
+            v[4 * q] += o.x; v[4 * q + 1] += o.y; v[4 * q + 2] += o.z; v[4 * q + 3] += o.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] += acc[j];
+        }
+      }
+      if (p.mode == kStoreF32 || p.mode == kAccumF32) {
+        float* dst = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
+        if (ncols == 32 && (p.ld32 & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) dst[j] = v[j];
+        }
+      } else {
+        __nv_bfloat16* dst = p.c16 + (p.row0_16 + row) * p.ld16 + col0;
+        if (ncols == 32 && (p.ld16 & 7) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = v[8 * q + j];
+            Vec8<__nv_bfloat16> pk;
+            pk.pack(t8);
+            *reinterpret_cast<uint4*>(dst + 8 * q) = pk.a;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+  }
+  __device__ void end_unit(const Geom&) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// The persistent warp-specialised GEMM.
+//   A: K-major  -> global [M rows][K] (K contiguous), one 64(k) x 128(m) box per stage
+//      MN-major -> global [K rows][M] (M contiguous), two 64(m) x 64(k) boxes per stage
+//   B: K-major  -> global [N rows][K], one 64 x 256 box;  MN-major -> [K rows][N], four 64 x 64 boxes
+// ---------------------------------------------------------------------------------------------
+template <class Epi, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Geom g,
+               const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + kStages * kABytes;
+  const uint32_t sBar = sB + kStages * kBBytes;
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return sBar + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return sBar + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
+
+  const int warp = threadIdx.x >> 5;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+        int m_blk, range, n_begin, n_end;
+        decode_unit(g, u, m_blk, range, n_begin, n_end);
+        for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+          for (int kb = 0; kb < g.num_k_blk; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t fb = full_bar(stage);
+            mbar_expect_tx(fb, kStageBytes);
+            const uint32_t a_dst = sA + stage * kABytes, b_dst = sB + stage * kBBytes;
+            if (!A_MN) {
+              tma_load_2d(a_dst, &tma_a, g.a_k0 + kb * BK, g.a_m0 + m_blk * BM, fb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(a_dst + j * kBoxMnBytes, &tma_a, g.a_m0 + m_blk * BM + 64 * j, g.a_k0 + kb * BK, fb);
+            }
+            if (!B_MN) {
+              tma_load_2d(b_dst, &tma_b, g.b_k0 + kb * BK, g.b_n0 + n_blk * BN, fb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(b_dst + j * kBoxMnBytes, &tma_b, g.b_n0 + n_blk * BN + 64 * j, g.b_k0 + kb * BK, fb);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint64_t a_base = A_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
+      constexpr uint64_t b_base = B_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
+      constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 elements
+      constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+        int m_blk, range, n_begin, n_end;
+        decode_unit(g, u, m_blk, range, n_begin, n_end);
+        for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < g.num_k_blk; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            fence_after_sync();
+            const uint32_t a_src = sA + stage * kABytes, b_src = sB + stage * kBBytes;
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              mma_bf16(d_tmem, smem_desc(a_base, a_src + k * a_kstep), smem_desc(b_base, b_src + k * b_kstep), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+            }
+            mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    EpiThread et;
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    et.row_in_tile = q * 32 + lane;
+    et.half = (warp - 4) >> 2;
+    et.tmem_lane_off = (uint32_t)(q * 32) << 16;
+    Epi epi(ep, et);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+      int m_blk, range, n_begin, n_end;
+      decode_unit(g, u, m_blk, range, n_begin, n_end);
+      epi.begin_unit(g, m_blk, range);
+      for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        fence_after_sync();
+        epi.tile(g, n_blk, tmem_base + (uint32_t)(acc * BN));
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      epi.end_unit(g);
+    }
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row merge: partial records of every (range, half) -> row_stats + loss sums
+// ---------------------------------------------------------------------------------------------
+struct MergeParams {
+  const float* partials;  // [nrec][R][8]
+  int nrec, R, V;
+  const int32_t* row_target;
+  const void* y;
+  int y_dtype;
+  int64_t y_stride;
+  int dense;
+  float inv_tau;
+  float* row_stats;     // [R][4]
+  float* block_sums;    // [gridDim.x][8]
+};
+
+__global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p) {
+  __shared__ float sm[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ce = 0.f, kl = 0.f, tce = 0.f, nv = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < p.R; row += gridDim.x * 8) {
+    const int target = p.row_target[row];
+    if (target < 0) {
+      if (lane == 0) *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float m = -CUDART_INF_F, s1 = 0.f, st = 0.f, mt = -CUDART_INF_F, t1 = 0.f, tt = 0.f, a = 0.f, zl = 0.f;
+    for (int j = lane; j < p.nrec; j += 32) {
+      const float* rec = p.partials + ((size_t)j * p.R + row) * kRecFloats;
+      const float4 x = *reinterpret_cast<const float4*>(rec);
+      const float4 w = *reinterpret_cast<const float4*>(rec + 4);
+      merge_student(m, s1, st, x.x, x.y, x.z, p.inv_tau);
+      if (p.dense) merge_teacher(mt, t1, tt, a, x.w, w.x, w.y, w.z, p.inv_tau);
+      zl += w.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), a2 = __shfl_xor_sync(0xffffffffu, s1, o),
+                  b2 = __shfl_xor_sync(0xffffffffu, st, o);
+      merge_student(m, s1, st, m2, a2, b2, p.inv_tau);
+      if (p.dense) {
+        const float mt2 = __shfl_xor_sync(0xffffffffu, mt, o), c2 = __shfl_xor_sync(0xffffffffu, t1, o),
+                    d2 = __shfl_xor_sync(0xffffffffu, tt, o), e2 = __shfl_xor_sync(0xffffffffu, a, o);
+        merge_teacher(mt, t1, tt, a, mt2, c2, d2, e2, p.inv_tau);
+      }
+      zl += __shfl_xor_sync(0xffffffffu, zl, o);
+    }
+    if (lane == 0) {
+      const float lse1 = m + ln_acc(s1);
+      const float lset = m * p.inv_tau + ln_acc(st);
+      float lsett = 0.f;
+      ce += lse1 - zl;
+      if (p.dense) {
+        lsett = mt * p.inv_tau + ln_acc(tt);
+        kl += a * p.inv_tau / tt - lsett + lset;
+        float yl;
+        const int64_t off = (int64_t)row * p.y_stride + target;
+        if (p.y_dtype == KD_DTYPE_F32) yl = reinterpret_cast<const float*>(p.y)[off];
+        else if (p.y_dtype == KD_DTYPE_BF16) yl = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.y)[off]);
+        else yl = __half2float(reinterpret_cast<const __half*>(p.y)[off]);
+        tce += (mt + ln_acc(t1)) - yl;
+      }
+      nv += 1.f;
+      *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(lse1, lset, lsett, 1.f);
+    }
+  }
+  if (lane == 0) {
+    sm[warp][0] = ce; sm[warp][1] = kl; sm[warp][2] = tce; sm[warp][3] = nv;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = 0.f;
+    if (threadIdx.x < 4)
+      for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+    p.block_sums[(size_t)blockIdx.x * kNumPartialSlots + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || sym == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// bf16 matrix [outer rows][inner cols] (inner contiguous), box = 64 inner x box_outer rows, 128-byte swizzle
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                     uint32_t box_outer, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * 2) % 16 != 0) {
+    set_error("%s: TMA needs a 16-byte aligned base and a row stride that is a multiple of 8 elements", what);
+    return 1;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu)", what, (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_elems);
+    return 1;
+  }
+  return 0;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <class Epi, bool A_MN, bool B_MN>
+static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const typename Epi::Params& ep,
+                       cudaStream_t stream) {
+  auto kern = kd_umma_kernel<Epi, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes),
+                   "kd_umma smem attribute"))
+      return 1;
+    attr_set = true;
+  }
+  if (g.num_units <= 0 || g.num_k_blk <= 0) {
+    set_error("kd_umma: empty problem (units=%d, k blocks=%d)", g.num_units, g.num_k_blk);
+    return 1;
+  }
+  const int grid = g.num_units < sm_count() ? g.num_units : sm_count();
+  kern<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, g, ep);
+  return check_cuda(cudaGetLastError(), "kd_umma launch");
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- workspace layout -----------------------------------------------------------------------------
+constexpr int kFwdTilesPerRange = 4;
+constexpr int kDefaultVChunk = 9472;  // 37 x 256: dW chunk GEMM = 74 x 4 tiles = 2 full waves of 148 SMs
+constexpr int kMergeBlocksMax = 1024;
+
+static int norm_v_chunk(int v_chunk, int V) {
+  if (v_chunk <= 0) v_chunk = kDefaultVChunk;
+  v_chunk = cdiv(v_chunk, BN) * BN;
+  const int vmax = cdiv(V, BN) * BN;
+  return v_chunk < vmax ? v_chunk : vmax;
+}
+
+struct Workspace {
+  size_t partials_off, partials_bytes;  // forward records
+  size_t bsums_off, bsums_bytes;        // merge block sums (+1 reduced record)
+  size_t g_off, g_bytes;                // backward gradient chunk, bf16 [R][v_chunk]
+  size_t dh_off, dh_bytes;              // backward dH accumulator, fp32 [R][H]
+  size_t total;
+};
+
+static Workspace plan_workspace(int R, int H, int V, int v_chunk) {
+  Workspace w;
+  const int num_ranges = cdiv(cdiv(V, BN), kFwdTilesPerRange);
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  w.partials_off = 0;
+  w.partials_bytes = up((size_t)num_ranges * 2 * R * kRecFloats * sizeof(float));
+  w.bsums_off = w.partials_off + w.partials_bytes;
+  w.bsums_bytes = up((size_t)(kMergeBlocksMax + 1) * kNumPartialSlots * sizeof(float));
+  // the backward reuses the same region from offset 0
+  const int vc = norm_v_chunk(v_chunk, V);
+  w.g_off = 0;
+  w.g_bytes = up((size_t)R * vc * 2);
+  w.dh_off = w.g_off + w.g_bytes;
+  w.dh_bytes = up((size_t)R * H * sizeof(float));
+  const size_t fwd = w.bsums_off + w.bsums_bytes, bwd = w.dh_off + w.dh_bytes;
+  w.total = fwd > bwd ? fwd : bwd;
+  return w;
+}
+
+static int check_common(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int R, int H, int V,
+                        float tau, const char* who) {
+  if (!h || !W || R <= 0 || H <= 0 || V <= 0) {
+    set_error("%s: null pointer or empty shape (R=%d H=%d V=%d)", who, R, H, V);
+    return 1;
+  }
+  if (H % 8 != 0 || h_stride % 8 != 0 || w_stride % 8 != 0) {
+    set_error("%s: hidden size and row strides must be multiples of 8 (TMA 16-byte rule); H=%d", who, H);
+    return 1;
+  }
+  if (!(tau > 0.f)) {
+    set_error("%s: temperature must be > 0", who);
+    return 1;
+  }
+  return 0;
+}
+
+template <bool DENSE, typename TY>
+static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const FwdParams& fp, bool tau2,
+                      cudaStream_t s) {
+  if (tau2) return launch_umma<FwdEpi<TY, DENSE, true>, false, false>(ta, tb, g, fp, s);
+  return launch_umma<FwdEpi<TY, DENSE, false>, false, false>(ta, tb, g, fp, s);
+}
+template <bool DENSE, typename TY>
+static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const GradParams& gp, bool tau2,
+                       cudaStream_t s) {
+  if (tau2) return launch_umma<GradEpi<TY, DENSE, true>, false, false>(ta, tb, g, gp, s);
+  return launch_umma<GradEpi<TY, DENSE, false>, false, false>(ta, tb, g, gp, s);
+}
+
+}  // namespace fused
+}  // namespace kd
+
+using namespace kd;
+using namespace kd::fused;
+
+extern "C" size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk) {
+  if (R <= 0 || H <= 0 || V <= 0) return 0;
+  return plan_workspace(R, H, V, v_chunk).total;
+}
+
+extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
+                                   const void* y, int y_dtype, int64_t y_stride, const float* topk_v,
+                                   const int32_t* topk_i, int K, const int32_t* row_target, int R, int H, int V,
+                                   float tau, float alpha, float* sums, float* row_stats, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  (void)alpha; (void)topk_v; (void)topk_i; (void)K;
+  if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_fwd")) return 1;
+  if (!row_target || !sums || !row_stats || !workspace) {
+    set_error("kd_fused_linear_fwd: null pointer argument");
+    return 1;
+  }
+  if (teacher_kind == KD_TEACHER_SPARSE) {
+    set_error("kd_fused_linear_fwd: sparse teacher is not implemented in the fused path yet; use kd_sparse_fwd_bwd");
+    return 3;
+  }
+  if (teacher_kind == KD_TEACHER_DENSE && (!y || (y_dtype != KD_DTYPE_BF16 && y_dtype != KD_DTYPE_F32))) {
+    set_error("kd_fused_linear_fwd: dense teacher must be bf16 or fp32");
+    return 1;
+  }
+  const Workspace ws = plan_workspace(R, H, V, 0);
+  if (workspace_bytes < ws.bsums_off + ws.bsums_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("kd_fused_linear_fwd: workspace too small or not 256-byte aligned (need %zu)", ws.total);
+    return 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
+  float* partials = reinterpret_cast<float*>(wsp + ws.partials_off);
+  float* bsums = reinterpret_cast<float*>(wsp + ws.bsums_off);
+
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
+  if (make_tmap(&tb, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, BN, "lm_head weight")) return 1;
+  Geom g = {};
+  g.num_m_blk = cdiv(R, BM);
+  g.num_n_blk = cdiv(V, BN);
+  g.num_k_blk = cdiv(H, BK);
+  g.n_per_unit = kFwdTilesPerRange;
+  const int num_ranges = cdiv(g.num_n_blk, g.n_per_unit);
+  g.num_units = g.num_m_blk * num_ranges;
+
+  FwdParams fp = {};
+  fp.row_target = row_target;
+  fp.y = y;
+  fp.y_stride = y_stride;
+  const size_t ys = y_dtype == KD_DTYPE_F32 ? 4 : 2;
+  fp.y_vec_ok = (y && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (y_stride * ys) % 16 == 0) ? 1 : 0;
+  fp.R = R;
+  fp.V = V;
+  fp.inv_tau = 1.0f / tau;
+  fp.partials = partials;
+  const bool tau2 = tau == 2.0f;
+  int rc;
+  if (teacher_kind == KD_TEACHER_DENSE) {
+    rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, g, fp, tau2, s)
+                                  : launch_fwd<true, float>(ta, tb, g, fp, tau2, s);
+  } else {
+    rc = launch_fwd<false, __nv_bfloat16>(ta, tb, g, fp, tau2, s);
+  }
+  if (rc) return rc;
+
+  MergeParams mp = {};
+  mp.partials = partials;
+  mp.nrec = num_ranges * 2;
+  mp.R = R;
+  mp.V = V;
+  mp.row_target = row_target;
+  mp.y = y;
+  mp.y_dtype = y_dtype;
+  mp.y_stride = y_stride;
+  mp.dense = teacher_kind == KD_TEACHER_DENSE ? 1 : 0;
+  mp.inv_tau = 1.0f / tau;
+  mp.row_stats = row_stats;
+  mp.block_sums = bsums;
+  int blocks = cdiv(R, 8);
+  if (blocks > kMergeBlocksMax) blocks = kMergeBlocksMax;
+  kd_fused_merge_kernel<<<blocks, 256, 0, s>>>(mp);
+  if (check_cuda(cudaGetLastError(), "kd_fused_merge launch")) return 1;
+  return reduce_partials(bsums, blocks, sums, s);
+}
+
+extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
+                                   const void* y, int y_dtype, int64_t y_stride, const float* topk_v,
+                                   const int32_t* topk_i, int K, const int32_t* row_target, const float* row_stats,
+                                   int R, int H, int V, float tau, const int32_t* n_norm,
+                                   const float* grad_coef, void* dH, int64_t dh_stride, void* dW, int64_t dw_stride,
+                                   int64_t dw_row_begin, int v_chunk, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  (void)topk_v; (void)topk_i; (void)K;
+  if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_bwd")) return 1;
+  if (!row_target || !row_stats || !n_norm || !grad_coef || !workspace || (!dH && !dW)) {
+    set_error("kd_fused_linear_bwd: null pointer argument");
+    return 1;
+  }
+  if (teacher_kind == KD_TEACHER_SPARSE) {
+    set_error("kd_fused_linear_bwd: sparse teacher is not implemented in the fused path yet; use kd_sparse_fwd_bwd");
+    return 3;
+  }
+  if (teacher_kind == KD_TEACHER_DENSE && (!y || (y_dtype != KD_DTYPE_BF16 && y_dtype != KD_DTYPE_F32))) {
+    set_error("kd_fused_linear_bwd: dense teacher must be bf16 or fp32");
+    return 1;
+  }
+  const int vc = norm_v_chunk(v_chunk, V);
+  const Workspace ws = plan_workspace(R, H, V, vc);
+  if (workspace_bytes < ws.dh_off + ws.dh_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("kd_fused_linear_bwd: workspace too small or not 256-byte aligned (need %zu)", ws.total);
+    return 1;
+  }
+  if (dH && dh_stride % 8 != 0) {
+    set_error("kd_fused_linear_bwd: dH row stride must be a multiple of 8");
+    return 1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(wsp + ws.g_off);
+  float* dh32 = reinterpret_cast<float*>(wsp + ws.dh_off);
+  const bool tau2 = tau == 2.0f;
+  const size_t ys = y_dtype == KD_DTYPE_F32 ? 4 : 2;
+  const int n_chunks = cdiv(V, vc);
+
+  CUtensorMap t_h_k, t_w_k, t_g_k, t_g_mn, t_h_mn, t_w_mn;
+  if (make_tmap(&t_h_k, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
+  if (make_tmap(&t_w_k, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, BN, "lm_head weight")) return 1;
+  if (make_tmap(&t_g_k, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)")) return 1;
+  if (make_tmap(&t_g_mn, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, 64, "G (MN-major)")) return 1;
+  if (make_tmap(&t_h_mn, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, 64, "hidden (MN-major)")) return 1;
+  if (make_tmap(&t_w_mn, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, 64, "lm_head weight (MN-major)")) return 1;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    const int v0 = c * vc;
+    const int cols = V - v0 < vc ? V - v0 : vc;
+    const int n_blks = cdiv(cols, BN);  // 256-wide column blocks of this chunk (G is zero-padded to the block)
+    const bool need_dw = dW != nullptr && (int64_t)(v0 + cols) > dw_row_begin;
+    // ---- 1. recompute logits tile, form G ----
+    {
+      Geom g = {};
+      g.num_m_blk = cdiv(R, BM);
+      g.num_n_blk = n_blks;
+      g.num_k_blk = cdiv(H, BK);
+      g.b_n0 = v0;
+      g.n_per_unit = 1;
+      g.num_units = g.num_m_blk * g.num_n_blk;
+      GradParams gp = {};
+      gp.row_target = row_target;
+      gp.row_stats = row_stats;
+      gp.y = y;
+      gp.y_stride = y_stride;
+      gp.y_vec_ok = (y && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (y_stride * ys) % 16 == 0) ? 1 : 0;
+      gp.R = R;
+      gp.V = V;
+      gp.tau = tau;
+      gp.use_kl = teacher_kind == KD_TEACHER_NONE ? 0 : 1;
+      gp.n_norm = n_norm;
+      gp.coef = grad_coef;
+      gp.G = G;
+      gp.ldg = vc;
+      gp.v0 = v0;
+      int rc;
+      if (teacher_kind == KD_TEACHER_DENSE) {
+        rc = y_dtype == KD_DTYPE_BF16 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, s)
+                                      : launch_grad<true, float>(t_h_k, t_w_k, g, gp, tau2, s);
+      } else {
+        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, s);
+      }
+      if (rc) return rc;
+    }
+    // ---- 2. dW[v0 : v0+cols, :] = G^T h   (rows are final: every token is in this GEMM's K) ----
+    if (need_dw) {
+      Geom g = {};
+      g.num_m_blk = cdiv(n_blks * BN, BM);
+      g.num_n_blk = cdiv(H, BN);
+      g.num_k_blk = cdiv(R, BK);
+      g.n_per_unit = 1;
+      g.num_units = g.num_m_blk * g.num_n_blk;
+      StoreParams sp = {};
+      sp.mode = kStoreBf16;
+      sp.m_total = cols;
+      sp.n_total = H;
+      const int64_t mb = dw_row_begin - v0;
+      sp.m_begin = mb > 0 ? (int)mb : 0;
+      sp.c16 = reinterpret_cast<__nv_bfloat16*>(dW);
+      sp.ld16 = dw_stride;
+      sp.row0_16 = v0;
+      if (launch_umma<StoreEpi, true, true>(t_g_mn, t_h_mn, g, sp, s)) return 1;
+    }
+    // ---- 3. dH (+)= G W[v0 : v0+cols, :] ----
+    if (dH) {
+      Geom g = {};
+      g.num_m_blk = cdiv(R, BM);
+      g.num_n_blk = cdiv(H, BN);
+      g.num_k_blk = n_blks * (BN / BK);
+      g.b_k0 = v0;
+      g.n_per_unit = 1;
+      g.num_units = g.num_m_blk * g.num_n_blk;
+      StoreParams sp = {};
+      const bool first = c == 0, last = c == n_chunks - 1;
+      sp.mode = first && last ? kStoreBf16 : (first ? kStoreF32 : (last ? kFinalBf16 : kAccumF32));
+      sp.m_total = R;
+      sp.n_total = H;
+      sp.m_begin = 0;
+      sp.c32 = dh32;
+      sp.ld32 = H;
+      sp.c16 = reinterpret_cast<__nv_bfloat16*>(dH);
+      sp.ld16 = dh_stride;
+      if (launch_umma<StoreEpi, false, true>(t_g_k, t_w_mn, g, sp, s)) return 1;
+    }
+  }
+  return 0;
+}
+
+extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                            float* C, int64_t ldc, int M, int N, int K, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) {
+    set_error("kd_gemm_bf16: bad arguments");
+    return 1;
+  }
+  CUtensorMap ta, tb;
+  if (a_mn_major) {
+    if (make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, "A (MN-major)")) return 1;
+  } else {
+    if (make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM, "A (K-major)")) return 1;
+  }
+  if (b_mn_major) {
+    if (make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, "B (MN-major)")) return 1;
+  } else {
+    if (make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BN, "B (K-major)")) return 1;
+  }
+  Geom g = {};
+  g.num_m_blk = cdiv(M, BM);
+  g.num_n_blk = cdiv(N, BN);
+  g.num_k_blk = cdiv(K, BK);
+  g.n_per_unit = 1;
+  g.num_units = g.num_m_blk * g.num_n_blk;
+  StoreParams sp = {};
+  sp.mode = kStoreF32;
+  sp.m_total = M;
+  sp.n_total = N;
+  sp.c32 = C;
+  sp.ld32 = ldc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a_mn_major && b_mn_major) return launch_umma<StoreEpi, true, true>(ta, tb, g, sp, s);
+  if (!a_mn_major && b_mn_major) return launch_umma<StoreEpi, false, true>(ta, tb, g, sp, s);
+  if (!a_mn_major && !b_mn_major) return launch_umma<StoreEpi, false, false>(ta, tb, g, sp, s);
+  set_error("kd_gemm_bf16: the (A MN-major, B K-major) combination is not instantiated");
+  return 1;
+}

@@ -1,0 +1,693 @@
+// K2: streaming KD loss + gradient on materialised logits (HBM-bound).
+//
+// Replaces distillation_loss.py:31-128 and its autograd.  One thread-block CLUSTER owns one
+// row (b,t) at a time; each CTA of the cluster streams its slice of the vocabulary from HBM
+// exactly once (16 B loads, L1 bypass), keeps the raw bytes in shared memory, accumulates
+// online soft-max statistics, exchanges the 7 per-row statistics over DSMEM, and then forms
+// the gradient from the shared-memory copy and streams it out.  HBM traffic = read z + read y
+// + write dz (6 B / element for bf16), the algorithmic minimum of SURVEY.md 8(d).
+//
+// Per valid row (appendix C of SURVEY.md), all fp32:
+//   student: m, S1 = sum e^{z-m}, St = sum e^{(z-m)/tau}
+//   teacher: mt, T1 = sum e^{y-mt}, Tt = sum e^{(y-mt)/tau}, A = sum e^{(y-mt)/tau} (y - z)
+//   CE = LSE1 - z_l ; KL = A/(tau Tt) - LSEt_tau + LSE_tau ; teacherCE = LSEt1 - y_l
+//   G  = c1 (e^{z-LSE1} - [v=l]) + c2 (e^{z/tau-LSE_tau} - P),  c1 = alpha g/N, c2 = (1-alpha) tau g/N
+#include <cooperative_groups.h>
+
+#include "kd_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace kd {
+
+constexpr int kStreamThreads = 512;
+constexpr int kMaxTopK = 1024;
+
+struct StreamParams {
+  const void* z;
+  const void* y;
+  int64_t z_sb, z_st, y_sb, y_st;  // strides in elements
+  const float* topk_v;
+  const int32_t* topk_i;
+  int K;
+  const int32_t* row_target;
+  int B, T, V;
+  float tau, alpha, grad_scale;
+  const int32_t* n_norm;
+  void* dlogits;
+  float* partials;  // [n_clusters][kNumPartialSlots]
+  int stash_elems;  // per CTA, multiple of 8
+  int slice_elems;  // per CTA, multiple of 8
+  int vec_ok;       // 16-byte vector path legal for every row pointer
+};
+
+struct Stats7 {
+  float m, s1, st;       // student
+  float mt, t1, tt, a;   // teacher (dense only)
+};
+
+template <bool DENSE>
+__device__ __forceinline__ Stats7 warp_merge(Stats7 s, float inv_tau) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, s.m, o);
+    const float a2 = __shfl_xor_sync(0xffffffffu, s.s1, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, s.st, o);
+    merge_student(s.m, s.s1, s.st, m2, a2, b2, inv_tau);
+    if (DENSE) {
+      const float mt2 = __shfl_xor_sync(0xffffffffu, s.mt, o);
+      const float t12 = __shfl_xor_sync(0xffffffffu, s.t1, o);
+      const float tt2 = __shfl_xor_sync(0xffffffffu, s.tt, o);
+      const float aa2 = __shfl_xor_sync(0xffffffffu, s.a, o);
+      merge_teacher(s.mt, s.t1, s.tt, s.a, mt2, t12, tt2, aa2, inv_tau);
+    }
+  }
+  return s;
+}
+
+// Shared-memory control block (static part)
+struct StreamShared {
+  Stats7 warp_stats[kStreamThreads / 32];
+  Stats7 cta_stats[2];  // double-buffered by row parity, read by peers over DSMEM
+  float row_consts[8];
+};
+
+template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
+__global__ void __launch_bounds__(kStreamThreads) kd_stream_kernel(const StreamParams p) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ StreamShared sh;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  const int cluster_id = blockIdx.x / csize;
+  const int n_clusters = gridDim.x / csize;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  TZ* stash_z = reinterpret_cast<TZ*>(dyn_smem);
+  TY* stash_y = reinterpret_cast<TY*>(dyn_smem + (size_t)p.stash_elems * sizeof(TZ));
+  // sparse scratch lives after the stash(es)
+  float* sp_p = reinterpret_cast<float*>(dyn_smem + (size_t)p.stash_elems * (sizeof(TZ) + (DENSE ? sizeof(TY) : 0)));
+  int32_t* sp_i = reinterpret_cast<int32_t*>(sp_p + (DENSE ? 0 : p.K));
+
+  const float inv_tau = 1.0f / p.tau;
+  const int V = p.V;
+  const int lo = min(V, crank * p.slice_elems);
+  const int hi = min(V, lo + p.slice_elems);
+  const int stash_hi = min(hi, lo + p.stash_elems);
+  const bool vec_ok = p.vec_ok != 0;
+  // vector body [lo, vhi), scalar tail [vhi, hi); without alignment everything is tail
+  const int vhi = vec_ok ? lo + ((hi - lo) & ~7) : lo;
+
+  const int n_rows = p.B * p.T;
+  float norm = 0.f;
+  if (GRAD) {
+    const int nn = *p.n_norm;
+    norm = nn > 0 ? p.grad_scale / (float)nn : 0.f;
+  }
+  const float c1 = p.alpha * norm;
+  const float c2 = (1.f - p.alpha) * p.tau * norm;
+
+  double acc_ce = 0.0, acc_kl = 0.0, acc_t = 0.0;
+  int acc_n = 0, acc_hits = 0;
+  int parity = 0;
+
+  for (int row = cluster_id; row < n_rows; row += n_clusters) {
+    const int b = row / p.T, t = row - b * p.T;
+    const int target = p.row_target[row];
+    TZ* out_row = GRAD ? reinterpret_cast<TZ*>(p.dlogits) + (size_t)row * V : nullptr;
+
+    if (target < 0) {  // invalid row: zero gradient, nothing to read (uniform across the cluster)
+      if (GRAD) {
+        if (vec_ok) {
+          const uint4 zero4 = make_uint4(0, 0, 0, 0);
+          constexpr int kPer16 = 16 / sizeof(TZ);
+          for (int i = lo + tid * kPer16; i + kPer16 <= hi; i += kStreamThreads * kPer16) stg_stream(out_row + i, zero4);
+          const int done = lo + ((hi - lo) / kPer16) * kPer16;
+          for (int i = done + tid; i < hi; i += kStreamThreads) out_row[i] = Elem<TZ>::from_f(0.f);
+        } else {
+          for (int i = lo + tid; i < hi; i += kStreamThreads) out_row[i] = Elem<TZ>::from_f(0.f);
+        }
+      }
+      continue;
+    }
+
+    const TZ* zrow = reinterpret_cast<const TZ*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
+    const TY* yrow = DENSE ? reinterpret_cast<const TY*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st : nullptr;
+
+    // ---------------- sweep 1: HBM -> registers -> smem stash, online statistics -------------
+    Stats7 s;
+    s.m = s.mt = -CUDART_INF_F;
+    s.s1 = s.st = s.t1 = s.tt = s.a = 0.f;
+    for (int i = lo + tid * 8; i < vhi; i += kStreamThreads * 8) {
+      Vec8<TZ> vz;
+      vz.load_global(zrow + i);
+      Vec8<TY> vy;
+      if (DENSE) vy.load_global(yrow + i);
+      if (i + 8 <= stash_hi) {
+        vz.store_shared(stash_z + (i - lo));
+        if (DENSE) vy.store_shared(stash_y + (i - lo));
+      }
+      float fz[8], fy[8];
+      vz.unpack(fz);
+      student_update<TAU2, 8>(fz, 8, inv_tau, s.m, s.s1, s.st);
+      if (DENSE) {
+        vy.unpack(fy);
+        teacher_update<TAU2, 8>(fy, fz, 8, inv_tau, s.mt, s.t1, s.tt, s.a);
+      }
+    }
+    for (int i = vhi + tid; i < hi; i += kStreamThreads) {  // scalar tail / unaligned path
+      float fz[8], fy[8];
+      const TZ zr = zrow[i];
+      fz[0] = Elem<TZ>::to_f(zr);
+      if (i < stash_hi) stash_z[i - lo] = zr;
+      student_update<TAU2, 8>(fz, 1, inv_tau, s.m, s.s1, s.st);
+      if (DENSE) {
+        const TY yr = yrow[i];
+        fy[0] = Elem<TY>::to_f(yr);
+        if (i < stash_hi) stash_y[i - lo] = yr;
+        teacher_update<TAU2, 8>(fy, fz, 1, inv_tau, s.mt, s.t1, s.tt, s.a);
+      }
+    }
+
+    // ---------------- block + cluster reduction of the statistics ----------------------------
+    s = warp_merge<DENSE>(s, inv_tau);
+    if (lane == 0) sh.warp_stats[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      Stats7 w;
+      if (lane < kStreamThreads / 32) {
+        w = sh.warp_stats[lane];
+      } else {
+        w.m = w.mt = -CUDART_INF_F;
+        w.s1 = w.st = w.t1 = w.tt = w.a = 0.f;
+      }
+      w = warp_merge<DENSE>(w, inv_tau);
+      if (lane == 0) sh.cta_stats[parity] = w;
+    }
+
+    // sparse teacher: every CTA needs p_k for its own fix-ups
+    float sp_lk = 0.f;
+    if (!DENSE) {
+      const float* vrow = p.topk_v + (size_t)row * p.K;
+      const int32_t* irow = p.topk_i + (size_t)row * p.K;
+      if (warp == 1) {
+        float vm = -CUDART_INF_F;
+        for (int k = lane; k < p.K; k += 32) vm = fmaxf(vm, vrow[k]);
+        vm = warp_max(vm);
+        float sum = 0.f;
+        for (int k = lane; k < p.K; k += 32) sum += ex2((vrow[k] - vm) * kLog2e * inv_tau);
+        sum = warp_sum(sum);
+        sp_lk = vm * inv_tau + ln_acc(sum);
+        for (int k = lane; k < p.K; k += 32) {
+          sp_p[k] = __expf(vrow[k] * inv_tau - sp_lk);
+          sp_i[k] = irow[k];
+        }
+        if (lane == 0) sh.row_consts[7] = sp_lk;
+      }
+    }
+    cluster.sync();  // cta_stats[parity] of every CTA is visible cluster-wide (also a CTA barrier)
+
+    Stats7 f = sh.cta_stats[parity];
+    if (csize > 1) {
+      f.m = f.mt = -CUDART_INF_F;
+      f.s1 = f.st = f.t1 = f.tt = f.a = 0.f;
+      for (int r = 0; r < csize; ++r) {
+        const Stats7* peer = cluster.map_shared_rank(&sh.cta_stats[parity], r);
+        const Stats7 o = *peer;
+        merge_student(f.m, f.s1, f.st, o.m, o.s1, o.st, inv_tau);
+        if (DENSE) merge_teacher(f.mt, f.t1, f.tt, f.a, o.mt, o.t1, o.tt, o.a, inv_tau);
+      }
+    }
+    parity ^= 1;
+
+    const float lse1 = f.m + ln_acc(f.s1);
+    const float lset = f.m * inv_tau + ln_acc(f.st);
+    float lsett = 0.f;
+    if (DENSE) lsett = f.mt * inv_tau + ln_acc(f.tt);
+    if (!DENSE) sp_lk = sh.row_consts[7];
+
+    // ---------------- per-row scalars (rank 0 only) -------------------------------------------
+    if (crank == 0) {
+      if (DENSE) {
+        if (tid == 0) {
+          const float zl = Elem<TZ>::to_f(zrow[target]);
+          const float yl = Elem<TY>::to_f(yrow[target]);
+          acc_ce += (double)(lse1 - zl);
+          acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
+          acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
+          acc_n += 1;
+        }
+      } else if (warp == 0) {
+        // KL_r = sum_k p_k (log p_k - z_{i_k}/tau) + LSE_tau ; monitor hits (distillation_loss.py:104-116)
+        const float* vrow = p.topk_v + (size_t)row * p.K;
+        float part = 0.f, hsum = 0.f;
+        int hits = 0;
+        for (int k = lane; k < p.K; k += 32) {
+          const int idx = sp_i[k];
+          const float pk = sp_p[k];
+          const float vk = vrow[k];
+          if (idx >= 0 && idx < V) {
+            const float zk = Elem<TZ>::to_f(zrow[idx]);
+            part += pk * ((vk * inv_tau - sp_lk) - zk * inv_tau);
+          }
+          if (idx == target) {
+            hits += 1;
+            hsum += vk;
+          }
+        }
+        part = warp_sum(part);
+        hsum = warp_sum(hsum);
+        hits = __reduce_add_sync(0xffffffffu, hits);
+        if (lane == 0) {
+          const float zl = Elem<TZ>::to_f(zrow[target]);
+          acc_ce += (double)(lse1 - zl);
+          acc_kl += (double)(part + lset);
+          acc_t += (double)hsum;
+          acc_hits += hits;
+          acc_n += 1;
+        }
+      }
+    }
+
+    // ---------------- sweep 2: gradient from the stash, streamed out ---------------------------
+    if (GRAD) {
+      // e^{z-LSE1} = E^2 (tau=2) with E = e^{(z-LSE1)/2};  e^{z/2-LSE_tau} = E * e^{LSE1/2-LSE_tau}
+      const float c_tau = kLog2e * inv_tau;
+      const float off1 = lse1 * kLog2e;            // e^{z-LSE1}
+      const float offt = lset * kLog2e;            // e^{z/tau-LSE_tau}
+      const float offy = lsett * kLog2e;           // e^{y/tau-LSEt_tau}
+      const float half_off1 = off1 * 0.5f;
+      const float k_tau = c2 * ex2(half_off1 - offt);  // tau=2 only
+      auto grad8 = [&](const float(&fz)[8], const float(&fy)[8], int base, int nvalid, float(&g)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < nvalid) {
+            float gi;
+            if (TAU2) {
+              const float e = ex2(fmaf(fz[i], c_tau, -half_off1));
+              gi = e * fmaf(e, c1, k_tau);
+            } else {
+              gi = c1 * ex2(fmaf(fz[i], kLog2e, -off1)) + c2 * ex2(fmaf(fz[i], c_tau, -offt));
+            }
+            if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
+            g[i] = gi;
+          }
+        }
+        const unsigned d = (unsigned)(target - base);
+        if (d < (unsigned)nvalid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((int)d == i) g[i] -= c1;
+        }
+      };
+      for (int i = lo + tid * 8; i < vhi; i += kStreamThreads * 8) {
+        Vec8<TZ> vz;
+        Vec8<TY> vy;
+        if (i + 8 <= stash_hi) {
+          vz.load_shared(stash_z + (i - lo));
+          if (DENSE) vy.load_shared(stash_y + (i - lo));
+        } else {  // beyond the stash: second read comes from L2
+          vz.load_global(zrow + i);
+          if (DENSE) vy.load_global(yrow + i);
+        }
+        float fz[8], fy[8], g[8];
+        vz.unpack(fz);
+        if (DENSE) vy.unpack(fy);
+        grad8(fz, fy, i, 8, g);
+        Vec8<TZ> vo;
+        vo.pack(g);
+        vo.store_global(out_row + i);
+      }
+      for (int i = vhi + tid; i < hi; i += kStreamThreads) {
+        float fz[8], fy[8], g[8];
+        fz[0] = Elem<TZ>::to_f(i < stash_hi ? stash_z[i - lo] : zrow[i]);
+        if (DENSE) fy[0] = Elem<TY>::to_f(i < stash_hi ? stash_y[i - lo] : yrow[i]);
+        grad8(fz, fy, i, 1, g);
+        out_row[i] = Elem<TZ>::from_f(g[0]);
+      }
+      if (!DENSE) {
+        // scatter part of the sparse gradient: G[i_k] -= c2 * (sum of p_j with i_j == i_k), exact in
+        // fp32 and written once by the CTA that owns the column (after its own sweep-2 stores)
+        __syncthreads();
+        for (int k = tid; k < p.K; k += kStreamThreads) {
+          const int idx = sp_i[k];
+          if (idx < lo || idx >= hi) continue;
+          float ptot = 0.f;
+          bool first = true;
+          for (int j = 0; j < p.K; ++j) {
+            if (sp_i[j] == idx) {
+              ptot += sp_p[j];
+              if (j < k) first = false;
+            }
+          }
+          if (!first) continue;
+          const float zk = Elem<TZ>::to_f(idx < stash_hi ? stash_z[idx - lo] : zrow[idx]);
+          float gi = c1 * ex2(fmaf(zk, kLog2e, -off1)) + c2 * (ex2(fmaf(zk, c_tau, -offt)) - ptot);
+          if (idx == target) gi -= c1;
+          out_row[idx] = Elem<TZ>::from_f(gi);
+        }
+      }
+    }
+    // the stash and sp_* are rewritten by the next row's sweep 1 only after this barrier
+    __syncthreads();
+  }
+
+  // peers may still be reading cta_stats over DSMEM: do not exit before everyone is done
+  cluster.sync();
+  if (crank == 0 && tid == 0) {
+    float* out = p.partials + (size_t)cluster_id * kNumPartialSlots;
+    out[0] = (float)acc_ce;
+    out[1] = (float)acc_kl;
+    out[2] = (float)acc_t;
+    out[3] = (float)acc_n;
+    out[4] = (float)acc_hits;
+    out[5] = out[6] = out[7] = 0.f;
+  }
+}
+
+// deterministic fixed-order reduction of the per-cluster partial records -> sums[8]
+__global__ void kd_reduce_partials_kernel(const float* __restrict__ partials, int n, float* __restrict__ sums) {
+  __shared__ double sm[kNumPartialSlots][33];
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;  // 8 warps, one per slot
+  double acc = 0.0;
+  for (int i = lane; i < n; i += 32) acc += (double)partials[(size_t)i * kNumPartialSlots + slot];
+  sm[slot][lane] = acc;
+  __syncwarp();
+  if (lane == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += sm[slot][i];
+    sums[slot] = (float)t;
+  }
+}
+
+int reduce_partials(const float* partials, int n, float* sums, cudaStream_t stream) {
+  kd_reduce_partials_kernel<<<1, 32 * kNumPartialSlots, 0, stream>>>(partials, n, sums);
+  return check_cuda(cudaGetLastError(), "kd_reduce_partials launch");
+}
+
+__global__ void kd_prepare_rows_kernel(const int64_t* __restrict__ labels, const uint8_t* __restrict__ mask, int B,
+                                       int T, int64_t ignore_index, int32_t* __restrict__ row_target,
+                                       int32_t* __restrict__ n_valid) {
+  __shared__ int warp_counts[32];
+  int cnt = 0;
+  const int n = B * T;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int b = r / T, t = r - b * T;
+    int64_t l = 0;
+    const bool ok = row_is_valid(labels, mask, T, b, t, ignore_index, &l);
+    if (row_target) row_target[r] = ok ? (int32_t)l : -1;
+    cnt += ok ? 1 : 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += warp_counts[i];
+    *n_valid = t;
+  }
+}
+
+__global__ void kd_finalize_kernel(const float* __restrict__ sums, float tau, float alpha, int sparse,
+                                   float* __restrict__ losses) {
+  const float n = sums[3];
+  if (n <= 0.f) {  // distillation_loss.py:47-53
+    losses[0] = losses[1] = losses[2] = losses[3] = 0.f;
+    return;
+  }
+  const float task = sums[0] / n;
+  const float distill = tau * tau * sums[1] / n;
+  float teacher;
+  if (sparse) {
+    teacher = sums[4] > 0.f ? -sums[2] / sums[4] : 0.f;  // :113-118
+  } else {
+    teacher = sums[2] / n;
+  }
+  losses[0] = alpha * task + (1.f - alpha) * distill;
+  losses[1] = task;
+  losses[2] = distill;
+  losses[3] = teacher;
+}
+
+template <typename T>
+__global__ void kd_scale_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ scale) {
+  const float s = *scale;
+  if (s == 1.0f) return;
+  const int64_t n8 = n / 8;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (aligned) {
+    for (int64_t i = gid; i < n8; i += stride) {
+      Vec8<T> v;
+      v.load_global(x + i * 8);
+      float f[8];
+      v.unpack(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= s;
+      v.pack(f);
+      v.store_global(x + i * 8);
+    }
+    for (int64_t i = n8 * 8 + gid; i < n; i += stride) x[i] = Elem<T>::from_f(Elem<T>::to_f(x[i]) * s);
+  } else {
+    for (int64_t i = gid; i < n; i += stride) x[i] = Elem<T>::from_f(Elem<T>::to_f(x[i]) * s);
+  }
+}
+
+template <typename T>
+__global__ void kd_zero_rows_kernel(T* __restrict__ x, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = Elem<T>::from_f(0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxClusters = 1024;
+
+template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
+static int launch_stream(const StreamParams& p0, cudaStream_t stream) {
+  StreamParams p = p0;
+  auto kern = kd_stream_kernel<TZ, TY, DENSE, TAU2, GRAD>;
+  int dev = 0, sms = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+
+  const size_t bytes_per_elem = sizeof(TZ) + (DENSE ? sizeof(TY) : 0);
+  const size_t sparse_bytes = DENSE ? 0 : (size_t)p.K * 8 + 16;
+  const size_t static_bytes = sizeof(StreamShared) + 64;
+  // Cluster size: smallest power of two <= 8 whose per-CTA slice fits in half an SM's shared
+  // memory (two CTAs per SM overlap one CTA's reduction bubbles with the other's streaming);
+  // else 8 with as much stash as fits, the rest of the slice is re-read through L2.
+  const size_t half_sm = (size_t)(max_optin - 2048) / 2 - static_bytes - sparse_bytes;
+  const size_t full_sm = (size_t)max_optin - static_bytes - sparse_bytes - 1024;
+  int csize = 8;
+  const int v8 = (p.V + 7) / 8;
+  for (int c = 1; c <= 8; c *= 2) {
+    const size_t slice = (size_t)((v8 + c - 1) / c) * 8;
+    if (slice * bytes_per_elem <= half_sm) {
+      csize = c;
+      break;
+    }
+  }
+  p.slice_elems = ((v8 + csize - 1) / csize) * 8;
+  size_t stash = (size_t)p.slice_elems;
+  if (stash * bytes_per_elem > half_sm) {
+    // does it fit with one CTA per SM?
+    if (stash * bytes_per_elem > full_sm) stash = (full_sm / bytes_per_elem) & ~(size_t)7;
+  }
+  p.stash_elems = (int)stash;
+  const size_t dyn = stash * bytes_per_elem + sparse_bytes;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "smem attr"))
+    return 1;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3(csize);
+  int max_clusters = 0;
+  if (check_cuda(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg), "cluster occupancy")) return 1;
+  if (max_clusters < 1) {
+    set_error("kd_stream: no cluster of %d CTAs with %zu B shared memory fits on this device", csize, dyn);
+    return 1;
+  }
+  const int n_rows = p.B * p.T;
+  int n_clusters = max_clusters < n_rows ? max_clusters : n_rows;
+  if (n_clusters > kMaxClusters) n_clusters = kMaxClusters;
+  cfg.gridDim = dim3(n_clusters * csize);
+  if (check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "kd_stream launch")) return 1;
+  return reduce_partials(p.partials, n_clusters, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
+}
+
+template <typename TZ, typename TY, bool DENSE>
+static int dispatch_flags(const StreamParams& p, cudaStream_t s) {
+  const bool tau2 = p.tau == 2.0f;
+  const bool grad = p.dlogits != nullptr;
+  if (tau2) return grad ? launch_stream<TZ, TY, DENSE, true, true>(p, s) : launch_stream<TZ, TY, DENSE, true, false>(p, s);
+  return grad ? launch_stream<TZ, TY, DENSE, false, true>(p, s) : launch_stream<TZ, TY, DENSE, false, false>(p, s);
+}
+
+template <typename TZ>
+static int dispatch_y(const StreamParams& p, int y_dtype, cudaStream_t s) {
+  switch (y_dtype) {
+    case KD_DTYPE_F32: return dispatch_flags<TZ, float, true>(p, s);
+    case KD_DTYPE_BF16: return dispatch_flags<TZ, __nv_bfloat16, true>(p, s);
+    case KD_DTYPE_F16: return dispatch_flags<TZ, __half, true>(p, s);
+  }
+  set_error("kd_dense_fwd_bwd: unsupported teacher dtype code %d", y_dtype);
+  return 1;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static size_t dtype_size(int code) { return code == KD_DTYPE_F32 ? 4 : 2; }
+
+static int stream_common(StreamParams& p, int z_dtype, int y_dtype, bool dense, float* sums, void* workspace,
+                         size_t workspace_bytes, cudaStream_t s) {
+  if (p.B <= 0 || p.T <= 0 || p.V <= 0) {
+    set_error("kd_stream: empty shape B=%d T=%d V=%d", p.B, p.T, p.V);
+    return 1;
+  }
+  if (!(p.tau > 0.f)) {
+    set_error("kd_stream: temperature must be > 0");
+    return 1;
+  }
+  if (workspace == nullptr || workspace_bytes < kd_stream_workspace_bytes() || !aligned16(workspace)) {
+    set_error("kd_stream: workspace must be 16-byte aligned and >= %zu bytes", kd_stream_workspace_bytes());
+    return 1;
+  }
+  p.partials = reinterpret_cast<float*>(workspace);
+  const size_t zs = dtype_size(z_dtype), ys = dtype_size(y_dtype);
+  bool ok = aligned16(p.z) && (p.z_sb * zs) % 16 == 0 && (p.z_st * zs) % 16 == 0;
+  if (dense) ok = ok && aligned16(p.y) && (p.y_sb * ys) % 16 == 0 && (p.y_st * ys) % 16 == 0;
+  if (p.dlogits) ok = ok && aligned16(p.dlogits) && ((size_t)p.V * zs) % 16 == 0;
+  p.vec_ok = ok ? 1 : 0;
+  int rc;
+  if (dense) {
+    switch (z_dtype) {
+      case KD_DTYPE_F32: rc = dispatch_y<float>(p, y_dtype, s); break;
+      case KD_DTYPE_BF16: rc = dispatch_y<__nv_bfloat16>(p, y_dtype, s); break;
+      case KD_DTYPE_F16: rc = dispatch_y<__half>(p, y_dtype, s); break;
+      default: set_error("kd_stream: unsupported student dtype code %d", z_dtype); return 1;
+    }
+  } else {
+    switch (z_dtype) {
+      case KD_DTYPE_F32: rc = dispatch_flags<float, float, false>(p, s); break;
+      case KD_DTYPE_BF16: rc = dispatch_flags<__nv_bfloat16, __nv_bfloat16, false>(p, s); break;
+      case KD_DTYPE_F16: rc = dispatch_flags<__half, __half, false>(p, s); break;
+      default: set_error("kd_stream: unsupported student dtype code %d", z_dtype); return 1;
+    }
+  }
+  if (rc) return rc;
+  // reduced record sits right after the per-cluster partials; copy it out
+  return check_cuda(cudaMemcpyAsync(sums, p.partials + (size_t)kMaxClusters * kNumPartialSlots,
+                                    kNumPartialSlots * sizeof(float), cudaMemcpyDeviceToDevice, s),
+                    "sums copy");
+}
+
+}  // namespace kd
+
+using namespace kd;
+
+extern "C" size_t kd_stream_workspace_bytes(void) {
+  return (size_t)(kMaxClusters + 1) * kNumPartialSlots * sizeof(float);
+}
+
+extern "C" int kd_prepare_rows(const int64_t* labels, const uint8_t* mask, int B, int T, int64_t ignore_index,
+                               int32_t* row_target, int32_t* n_valid, void* stream) {
+  if (labels == nullptr || n_valid == nullptr || B <= 0 || T <= 0) {
+    set_error("kd_prepare_rows: bad arguments");
+    return 1;
+  }
+  kd_prepare_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(labels, mask, B, T, ignore_index, row_target, n_valid);
+  return check_cuda(cudaGetLastError(), "kd_prepare_rows launch");
+}
+
+extern "C" int kd_finalize_losses(const float* sums, float tau, float alpha, int sparse, float* losses, void* stream) {
+  if (!sums || !losses) {
+    set_error("kd_finalize_losses: null pointer");
+    return 1;
+  }
+  kd_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, tau, alpha, sparse, losses);
+  return check_cuda(cudaGetLastError(), "kd_finalize launch");
+}
+
+extern "C" int kd_dense_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b, int64_t z_stride_t, const void* y,
+                                int y_dtype, int64_t y_stride_b, int64_t y_stride_t, const int32_t* row_target, int B,
+                                int T, int V, float tau, float alpha, const int32_t* n_norm, float grad_scale,
+                                float* sums, void* dlogits, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!z || !y || !row_target || !sums || (dlogits && !n_norm)) {
+    set_error("kd_dense_fwd_bwd: null pointer argument");
+    return 1;
+  }
+  StreamParams p = {};
+  p.z = z; p.y = y;
+  p.z_sb = z_stride_b; p.z_st = z_stride_t; p.y_sb = y_stride_b; p.y_st = y_stride_t;
+  p.row_target = row_target;
+  p.B = B; p.T = T; p.V = V;
+  p.tau = tau; p.alpha = alpha; p.grad_scale = grad_scale;
+  p.n_norm = n_norm; p.dlogits = dlogits;
+  return stream_common(p, z_dtype, y_dtype, true, sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int kd_sparse_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b, int64_t z_stride_t,
+                                 const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target, int B,
+                                 int T, int V, float tau, float alpha, const int32_t* n_norm, float grad_scale,
+                                 float* sums, void* dlogits, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!z || !topk_v || !topk_i || !row_target || !sums || (dlogits && !n_norm)) {
+    set_error("kd_sparse_fwd_bwd: null pointer argument");
+    return 1;
+  }
+  if (K <= 0 || K > kMaxTopK) {
+    set_error("kd_sparse_fwd_bwd: K=%d outside [1, %d]", K, kMaxTopK);
+    return 1;
+  }
+  StreamParams p = {};
+  p.z = z;
+  p.z_sb = z_stride_b; p.z_st = z_stride_t;
+  p.topk_v = topk_v; p.topk_i = topk_i; p.K = K;
+  p.row_target = row_target;
+  p.B = B; p.T = T; p.V = V;
+  p.tau = tau; p.alpha = alpha; p.grad_scale = grad_scale;
+  p.n_norm = n_norm; p.dlogits = dlogits;
+  return stream_common(p, z_dtype, z_dtype, false, sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int kd_scale_inplace(void* x, int dtype, int64_t n, const float* scale, void* stream) {
+  if (!x || !scale || n < 0) {
+    set_error("kd_scale_inplace: bad arguments");
+    return 1;
+  }
+  if (n == 0) return 0;
+  const int threads = 256;
+  int64_t want = (n / 8 + threads - 1) / threads;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case KD_DTYPE_F32: kd_scale_kernel<float><<<blocks, threads, 0, s>>>((float*)x, n, scale); break;
+    case KD_DTYPE_BF16: kd_scale_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>((__nv_bfloat16*)x, n, scale); break;
+    case KD_DTYPE_F16: kd_scale_kernel<__half><<<blocks, threads, 0, s>>>((__half*)x, n, scale); break;
+    default: set_error("kd_scale_inplace: unsupported dtype code %d", dtype); return 1;
+  }
+  return check_cuda(cudaGetLastError(), "kd_scale launch");
+}
+
+extern "C" int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stream) {
+  if (!grad || old_vocab < 0 || H <= 0) {
+    set_error("kd_mask_rows: bad arguments");
+    return 1;
+  }
+  const int64_t n = old_vocab * H;
+  if (n == 0) return 0;
+  // a memset is the fastest zero-fill the device offers (all supported dtypes have all-zero-bits 0.0)
+  return check_cuda(cudaMemsetAsync(grad, 0, (size_t)n * dtype_size(dtype), (cudaStream_t)stream), "kd_mask_rows memset");
+}

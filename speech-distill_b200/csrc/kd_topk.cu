@@ -1,0 +1,269 @@
+// K3: teacher top-k log-prob compaction (HBM-bound, one read of the logits).
+//
+// Replaces the three torch calls of extract_teacher_logits.py:114-129 / train.py:82-91:
+//   log_softmax(logits) -> topk(k) -> values fp16, indices int32.
+// One CTA per row:
+//   pass 1 (HBM): online log-sum-exp + per-thread running maximum;
+//   threshold   : the k-th largest of the 512 per-thread maxima is a lower bound of the k-th
+//                 largest logit (at least k elements are >= it);
+//   pass 2 (L2) : every logit >= threshold is appended to a shared-memory candidate list
+//                 (typically 1-2 k entries for k = 64..128 at V = 153k);
+//   select      : bitonic sort of the candidates by (logit desc, index asc), first k win;
+//   values      : round_to_input_dtype((x - max) - log(sum)) -> fp16.
+// Rounding is monotone, so this is a valid top-k of the rounded log-probs under a fixed
+// tie-break and equals torch.topk(log_softmax(x)) index-for-index on tie-free rows
+// (hard part 4).  Rows whose candidate list overflows (massive ties, constant
+// rows) take an exact but slow bisection path.
+#include "kd_common.cuh"
+
+namespace kd {
+
+constexpr int kTopkThreads = 512;
+constexpr int kTopkCap = 2048;
+
+__device__ __forceinline__ uint32_t order_key(float x) {
+  x = x + 0.0f;  // -0.0 -> +0.0 so that equal values get equal keys
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+struct TopkShared {
+  uint64_t cand[kTopkCap];
+  uint32_t tmax[kTopkThreads];
+  float red_m[kTopkThreads / 32];
+  float red_s[kTopkThreads / 32];
+  int count;
+  int cnt_a, cnt_b;
+  float lse_m, lse_log;
+};
+
+// descending bitonic sort of n (power of two) 64-bit keys in shared memory
+__device__ void bitonic_desc_u64(uint64_t* a, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const bool desc = (i & size) == 0;
+        const uint64_t x = a[i], y = a[j];
+        if ((x < y) == desc) {
+          a[i] = y;
+          a[j] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ void bitonic_desc_u32(uint32_t* a, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const bool desc = (i & size) == 0;
+        const uint32_t x = a[i], y = a[j];
+        if ((x < y) == desc) {
+          a[i] = y;
+          a[j] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T, typename F>
+__device__ __forceinline__ void for_each_elem(const T* __restrict__ row, int V, bool vec_ok, F&& fn) {
+  const int tid = threadIdx.x;
+  const int vhi = vec_ok ? (V & ~7) : 0;
+  for (int i = tid * 8; i < vhi; i += kTopkThreads * 8) {
+    Vec8<T> v;
+    v.load_global(row + i);
+    float f[8];
+    v.unpack(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fn(f[j], i + j);
+  }
+  for (int i = vhi + tid; i < V; i += kTopkThreads) fn(Elem<T>::to_f(row[i]), i);
+}
+
+// block-wide count of elements satisfying pred (two alternating counters avoid a reset barrier)
+template <typename T, typename P>
+__device__ int block_count(const T* row, int V, bool vec_ok, TopkShared& sh, P&& pred) {
+  int c = 0;
+  for_each_elem(row, V, vec_ok, [&](float x, int idx) { c += pred(order_key(x), idx) ? 1 : 0; });
+  c = __reduce_add_sync(0xffffffffu, c);
+  __syncthreads();
+  if (threadIdx.x == 0) sh.cnt_a = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh.cnt_a, c);
+  __syncthreads();
+  return sh.cnt_a;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restrict__ logits, int64_t R, int V,
+                                                               int64_t row_stride, int k, __half* __restrict__ out_v,
+                                                               int32_t* __restrict__ out_i, int vec_ok_i) {
+  __shared__ TopkShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool vec_ok = vec_ok_i != 0;
+
+  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+    const T* row = logits + r * row_stride;
+    // ---- pass 1: online LSE, thread maximum ------------------------------------------------
+    float m = -CUDART_INF_F, s = 0.f;
+    {
+      const int vhi = vec_ok ? (V & ~7) : 0;
+      for (int i = tid * 8; i < vhi; i += kTopkThreads * 8) {
+        Vec8<T> v;
+        v.load_global(row + i);
+        float f[8];
+        v.unpack(f);
+        float vm = f[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) vm = fmaxf(vm, f[j]);
+        if (vm > m) {
+          s *= exp_diff(m, vm, kLog2e);
+          m = vm;
+        }
+        if (m != -CUDART_INF_F) {
+          const float off = m * kLog2e;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += ex2(fmaf(f[j], kLog2e, -off));
+        }
+      }
+      for (int i = vhi + tid; i < V; i += kTopkThreads) {
+        const float x = Elem<T>::to_f(row[i]);
+        if (x > m) {
+          s *= exp_diff(m, x, kLog2e);
+          m = x;
+        }
+        if (m != -CUDART_INF_F) s += ex2((x - m) * kLog2e);
+      }
+    }
+    sh.tmax[tid] = order_key(m);
+    // block LSE
+    float wm = warp_max(m);
+    float ws = warp_sum(s * exp_diff(m, wm, kLog2e));
+    if (lane == 0) {
+      sh.red_m[warp] = wm;
+      sh.red_s[warp] = ws;
+    }
+    if (tid == 0) sh.count = 0;
+    __syncthreads();
+    if (warp == 0) {
+      float a = lane < kTopkThreads / 32 ? sh.red_m[lane] : -CUDART_INF_F;
+      float b = lane < kTopkThreads / 32 ? sh.red_s[lane] : 0.f;
+      const float mm = warp_max(a);
+      b = warp_sum(b * exp_diff(a, mm, kLog2e));
+      if (lane == 0) {
+        sh.lse_m = mm;
+        sh.lse_log = ln_acc(b);
+      }
+    }
+    // ---- threshold: k-th largest thread maximum ---------------------------------------------
+    bitonic_desc_u32(sh.tmax, kTopkThreads);
+    const uint32_t t0 = sh.tmax[k - 1];
+    // ---- pass 2: collect candidates ----------------------------------------------------------
+    for_each_elem(row, V, vec_ok, [&](float x, int idx) {
+      const uint32_t key = order_key(x);
+      if (key >= t0) {
+        const int slot = atomicAdd(&sh.count, 1);
+        if (slot < kTopkCap) sh.cand[slot] = ((uint64_t)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)idx);
+      }
+    });
+    __syncthreads();
+    int count = sh.count;
+    if (count > kTopkCap) {
+      // ---- exact slow path: bisection on the key, then on the index among ties ---------------
+      uint32_t lo = t0, hi = 0xffffffffu;  // invariant: count(key >= lo) >= k
+      while (lo < hi) {
+        const uint32_t mid = lo + (uint32_t)(((uint64_t)hi - lo + 1) >> 1);
+        const int c = block_count(row, V, vec_ok, sh, [&](uint32_t key, int) { return key >= mid; });
+        if (c >= k) lo = mid; else hi = mid - 1;
+      }
+      const uint32_t kth = lo;
+      const int above = block_count(row, V, vec_ok, sh, [&](uint32_t key, int) { return key > kth; });
+      const int need = k - above;  // >= 1 ties at kth to take, smallest indices first
+      int jl = 0, jh = V - 1;      // smallest J with count(key == kth && idx <= J) >= need
+      while (jl < jh) {
+        const int mid = jl + ((jh - jl) >> 1);
+        const int c = block_count(row, V, vec_ok, sh, [&](uint32_t key, int idx) { return key == kth && idx <= mid; });
+        if (c >= need) jh = mid; else jl = mid + 1;
+      }
+      const int jmax = jl;
+      __syncthreads();
+      if (tid == 0) sh.count = 0;
+      __syncthreads();
+      for_each_elem(row, V, vec_ok, [&](float x, int idx) {
+        const uint32_t key = order_key(x);
+        if (key > kth || (key == kth && idx <= jmax)) {
+          const int slot = atomicAdd(&sh.count, 1);
+          if (slot < kTopkCap) sh.cand[slot] = ((uint64_t)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)idx);
+        }
+      });
+      __syncthreads();
+      count = sh.count;  // == k
+    }
+    // ---- sort candidates, emit the first k ---------------------------------------------------
+    int n = 32;
+    while (n < count) n <<= 1;
+    for (int i = count + tid; i < n; i += kTopkThreads) sh.cand[i] = 0ull;  // pads sort last
+    bitonic_desc_u64(sh.cand, n);
+    const float lm = sh.lse_m, ll = sh.lse_log;
+    for (int j = tid; j < k; j += kTopkThreads) {
+      const uint64_t c = sh.cand[j];
+      const float x = key_to_float((uint32_t)(c >> 32));
+      const int idx = (int)(0xffffffffu - (uint32_t)(c & 0xffffffffu));
+      const float lp = (x - lm) - ll;
+      const float lp_r = Elem<T>::to_f(Elem<T>::from_f(lp));  // log_softmax returns the logits' dtype
+      out_v[r * k + j] = __float2half_rn(lp_r);
+      out_i[r * k + j] = idx;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace kd
+
+using namespace kd;
+
+extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k, void* out_v,
+                                int32_t* out_i, void* stream) {
+  if (!logits || !out_v || !out_i) {
+    set_error("kd_topk_logprobs: null pointer argument");
+    return 1;
+  }
+  if (R < 0 || V <= 0 || k <= 0 || k > V || k > kTopkThreads) {
+    set_error("kd_topk_logprobs: need 1 <= k <= min(V, %d); got k=%d V=%d R=%lld", kTopkThreads, k, V, (long long)R);
+    return 1;
+  }
+  if (R == 0) return 0;
+  const size_t es = dtype == KD_DTYPE_F32 ? 4 : 2;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * es) % 16 == 0) ? 1 : 0;
+  const int grid = (int)(R < 148 * 64 ? R : 148 * 64);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case KD_DTYPE_F32:
+      kd_topk_kernel<float><<<grid, kTopkThreads, 0, s>>>((const float*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok);
+      break;
+    case KD_DTYPE_BF16:
+      kd_topk_kernel<__nv_bfloat16><<<grid, kTopkThreads, 0, s>>>((const __nv_bfloat16*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok);
+      break;
+    case KD_DTYPE_F16:
+      kd_topk_kernel<__half><<<grid, kTopkThreads, 0, s>>>((const __half*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok);
+      break;
+    default:
+      set_error("kd_topk_logprobs: unsupported dtype code %d", dtype);
+      return 1;
+  }
+  return check_cuda(cudaGetLastError(), "kd_topk launch");
+}

@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference loss interface over the C ABI (include/kd_b200.h).
+
+``DistillationLoss`` keeps the reference's constructor, ``forward`` signature, 4-tuple return and
+error behaviour (reference ``distillation_loss.py:6-128``); ``fused_linear_kd_loss`` is the opt-in
+form that takes hidden states + LM-head weight instead of logits.  Everything here
+is plumbing: row bookkeeping, dtype/stride checks, autograd registration.  All arithmetic runs in
+libkd_b200.so on the current CUDA stream; there is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import KdError, check, dtype_code, require_cuda, stream_ptr
+
+IGNORE_INDEX = -100
+
+
+# --------------------------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------------------------
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _as_btv(x, name):
+    """View logits-like input as [B, T, V] with a unit last stride (copy only if unavoidable)."""
+    if x.dim() < 2:
+        raise ValueError(f"{name} must have at least 2 dimensions [..., T, V]")
+    if x.dim() == 2:
+        x = x.unsqueeze(0)
+    elif x.dim() > 3:
+        x = x.reshape(-1, x.size(-2), x.size(-1))
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    return x
+
+
+def prepare_rows(labels, speech_token_mask, B, T, ignore_index, device):
+    """kd_prepare_rows: row_target int32 [B*T] (-1 = row not scored) and n_valid int32 [1]."""
+    lib = _lib.load()
+    labels = labels.to(device=device, dtype=torch.int64).reshape(B, T).contiguous()
+    mask_u8 = None
+    if speech_token_mask is not None:
+        mask_u8 = (speech_token_mask.to(device).reshape(B, T) != 0).to(torch.uint8).contiguous()
+    row_target = torch.empty(B * T, dtype=torch.int32, device=device)
+    n_valid = torch.empty(1, dtype=torch.int32, device=device)
+    check(
+        lib.kd_prepare_rows(labels.data_ptr(), _ptr(mask_u8), B, T, int(ignore_index), row_target.data_ptr(),
+                            n_valid.data_ptr(), stream_ptr(device)),
+        "kd_prepare_rows",
+    )
+    return row_target, n_valid
+
+
+def finalize_losses(sums, tau, alpha, sparse):
+    lib = _lib.load()
+    losses = torch.empty(4, dtype=torch.float32, device=sums.device)
+    check(lib.kd_finalize_losses(sums.data_ptr(), float(tau), float(alpha), int(bool(sparse)), losses.data_ptr(),
+                                 stream_ptr(sums.device)), "kd_finalize_losses")
+    return losses
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _stream_call(z, y, topk_v, topk_i, row_target, n_norm, tau, alpha, grad_scale, want_grad):
+    """One launch of K2 (dense or sparse).  Returns (sums[8], dlogits or None)."""
+    lib = _lib.load()
+    B, T, V = z.shape
+    dev = z.device
+    sums = torch.empty(8, dtype=torch.float32, device=dev)
+    dlogits = torch.empty((B, T, V), dtype=z.dtype, device=dev) if want_grad else None
+    ws = _workspace(lib.kd_stream_workspace_bytes(), dev)
+    if y is not None:
+        rc = lib.kd_dense_fwd_bwd(
+            z.data_ptr(), dtype_code(z.dtype), z.stride(0), z.stride(1),
+            y.data_ptr(), dtype_code(y.dtype), y.stride(0), y.stride(1),
+            row_target.data_ptr(), B, T, V, float(tau), float(alpha), n_norm.data_ptr(), float(grad_scale),
+            sums.data_ptr(), _ptr(dlogits), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        check(rc, "kd_dense_fwd_bwd")
+    else:
+        K = topk_v.size(-1)
+        rc = lib.kd_sparse_fwd_bwd(
+            z.data_ptr(), dtype_code(z.dtype), z.stride(0), z.stride(1),
+            topk_v.data_ptr(), topk_i.data_ptr(), K,
+            row_target.data_ptr(), B, T, V, float(tau), float(alpha), n_norm.data_ptr(), float(grad_scale),
+            sums.data_ptr(), _ptr(dlogits), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        check(rc, "kd_sparse_fwd_bwd")
+    return sums, dlogits
+
+
+# --------------------------------------------------------------------------------------------
+# K2 behind autograd: loss on materialised logits
+# --------------------------------------------------------------------------------------------
+class _KDOnLogits(torch.autograd.Function):
+    """(total, task, distill, teacher_task) = f(student_logits); gradient formed in the same sweep."""
+
+    @staticmethod
+    def forward(ctx, z, y, topk_v, topk_i, row_target, n_valid, n_norm, tau, alpha, reduce_fn):
+        need_grad = bool(ctx.needs_input_grad[0])
+        sums, dlogits = _stream_call(z, y, topk_v, topk_i, row_target, n_norm, tau, alpha, 1.0, need_grad)
+        if reduce_fn is not None:  # data-parallel: all-reduce the 8-float record before normalising
+            sums = reduce_fn(sums)
+        losses = finalize_losses(sums, tau, alpha, y is None)
+        ctx.set_materialize_grads(False)
+        ctx.dlogits = dlogits
+        ctx.cfg = (tau, alpha)
+        ctx.shape = z.shape
+        ctx.save_for_backward(z, y, topk_v, topk_i, row_target, n_norm)
+        total, task, distill, teacher = losses.unbind(0)
+        ctx.mark_non_differentiable(teacher)
+        return total, task, distill, teacher
+
+    @staticmethod
+    def backward(ctx, g_total, g_task, g_distill, g_teacher):
+        lib = _lib.load()
+        z, y, topk_v, topk_i, row_target, n_norm = ctx.saved_tensors
+        tau, alpha = ctx.cfg
+        grad = None
+        if g_total is not None:
+            if ctx.dlogits is None:
+                raise KdError("backward called twice on the fused KD loss; recompute the loss instead")
+            grad = ctx.dlogits
+            ctx.dlogits = None  # scaled in place below: single use
+            scale = g_total.detach().to(torch.float32).reshape(1).contiguous()
+            check(lib.kd_scale_inplace(grad.data_ptr(), dtype_code(grad.dtype), grad.numel(), scale.data_ptr(),
+                                       stream_ptr(grad.device)), "kd_scale_inplace")
+        # rare: a caller differentiates task / distill on their own (the reference's autograd allows it)
+        for g_part, a_part in ((g_task, 1.0), (g_distill, 0.0)):
+            if g_part is None:
+                continue
+            _, d_part = _stream_call(z, y, topk_v, topk_i, row_target, n_norm, tau, a_part, 1.0, True)
+            d_part = d_part * g_part.to(d_part.dtype)
+            grad = d_part if grad is None else grad + d_part
+        if grad is not None:
+            grad = grad.view(ctx.shape)
+        return grad, None, None, None, None, None, None, None, None, None
+
+
+def kd_loss_on_logits(student_logits, labels, teacher_logits=None, teacher_top_k_v=None, teacher_top_k_i=None,
+                      speech_token_mask=None, temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX,
+                      reduce_fn=None, count_reduce_fn=None):
+    """Functional form of the reference forward (distillation_loss.py:14-128) on CUDA tensors.
+
+    Returns four 0-dim fp32 tensors (total, task, distill, teacher_task); ``total``, ``task`` and
+    ``distill`` are differentiable w.r.t. ``student_logits``.  ``reduce_fn`` / ``count_reduce_fn``
+    are the data-parallel hooks (all-reduce of the sums record / of the valid-row count).
+    """
+    require_cuda(student_logits)
+    if teacher_logits is None and (teacher_top_k_v is None or teacher_top_k_i is None):
+        raise ValueError("Either teacher_logits or top_k must be provided")  # distillation_loss.py:120
+    z = _as_btv(student_logits, "student_logits")
+    B, T, V = z.shape
+    dev = z.device
+    if labels.numel() != B * T:
+        raise ValueError(f"labels has {labels.numel()} elements, expected {B * T}")
+    row_target, n_valid = prepare_rows(labels, speech_token_mask, B, T, ignore_index, dev)
+    n_norm = count_reduce_fn(n_valid) if count_reduce_fn is not None else n_valid
+    y = v = i = None
+    if teacher_logits is not None:  # dense wins when both are given (:56 before :73)
+        y = _as_btv(teacher_logits.detach(), "teacher_logits")
+        if y.device != dev:
+            y = y.to(dev)
+        if tuple(y.shape) != (B, T, V):
+            raise ValueError(f"teacher_logits shape {tuple(y.shape)} != student_logits shape {(B, T, V)}")
+    else:
+        K = teacher_top_k_v.size(-1)
+        # :82-90 - values to fp32 on the student's device, indices to integer
+        v = teacher_top_k_v.detach().to(device=dev, dtype=torch.float32).reshape(B, T, K).contiguous()
+        i = teacher_top_k_i.detach().to(device=dev, dtype=torch.int32).reshape(B, T, K).contiguous()
+    return _KDOnLogits.apply(z, y, v, i, row_target, n_valid, n_norm, float(temperature), float(alpha), reduce_fn)
+
+
+# --------------------------------------------------------------------------------------------
+# K1 behind autograd: LM head + loss without materialising logits
+# --------------------------------------------------------------------------------------------
+def _fused_workspace(R, H, V, v_chunk, device):
+    lib = _lib.load()
+    return _workspace(lib.kd_fused_workspace_bytes(R, H, V, int(v_chunk)), device)
+
+
+class _KDFusedLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn):
+        lib = _lib.load()
+        R, H = h.shape
+        V = W.shape[0]
+        dev = h.device
+        teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
+        sums = torch.empty(8, dtype=torch.float32, device=dev)
+        row_stats = torch.empty((R, 4), dtype=torch.float32, device=dev)
+        ws = _fused_workspace(R, H, V, v_chunk, dev)
+        rc = lib.kd_fused_linear_fwd(
+            h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
+            _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
+            0, 0, 0, row_target.data_ptr(), R, H, V, float(tau), float(alpha),
+            sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        check(rc, "kd_fused_linear_fwd")
+        if reduce_fn is not None:
+            sums = reduce_fn(sums)
+        eff_alpha = alpha if y is not None else 1.0
+        losses = finalize_losses(sums, tau, eff_alpha, False)
+        ctx.set_materialize_grads(False)
+        ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk))
+        ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm)
+        ctx.ws = ws
+        total, task, distill, teacher = losses.unbind(0)
+        ctx.mark_non_differentiable(teacher)
+        return total, task, distill, teacher
+
+    @staticmethod
+    def backward(ctx, g_total, g_task, g_distill, g_teacher):
+        lib = _lib.load()
+        h, W, y, row_target, row_stats, n_norm = ctx.saved_tensors
+        tau, alpha, teacher_kind, dw_row_begin, v_chunk = ctx.cfg
+        R, H = h.shape
+        V = W.shape[0]
+        dev = h.device
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        gt = zero if g_total is None else g_total.detach().float()
+        w_ce = gt * alpha + (zero if g_task is None else g_task.detach().float())
+        w_kl = gt * (1.0 - alpha) + (zero if g_distill is None else g_distill.detach().float())
+        coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
+        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dH = torch.empty((R, H), dtype=torch.bfloat16, device=dev) if need_h else None
+        dW = None
+        if need_w:
+            # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
+            dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=torch.bfloat16, device=dev)
+        ws = ctx.ws if ctx.ws is not None else _fused_workspace(R, H, V, v_chunk, dev)
+        rc = lib.kd_fused_linear_bwd(
+            h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
+            _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
+            0, 0, 0, row_target.data_ptr(), row_stats.data_ptr(), R, H, V, float(tau),
+            n_norm.data_ptr(), coef.data_ptr(), _ptr(dH), H, _ptr(dW), H, int(dw_row_begin), int(v_chunk),
+            ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        check(rc, "kd_fused_linear_bwd")
+        return dH, dW, None, None, None, None, None, None, None, None, None
+
+
+def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
+                         temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
+                         reduce_fn=None, count_reduce_fn=None):
+    """``DistillationLoss(student_logits = hidden @ lm_head_weight.T, ...)`` without the logits.
+
+    hidden [B,T,H] (or [R,H] with labels [.., T]) bf16, lm_head_weight [V,H] bf16, labels [B,T].
+    teacher_logits [B,T,V] (bf16/fp32) or None for plain causal-LM cross-entropy (stage1).
+    ``dw_row_begin``: first vocabulary row that receives a weight gradient (stage1.py:46-57 passes
+    the old vocabulary size; rows below stay exactly zero and are never computed).
+    """
+    require_cuda(hidden, lm_head_weight)
+    if hidden.dtype != torch.bfloat16 or lm_head_weight.dtype != torch.bfloat16:
+        raise TypeError("fused_linear_kd_loss computes in bf16 with fp32 accumulation: pass bf16 hidden and weight")
+    if hidden.dim() != 3:
+        raise ValueError("hidden must be [B, T, H]")
+    B, T, H = hidden.shape
+    V = lm_head_weight.shape[0]
+    dev = hidden.device
+    h2 = hidden.reshape(B * T, H)
+    if h2.stride(-1) != 1:
+        h2 = h2.contiguous()
+    W = lm_head_weight if lm_head_weight.stride(-1) == 1 else lm_head_weight.contiguous()
+    row_target, n_valid = prepare_rows(labels, speech_token_mask, B, T, ignore_index, dev)
+    n_norm = count_reduce_fn(n_valid) if count_reduce_fn is not None else n_valid
+    y = None
+    if teacher_logits is not None:
+        y = teacher_logits.detach()
+        if tuple(y.shape[-1:]) != (V,) or y.numel() != B * T * V:
+            raise ValueError(f"teacher_logits shape {tuple(y.shape)} does not match [B={B}, T={T}, V={V}]")
+        y = y.reshape(B * T, V)
+        if y.stride(-1) != 1:
+            y = y.contiguous()
+        if y.dtype == torch.float16:
+            y = y.float()
+    out = _KDFusedLinear.apply(h2, W, y, row_target, n_valid, n_norm, float(temperature), float(alpha),
+                               int(dw_row_begin), int(v_chunk), reduce_fn)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# the reference-facing module
+# --------------------------------------------------------------------------------------------
+class DistillationLoss(nn.Module):
+    """Drop-in for the reference ``DistillationLoss`` (distillation_loss.py:6-128).
+
+    Same constructor (plus ``ignore_index``, default -100 as hard-coded at :39-41), same forward
+    signature, same 4-tuple.  Opt-in fused form: pass ``student_hidden=`` and ``lm_head_weight=``
+    (and ``student_logits=None``) to skip the logits tensor altogether.
+    """
+
+    def __init__(self, temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, reference_dtypes=True):
+        super().__init__()
+        self.temperature = temperature
+        self.alpha = alpha
+        self.ignore_index = ignore_index
+        self.reference_dtypes = reference_dtypes
+
+    def forward(self, student_logits, labels, teacher_logits=None, teacher_top_k_v=None, teacher_top_k_i=None,
+                speech_token_mask=None, student_hidden=None, lm_head_weight=None):
+        if student_logits is None:
+            if student_hidden is None or lm_head_weight is None:
+                raise ValueError("pass student_logits, or student_hidden together with lm_head_weight")
+            if teacher_logits is None:
+                raise ValueError("Either teacher_logits or top_k must be provided")
+            out = fused_linear_kd_loss(student_hidden, lm_head_weight, labels, teacher_logits=teacher_logits,
+                                       speech_token_mask=speech_token_mask, temperature=self.temperature,
+                                       alpha=self.alpha, ignore_index=self.ignore_index)
+            ref_dtype = student_hidden.dtype
+            dense = True
+        else:
+            out = kd_loss_on_logits(student_logits, labels, teacher_logits, teacher_top_k_v, teacher_top_k_i,
+                                    speech_token_mask, self.temperature, self.alpha, self.ignore_index)
+            ref_dtype = student_logits.dtype
+            dense = teacher_logits is not None
+        total, task, distill, teacher = out
+        if self.reference_dtypes and ref_dtype != torch.float32:
+            # dtypes the reference returns: dense -> all in the logits dtype;
+            # sparse -> task in the logits dtype, the rest fp32
+            task = task.to(ref_dtype)
+            if dense:
+                total, distill, teacher = total.to(ref_dtype), distill.to(ref_dtype), teacher.to(ref_dtype)
+        return total, task, distill, teacher

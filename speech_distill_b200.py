@@ -1,0 +1,13 @@
+"""Import alias: ``import speech_distill_b200`` loads the package kept in ``speech-distill_b200/``
+(the directory name required by the project layout is not a valid Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "speech-distill_b200")
+_spec = importlib.util.spec_from_file_location(
+    "speech_distill_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["speech_distill_b200"] = _mod
+_spec.loader.exec_module(_mod)

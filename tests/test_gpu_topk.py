@@ -1,0 +1,103 @@
+"""GPU parity of K3 (teacher top-k log-prob compaction): indices bit-exact on tie-free inputs,
+documented tie rule otherwise (hard part 4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kd_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_golden_fp32_indices_bit_exact():
+    import speech_distill_b200 as K
+
+    d = np.load(os.path.join(GOLDEN, "topk_f32.npz"))
+    v, i = K.teacher_topk_logprobs(torch.from_numpy(d["logits"]).cuda(), int(d["k"]))
+    assert v.dtype == torch.float16 and i.dtype == torch.int32
+    np.testing.assert_array_equal(i.cpu().numpy(), d["i"])
+    assert np.abs(v.float().cpu().numpy() - d["v"].astype(np.float32)).max() <= 2 ** -7  # <= 1 fp16 ulp at |v|~8
+
+
+@pytest.mark.parametrize("R,V,k,dtype", [(7, 152936, 64, torch.float32), (5, 152936, 128, torch.float32),
+                                         (3, 159488, 100, torch.float32), (9, 1031, 16, torch.float32),
+                                         (4, 700, 512, torch.float32), (2, 64, 64, torch.float32), (3, 5000, 1, torch.float32)])
+def test_fp32_matches_torch_topk(R, V, k, dtype):
+    import speech_distill_b200 as K
+
+    g = torch.Generator().manual_seed(R * V + k)
+    x = torch.randn(R, V, generator=g) * 3
+    v_ref, i_ref = O.topk_logprobs_reference(x, k)
+    v, i = K.teacher_topk_logprobs(x.cuda(), k)
+    np.testing.assert_array_equal(i.cpu().numpy(), i_ref.numpy())
+    assert (v.float().cpu() - v_ref.float()).abs().max() <= 2 ** -6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_16bit_inputs_tie_rule(dtype):
+    import speech_distill_b200 as K
+
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(6, 152936, generator=g) * 2).to(dtype)
+    k = 64
+    v, i = K.teacher_topk_logprobs(x.cuda(), k)
+    v_spec, i_spec = O.topk_spec(x, k)
+    np.testing.assert_array_equal(i.cpu().numpy(), i_spec.numpy())  # deterministic spec: bit-exact
+    assert (v.float().cpu() - v_spec.float()).abs().max() <= 2 ** -5
+    # and a valid top-k of the reference: same multiset of selected logits as torch.topk on the raw logits
+    top_ref = torch.topk(x.float(), k, -1).values
+    sel = torch.gather(x.float(), -1, i.cpu().long())
+    assert torch.equal(sel, top_ref)
+    # values sorted descending, indices ascending inside equal values
+    xs = sel.numpy()
+    ii = i.cpu().numpy()
+    assert (np.diff(xs, axis=-1) <= 0).all()
+    assert ((np.diff(xs, axis=-1) < 0) | (np.diff(ii, axis=-1) > 0)).all()
+
+
+def test_massive_ties_take_the_exact_path():
+    import speech_distill_b200 as K
+
+    x = torch.zeros(3, 20000)
+    x[1, ::2] = 1.0  # 10000 ties at the top
+    x[2, 5] = 3.0
+    x[2, 17] = 3.0
+    v, i = K.teacher_topk_logprobs(x.cuda(), 32)
+    i = i.cpu().numpy()
+    np.testing.assert_array_equal(i[0], np.arange(32))
+    np.testing.assert_array_equal(i[1], np.arange(0, 64, 2))
+    np.testing.assert_array_equal(i[2], np.array([5, 17] + [j for j in range(40) if j not in (5, 17)][:30]))
+    v_spec, i_spec = O.topk_spec(x, 32)
+    np.testing.assert_array_equal(i, i_spec.numpy())
+
+
+def test_truncation_and_batch_shape():
+    import speech_distill_b200 as K
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 5, 3000, generator=g)
+    v, i = K.teacher_topk_logprobs(x.cuda(), 8, vocab_size=2500)  # train.py:82-83
+    v_ref, i_ref = O.topk_logprobs_reference(x[..., :2500], 8)
+    assert v.shape == (2, 5, 8)
+    np.testing.assert_array_equal(i.cpu().numpy(), i_ref.numpy())
+    mask = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1]])
+    vs, is_ = K.extract_batch(x.cuda(), mask.cuda(), 8)
+    assert [a.shape for a in vs] == [(3, 8), (5, 8)] and is_[0].dtype == np.int32 and vs[0].dtype == np.float16
+
+
+def test_topk_feeds_sparse_loss_like_train_py():
+    """train.py:74-104: on-the-fly top-k of the teacher, then the sparse loss."""
+    import speech_distill_b200 as K
+
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(2, 6, 8192, generator=g) * 2
+    y = torch.randn(2, 6, 8192, generator=g) * 2
+    lab = torch.randint(0, 8192, (2, 6), generator=g)
+    v_ref, i_ref = O.topk_logprobs_reference(y, 64)
+    ref = O.reference_loss(z, lab, teacher_top_k_v=v_ref, teacher_top_k_i=i_ref)
+    v, i = K.teacher_topk_logprobs(y.cuda(), 64)
+    out = K.kd_loss_on_logits(z.cuda(), lab.cuda(), teacher_top_k_v=v, teacher_top_k_i=i)
+    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-3)
