@@ -113,7 +113,8 @@ int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stre
  * or none (alpha is forced to 1: plain causal-LM CE, stage1).
  *
  * kd_fused_linear_fwd  : sums[8] and row_stats float[R,4] = (LSE1, LSEtau, LSEteacher_tau, valid).
- * kd_fused_linear_bwd  : dH [R,H] bf16 and dW [V,H] bf16 (rows < dw_row_begin are NOT written:
+ * kd_fused_linear_bwd  : dH [R,H] and dW [V,H] in grad_dtype (KD_DTYPE_BF16 = what autograd hands a bf16
+ *                        parameter; KD_DTYPE_F32 = unrounded accumulators, for verification) (rows < dw_row_begin are NOT written:
  *                        stage1 passes old_vocab and zero-fills once, stage1.py:46-57);
  *                        grad_coef: device float[2] = (w_ce, w_kl); the gradient returned is
  *                        d[(w_ce * sum CE + w_kl * tau^2 * sum KL) / N]; the usual call passes
@@ -132,7 +133,7 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                         const float* topk_v, const int32_t* topk_i, int K,
                         const int32_t* row_target, const float* row_stats, int R, int H, int V,
-                        float tau, const int32_t* n_norm, const float* grad_coef,
+                        float tau, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
                         void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
                         int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -140,9 +141,10 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
  *   C[M,N] (ldc) = op(A) * op(B)^T with
  *   a_mn_major = 0: A is [M][K] (K contiguous, lda)   | 1: A is [K][M] (M contiguous, lda)
  *   b_mn_major = 0: B is [N][K] (K contiguous, ldb)   | 1: B is [K][N] (N contiguous, ldb)
- * (a_mn_major = 1, b_mn_major = 0) is not instantiated. */
-int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
-                 float* C, int64_t ldc, int M, int N, int K, void* stream);
+ * a_dtype: KD_DTYPE_BF16, or KD_DTYPE_F16 (mixed fp16 x bf16 MMA, the backward's gradient operand; only
+ * with b_mn_major = 1).  (a_mn_major = 1, b_mn_major = 0) is not instantiated. */
+int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, int a_dtype, const void* B, int64_t ldb,
+                 int b_mn_major, float* C, int64_t ldc, int M, int N, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -182,29 +182,35 @@ def _fused_workspace(R, H, V, v_chunk, device):
     return _workspace(lib.kd_fused_workspace_bytes(R, H, V, int(v_chunk)), device)
 
 
+def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk):
+    lib = _lib.load()
+    R, H = h.shape
+    V = W.shape[0]
+    dev = h.device
+    teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
+    sums = torch.empty(8, dtype=torch.float32, device=dev)
+    row_stats = torch.empty((R, 4), dtype=torch.float32, device=dev)
+    ws = _fused_workspace(R, H, V, v_chunk, dev)
+    rc = lib.kd_fused_linear_fwd(
+        h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
+        _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
+        0, 0, 0, row_target.data_ptr(), R, H, V, float(tau), float(alpha),
+        sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+    check(rc, "kd_fused_linear_fwd")
+    return sums, row_stats, ws
+
+
 class _KDFusedLinear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn):
-        lib = _lib.load()
-        R, H = h.shape
-        V = W.shape[0]
-        dev = h.device
+    def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype):
         teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
-        sums = torch.empty(8, dtype=torch.float32, device=dev)
-        row_stats = torch.empty((R, 4), dtype=torch.float32, device=dev)
-        ws = _fused_workspace(R, H, V, v_chunk, dev)
-        rc = lib.kd_fused_linear_fwd(
-            h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
-            _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-            0, 0, 0, row_target.data_ptr(), R, H, V, float(tau), float(alpha),
-            sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
-        check(rc, "kd_fused_linear_fwd")
+        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
         eff_alpha = alpha if y is not None else 1.0
         losses = finalize_losses(sums, tau, eff_alpha, False)
         ctx.set_materialize_grads(False)
-        ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk))
+        ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk), grad_dtype)
         ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm)
         ctx.ws = ws
         total, task, distill, teacher = losses.unbind(0)
@@ -213,43 +219,71 @@ class _KDFusedLinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, g_task, g_distill, g_teacher):
-        lib = _lib.load()
         h, W, y, row_target, row_stats, n_norm = ctx.saved_tensors
-        tau, alpha, teacher_kind, dw_row_begin, v_chunk = ctx.cfg
-        R, H = h.shape
-        V = W.shape[0]
+        tau, alpha, teacher_kind, dw_row_begin, v_chunk, grad_dtype = ctx.cfg
         dev = h.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         gt = zero if g_total is None else g_total.detach().float()
         w_ce = gt * alpha + (zero if g_task is None else g_task.detach().float())
         w_kl = gt * (1.0 - alpha) + (zero if g_distill is None else g_distill.detach().float())
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
-        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dH = torch.empty((R, H), dtype=torch.bfloat16, device=dev) if need_h else None
-        dW = None
-        if need_w:
-            # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
-            dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=torch.bfloat16, device=dev)
-        ws = ctx.ws if ctx.ws is not None else _fused_workspace(R, H, V, v_chunk, dev)
-        rc = lib.kd_fused_linear_bwd(
-            h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
-            _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-            0, 0, 0, row_target.data_ptr(), row_stats.data_ptr(), R, H, V, float(tau),
-            n_norm.data_ptr(), coef.data_ptr(), _ptr(dH), H, _ptr(dW), H, int(dw_row_begin), int(v_chunk),
-            ws.data_ptr(), ws.numel(), stream_ptr(dev))
-        check(rc, "kd_fused_linear_bwd")
-        return dH, dW, None, None, None, None, None, None, None, None, None
+        dH, dW = _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin,
+                                 v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws)
+        return dH, dW, None, None, None, None, None, None, None, None, None, None
+
+
+def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin, v_chunk,
+                    grad_dtype, need_h, need_w, ws=None):
+    lib = _lib.load()
+    R, H = h.shape
+    V = W.shape[0]
+    dev = h.device
+    dH = torch.empty((R, H), dtype=grad_dtype, device=dev) if need_h else None
+    dW = None
+    if need_w:
+        # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
+        dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
+    if ws is None:
+        ws = _fused_workspace(R, H, V, v_chunk, dev)
+    rc = lib.kd_fused_linear_bwd(
+        h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
+        _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
+        0, 0, 0, row_target.data_ptr(), row_stats.data_ptr(), R, H, V, float(tau),
+        n_norm.data_ptr(), coef.data_ptr(), dtype_code(grad_dtype), _ptr(dH), H, _ptr(dW), H,
+        int(dw_row_begin), int(v_chunk), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+    check(rc, "kd_fused_linear_bwd")
+    return dH, dW
+
+
+def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
+                                   temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
+                                   grad_dtype=torch.float32):
+    """Forward + backward in one call, outside autograd: returns (losses[4] fp32, dHidden, dWeight) with the
+    gradients of ``total`` in ``grad_dtype``.  fp32 exposes the kernels' accumulators before the final
+    rounding to bf16 that autograd imposes on bf16 leaves (used by the parity tests and by callers that keep
+    fp32 master gradients)."""
+    with torch.no_grad():
+        out = fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits, speech_token_mask, temperature,
+                                   alpha, ignore_index, dw_row_begin, v_chunk, _return_ctx=True)
+    losses, saved = out
+    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha = saved
+    coef = torch.tensor([eff_alpha, 1.0 - eff_alpha], dtype=torch.float32, device=h2.device)
+    dH, dW = _fused_backward(h2, W, y, row_target, row_stats, n_norm, coef, float(temperature), teacher_kind,
+                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True)
+    return losses, dH.view(hidden.shape), dW
 
 
 def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                          temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
-                         reduce_fn=None, count_reduce_fn=None):
+                         reduce_fn=None, count_reduce_fn=None, grad_dtype=torch.bfloat16, _return_ctx=False):
     """``DistillationLoss(student_logits = hidden @ lm_head_weight.T, ...)`` without the logits.
 
     hidden [B,T,H] (or [R,H] with labels [.., T]) bf16, lm_head_weight [V,H] bf16, labels [B,T].
     teacher_logits [B,T,V] (bf16/fp32) or None for plain causal-LM cross-entropy (stage1).
     ``dw_row_begin``: first vocabulary row that receives a weight gradient (stage1.py:46-57 passes
     the old vocabulary size; rows below stay exactly zero and are never computed).
+    ``grad_dtype``: torch.bfloat16 (what autograd requires for bf16 leaves) or torch.float32 - the
+    unrounded fp32 accumulators, usable only with non-leaf / fp32-grad consumers (verification).
     """
     require_cuda(hidden, lm_head_weight)
     if hidden.dtype != torch.bfloat16 or lm_head_weight.dtype != torch.bfloat16:
@@ -275,8 +309,16 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
             y = y.contiguous()
         if y.dtype == torch.float16:
             y = y.float()
+    if _return_ctx:  # fused_linear_kd_value_and_grad: forward pieces without an autograd node
+        teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
+        sums, row_stats, _ = _fused_forward(h2, W, y, row_target, float(temperature), float(alpha), v_chunk)
+        if reduce_fn is not None:
+            sums = reduce_fn(sums)
+        eff_alpha = float(alpha) if y is not None else 1.0
+        losses = finalize_losses(sums, temperature, eff_alpha, False)
+        return losses, (h2.detach(), W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha)
     out = _KDFusedLinear.apply(h2, W, y, row_target, n_valid, n_norm, float(temperature), float(alpha),
-                               int(dw_row_begin), int(v_chunk), reduce_fn)
+                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype)
     return out
 
 

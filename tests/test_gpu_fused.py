@@ -26,17 +26,21 @@ def gemm(A, B, a_mn, b_mn, M, N, K):
 
     lib = _lib.load()
     C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
-    _lib.check(lib.kd_gemm_bf16(A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn, C.data_ptr(),
-                                C.stride(0), M, N, K, torch.cuda.current_stream().cuda_stream), "kd_gemm_bf16")
+    _lib.check(lib.kd_gemm_bf16(A.data_ptr(), A.stride(0), a_mn, _lib.dtype_code(A.dtype), B.data_ptr(), B.stride(0),
+                                b_mn, C.data_ptr(), C.stride(0), M, N, K, torch.cuda.current_stream().cuda_stream),
+               "kd_gemm_bf16")
     return C
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 1024), (256, 512, 192), (300, 700, 136), (4096, 2048, 1024)])
-@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
-def test_umma_gemm_all_layouts(M, N, K, a_mn, b_mn):
-    """The tcgen05 mainloop alone: K-major and MN-major operand descriptors, ragged edges via TMA zero fill."""
+# ragged M/N/K against the 128 x 256 x 64 tile (TMA zero fill); MN-major storage needs 16-byte row strides
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 1024), (256, 512, 192), (304, 704, 136), (4096, 2048, 1024)])
+@pytest.mark.parametrize("a_mn,b_mn,a_dtype", [(0, 0, torch.bfloat16), (0, 1, torch.bfloat16), (1, 1, torch.bfloat16),
+                                               (0, 1, torch.float16), (1, 1, torch.float16)])
+def test_umma_gemm_all_layouts(M, N, K, a_mn, b_mn, a_dtype):
+    """The tcgen05 mainloop alone: K-major and MN-major operand descriptors, ragged edges via TMA zero
+    fill, and the mixed fp16 x bf16 MMA used for the gradient operand."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    A = torch.randn(M, K, device="cuda", generator=g).to(a_dtype)
     B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
     ref = A.float() @ B.float().t()
     Ain = A.t().contiguous() if a_mn else A  # MN-major storage = [K][M]
@@ -45,6 +49,15 @@ def test_umma_gemm_all_layouts(M, N, K, a_mn, b_mn):
     torch.cuda.synchronize()
     assert torch.isfinite(C).all()
     assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 1e-5 * max(1, K // 256 + 1)
+
+
+def test_umma_gemm_rejects_unaligned_rows():
+    from speech_distill_b200 import _lib
+
+    A = torch.randn(136, 300, device="cuda").bfloat16()  # [K][M] with a 600-byte row stride
+    B = torch.randn(136, 704, device="cuda").bfloat16()
+    with pytest.raises(_lib.KdError, match="16-byte"):
+        gemm(A, B, 1, 1, 300, 704, 136)
 
 
 def _case(seed, B, T, H, V, y_dtype=torch.bfloat16, mask=True):
@@ -57,6 +70,16 @@ def _case(seed, B, T, H, V, y_dtype=torch.bfloat16, mask=True):
         labels[:, : max(1, T // 4)] = -100
         labels[0, -1] = -100
     return h, W, y, labels
+
+
+def _torch_bf16_pipeline(h, W, y, labels, tau, alpha):
+    """What the reference does on a GPU today: bf16 nn.Linear + distillation_loss ops + autograd, all bf16."""
+    hc = h.cuda().requires_grad_(True)
+    Wc = W.cuda().requires_grad_(True)
+    out = O.reference_loss(torch.nn.functional.linear(hc, Wc), labels.cuda(), teacher_logits=y.cuda(),
+                           temperature=tau, alpha=alpha)
+    out[0].backward()
+    return hc.grad, Wc.grad
 
 
 def _run_fused(h, W, y, labels, tau, alpha, **kw):
@@ -78,8 +101,8 @@ def test_fused_golden_f64():
     y = torch.from_numpy(d["y"]).bfloat16()
     losses, gh, gw = _run_fused(h, W, y, torch.from_numpy(d["labels"]), float(d["tau"]), float(d["alpha"]))
     np.testing.assert_allclose(losses, d["losses"], rtol=1e-3)
-    assert rel_err(gh.float().cpu().numpy(), d["dh"]) < 5e-3
-    assert rel_err(gw.float().cpu().numpy(), d["dW"]) < 5e-3
+    assert rel_err(gh.float().cpu().numpy(), d["dh"]) < 3e-3
+    assert rel_err(gw.float().cpu().numpy(), d["dW"]) < 3e-3
 
 
 @pytest.mark.parametrize("B,T,H,V,tau,alpha,y_dtype", [
@@ -97,10 +120,22 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
     eh = rel_err(gh.float().cpu().numpy(), gh_ref.numpy())
     ew = rel_err(gw.float().cpu().numpy(), gw_ref.numpy())
-    # gradients are returned in bf16 (as autograd would for bf16 parameters): half-ulp 2^-9 = 2e-3 on the
-    # largest entry is the floor; the accumulated value itself is held to 1e-3 before that rounding
-    assert eh < 4e-3 and ew < 4e-3, (eh, ew)
     assert gh.dtype == torch.bfloat16 and gw.dtype == torch.bfloat16
+    # (1) the kernels' fp32 accumulators, before autograd's mandatory rounding to the bf16 leaves: 1e-3
+    import speech_distill_b200 as K
+
+    l32, gh32, gw32 = K.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), teacher_logits=y.cuda(),
+                                                       temperature=tau, alpha=alpha)
+    eh32 = rel_err(gh32.cpu().numpy(), gh_ref.numpy())
+    ew32 = rel_err(gw32.cpu().numpy(), gw_ref.numpy())
+    assert eh32 < 1e-3 and ew32 < 1e-3, (eh32, ew32)
+    # (2) bf16 gradients: bf16 half-ulp (2^-9 = 1.95e-3 on the largest entry) on top of (1), and never worse
+    # than the reference's own all-bf16 GPU pipeline measured against the same fp64 oracle
+    rh, rw = _torch_bf16_pipeline(h, W, y, labels, tau, alpha)
+    eh_ref = rel_err(rh.float().cpu().numpy(), gh_ref.numpy())
+    ew_ref = rel_err(rw.float().cpu().numpy(), gw_ref.numpy())
+    assert eh < 3e-3 and ew < 3e-3, (eh, ew)
+    assert eh <= max(1.25 * eh_ref, 2.2e-3) and ew <= max(1.25 * ew_ref, 2.2e-3), (eh, eh_ref, ew, ew_ref)
 
 
 def test_fused_equals_streaming_path():
@@ -127,8 +162,14 @@ def test_stage1_fused_ce_masks_old_rows():
     assert abs(float(loss) - float(loss_ref)) < 1e-3 * float(loss_ref)
     gw = Wc.grad.float().cpu()
     assert float(gw[:old].abs().max()) == 0.0  # stage1.py:53-57: exactly zero
-    assert rel_err(gw[old:].numpy(), gw_ref[old:].numpy()) < 4e-3
-    assert rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()) < 4e-3
+    assert rel_err(gw[old:].numpy(), gw_ref[old:].numpy()) < 3e-3
+    assert rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()) < 3e-3
+    # fp32 accumulators: 1e-3
+    _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), teacher_logits=None,
+                                                     temperature=1.0, alpha=1.0, dw_row_begin=old, v_chunk=1024)
+    assert float(gw32[:old].abs().max()) == 0.0
+    assert rel_err(gw32[old:].cpu().numpy(), gw_ref[old:].numpy()) < 1e-3
+    assert rel_err(gh32.cpu().numpy(), gh_ref.numpy()) < 1e-3
 
 
 def test_mask_rows_kernel():
