@@ -141,10 +141,9 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
  *   C[M,N] (ldc) = op(A) * op(B)^T with
  *   a_mn_major = 0: A is [M][K] (K contiguous, lda)   | 1: A is [K][M] (M contiguous, lda)
  *   b_mn_major = 0: B is [N][K] (K contiguous, ldb)   | 1: B is [K][N] (N contiguous, ldb)
- * a_dtype: KD_DTYPE_BF16, or KD_DTYPE_F16 (mixed fp16 x bf16 MMA, the backward's gradient operand; only
- * with b_mn_major = 1).  (a_mn_major = 1, b_mn_major = 0) is not instantiated. */
-int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, int a_dtype, const void* B, int64_t ldb,
-                 int b_mn_major, float* C, int64_t ldc, int M, int N, int K, void* stream);
+ * (a_mn_major = 1, b_mn_major = 0) is not instantiated. */
+int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                 float* C, int64_t ldc, int M, int N, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@ SIGNATURES = {
     "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32,
                                    _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz,
                                    _vp]),
-    "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -165,26 +165,6 @@ struct FwdEpi {
 };
 
 // ---- backward: gradient tile ------------------------------------------------------------------
-// G is handed to the dW / dH GEMMs as fp16 scaled by a power of two S chosen so that max|G S| < 2^11:
-// 11 mantissa bits instead of bf16's 8 on the operand that carries the soft-max differences.
-// |G| <= (|w_ce| + |w_kl| tau) / N, so S depends only on the launch scalars and every kernel of the
-// backward derives the same value.
-__device__ __forceinline__ float grad_pow2_scale(const float* coef, const int32_t* n_norm, float tau, int use_kl,
-                                                 float* inv_scale) {
-  const int nn = *n_norm;
-  const float amax = nn > 0 ? (fabsf(coef[0]) + (use_kl ? fabsf(coef[1]) * tau : 0.f)) / (float)nn : 0.f;
-  if (!(amax > 0.f) || !isfinite(amax)) {
-    *inv_scale = 1.f;
-    return 1.f;
-  }
-  int e;
-  frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
-  int k = 11 - e;
-  k = k > 100 ? 100 : (k < -100 ? -100 : k);
-  *inv_scale = ldexpf(1.f, -k);
-  return ldexpf(1.f, k);
-}
-
 struct GradParams {
   const int32_t* row_target;
   const float* row_stats;  // [R][4] = LSE1, LSE_tau, LSEteacher_tau, valid
@@ -196,12 +176,12 @@ struct GradParams {
   int use_kl;  // 0: CE only (no teacher)
   const int32_t* n_norm;
   const float* coef;  // device float[2]: weight of d(sum CE) and of tau^2 d(sum KL) in the returned gradient
-  void* G;  // [R][ldg] fp16 (scaled) or bf16, column j <-> vocabulary index v0 + j
+  __nv_bfloat16* G;  // [R][ldg] bf16 (the dtype the reference's dlogits have), column j <-> vocabulary index v0 + j
   int64_t ldg;
   int v0;
 };
 
-template <typename TY, bool DENSE, bool TAU2, bool G_F16>
+template <typename TY, bool DENSE, bool TAU2>
 struct GradEpi {
   using Params = GradParams;
   const Params& p;
@@ -212,10 +192,8 @@ struct GradEpi {
   __device__ GradEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {
     const int nn = *p.n_norm;
     const float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
-    float inv_s, s = 1.f;
-    if (G_F16) s = grad_pow2_scale(p.coef, p.n_norm, p.tau, p.use_kl, &inv_s);
-    c1 = p.coef[0] * inv_n * s;
-    c2 = p.use_kl ? p.coef[1] * p.tau * inv_n * s : 0.f;
+    c1 = p.coef[0] * inv_n;
+    c2 = p.use_kl ? p.coef[1] * p.tau * inv_n : 0.f;
     c_tau = kLog2e / p.tau;
   }
 
@@ -274,14 +252,13 @@ struct GradEpi {
             if (j == (int)d) gq[j] -= c1;
         }
       }
-      using TG = typename std::conditional<G_F16, __half, __nv_bfloat16>::type;
-      TG* out = reinterpret_cast<TG*>(p.G) + (int64_t)row * p.ldg + j0;
+      __nv_bfloat16* out = p.G + (int64_t)row * p.ldg + j0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float t8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) t8[j] = gq[8 * q + j];
-        Vec8<TG> v;
+        Vec8<__nv_bfloat16> v;
         v.pack(t8);
         *reinterpret_cast<uint4*>(out + 8 * q) = v.a;  // stays in L2 for the dW / dH GEMMs
       }
@@ -302,11 +279,6 @@ struct StoreParams {
   __nv_bfloat16* c16;      // bf16 output, row stride ld16
   int64_t ld16;
   int64_t row0_32, row0_16;  // row offsets of tile row 0 inside c32 / c16
-  // when coef != NULL the accumulator holds S * result (A operand = scaled fp16 G): multiply by 1/S
-  const float* coef;
-  const int32_t* n_norm;
-  float tau;
-  int use_kl;
 };
 
 struct StoreEpi {
@@ -315,12 +287,7 @@ struct StoreEpi {
   EpiThread t;
   int row;
 
-  float descale;
-
-  __device__ StoreEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {
-    descale = 1.f;
-    if (p.coef != nullptr) grad_pow2_scale(p.coef, p.n_norm, p.tau, p.use_kl, &descale);
-  }
+  __device__ StoreEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {}
   __device__ void begin_unit(const Geom&, int m_blk, int) { row = m_blk * BM + t.row_in_tile; }
 
   __device__ void tile(const Geom&, int n_blk, uint32_t tmem_acc) {
@@ -337,7 +304,7 @@ struct StoreEpi {
       if (!row_ok || ncols <= 0) continue;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * descale;
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
       if (p.mode == kAccumF32 || p.mode == kFinalBf16) {
         const float* acc = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
         if (ncols == 32 && (p.ld32 & 3) == 0) {
@@ -392,7 +359,7 @@ struct StoreEpi {
 //      MN-major -> global [K rows][M] (M contiguous), two 64(m) x 64(k) boxes per stage
 //   B: K-major  -> global [N rows][K], one 64 x 256 box;  MN-major -> [K rows][N], four 64 x 64 boxes
 // ---------------------------------------------------------------------------------------------
-template <class Epi, bool A_MN, bool B_MN, bool A_F16>
+template <class Epi, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Geom g,
                const typename Epi::Params ep) {
@@ -473,7 +440,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_bf16(BM, BN, A_MN, B_MN, A_F16);
+      constexpr uint32_t idesc = instr_desc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint64_t a_base = A_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
       constexpr uint64_t b_base = B_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 elements
@@ -649,7 +616,7 @@ static EncodeTiledFn get_encode() {
 
 // bf16 matrix [outer rows][inner cols] (inner contiguous), box = 64 inner x box_outer rows, 128-byte swizzle
 static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
-                     uint32_t box_outer, const char* what, bool f16 = false) {
+                     uint32_t box_outer, const char* what) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * 2) % 16 != 0) {
@@ -660,7 +627,7 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
   cuuint64_t strides[1] = {row_stride_elems * 2};
   cuuint32_t box[2] = {64, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -681,10 +648,10 @@ static int sm_count() {
   return n;
 }
 
-template <class Epi, bool A_MN, bool B_MN, bool A_F16 = false>
+template <class Epi, bool A_MN, bool B_MN>
 static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const typename Epi::Params& ep,
                        cudaStream_t stream) {
-  auto kern = kd_umma_kernel<Epi, A_MN, B_MN, A_F16>;
+  auto kern = kd_umma_kernel<Epi, A_MN, B_MN>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes),
@@ -767,23 +734,9 @@ static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& 
 }
 template <bool DENSE, typename TY>
 static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const GradParams& gp, bool tau2,
-                       bool g_f16, cudaStream_t s) {
-  if (g_f16) {
-    if (tau2) return launch_umma<GradEpi<TY, DENSE, true, true>, false, false>(ta, tb, g, gp, s);
-    return launch_umma<GradEpi<TY, DENSE, false, true>, false, false>(ta, tb, g, gp, s);
-  }
-  if (tau2) return launch_umma<GradEpi<TY, DENSE, true, false>, false, false>(ta, tb, g, gp, s);
-  return launch_umma<GradEpi<TY, DENSE, false, false>, false, false>(ta, tb, g, gp, s);
-}
-
-// KD_FUSED_G_BF16=1 keeps the gradient operand in bf16 (debug / A-B comparison of the fp16 path)
-static bool grad_operand_f16() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("KD_FUSED_G_BF16");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
+                       cudaStream_t s) {
+  if (tau2) return launch_umma<GradEpi<TY, DENSE, true>, false, false>(ta, tb, g, gp, s);
+  return launch_umma<GradEpi<TY, DENSE, false>, false, false>(ta, tb, g, gp, s);
 }
 
 }  // namespace fused
@@ -909,10 +862,9 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
     return 1;
   }
   const bool out32 = grad_dtype == KD_DTYPE_F32;
-  const bool g_f16 = grad_operand_f16();
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
-  void* G = wsp + ws.g_off;
+  __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(wsp + ws.g_off);
   float* dh32 = reinterpret_cast<float*>(wsp + ws.dh_off);
   const bool tau2 = tau == 2.0f;
   const size_t ys = y_dtype == KD_DTYPE_F32 ? 4 : 2;
@@ -921,8 +873,8 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
   CUtensorMap t_h_k, t_w_k, t_g_k, t_g_mn, t_h_mn, t_w_mn;
   if (make_tmap(&t_h_k, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
   if (make_tmap(&t_w_k, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, BN, "lm_head weight")) return 1;
-  if (make_tmap(&t_g_k, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)", g_f16)) return 1;
-  if (make_tmap(&t_g_mn, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, 64, "G (MN-major)", g_f16)) return 1;
+  if (make_tmap(&t_g_k, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)")) return 1;
+  if (make_tmap(&t_g_mn, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, 64, "G (MN-major)")) return 1;
   if (make_tmap(&t_h_mn, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, 64, "hidden (MN-major)")) return 1;
   if (make_tmap(&t_w_mn, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, 64, "lm_head weight (MN-major)")) return 1;
 
@@ -957,10 +909,10 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       gp.v0 = v0;
       int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
-        rc = y_dtype == KD_DTYPE_BF16 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, g_f16, s)
-                                      : launch_grad<true, float>(t_h_k, t_w_k, g, gp, tau2, g_f16, s);
+        rc = y_dtype == KD_DTYPE_BF16 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, s)
+                                      : launch_grad<true, float>(t_h_k, t_w_k, g, gp, tau2, s);
       } else {
-        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, g_f16, s);
+        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, s);
       }
       if (rc) return rc;
     }
@@ -984,12 +936,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       sp.c32 = reinterpret_cast<float*>(dW);
       sp.ld32 = dw_stride;
       sp.row0_32 = v0;
-      if (g_f16) {
-        sp.coef = grad_coef; sp.n_norm = n_norm; sp.tau = tau; sp.use_kl = teacher_kind == KD_TEACHER_NONE ? 0 : 1;
-        if (launch_umma<StoreEpi, true, true, true>(t_g_mn, t_h_mn, g, sp, s)) return 1;
-      } else {
-        if (launch_umma<StoreEpi, true, true, false>(t_g_mn, t_h_mn, g, sp, s)) return 1;
-      }
+      if (launch_umma<StoreEpi, true, true>(t_g_mn, t_h_mn, g, sp, s)) return 1;
     }
     // ---- 3. dH (+)= G W[v0 : v0+cols, :] ----
     if (dH) {
@@ -1016,29 +963,23 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
         sp.c16 = reinterpret_cast<__nv_bfloat16*>(dH);
         sp.ld16 = dh_stride;
       }
-      if (g_f16) {
-        sp.coef = grad_coef; sp.n_norm = n_norm; sp.tau = tau; sp.use_kl = teacher_kind == KD_TEACHER_NONE ? 0 : 1;
-        if (launch_umma<StoreEpi, false, true, true>(t_g_k, t_w_mn, g, sp, s)) return 1;
-      } else {
-        if (launch_umma<StoreEpi, false, true, false>(t_g_k, t_w_mn, g, sp, s)) return 1;
-      }
+      if (launch_umma<StoreEpi, false, true>(t_g_k, t_w_mn, g, sp, s)) return 1;
     }
   }
   return 0;
 }
 
-extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, int a_dtype, const void* B, int64_t ldb,
-                            int b_mn_major, float* C, int64_t ldc, int M, int N, int K, void* stream) {
-  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || (a_dtype != KD_DTYPE_BF16 && a_dtype != KD_DTYPE_F16)) {
+extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                            float* C, int64_t ldc, int M, int N, int K, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) {
     set_error("kd_gemm_bf16: bad arguments");
     return 1;
   }
-  const bool a16 = a_dtype == KD_DTYPE_F16;
   CUtensorMap ta, tb;
   if (a_mn_major) {
-    if (make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, "A (MN-major)", a16)) return 1;
+    if (make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, "A (MN-major)")) return 1;
   } else {
-    if (make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM, "A (K-major)", a16)) return 1;
+    if (make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM, "A (K-major)")) return 1;
   }
   if (b_mn_major) {
     if (make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, "B (MN-major)")) return 1;
@@ -1058,13 +999,9 @@ extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, int a_dt
   sp.c32 = C;
   sp.ld32 = ldc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (a_mn_major && b_mn_major)
-    return a16 ? launch_umma<StoreEpi, true, true, true>(ta, tb, g, sp, s)
-               : launch_umma<StoreEpi, true, true, false>(ta, tb, g, sp, s);
-  if (!a_mn_major && b_mn_major)
-    return a16 ? launch_umma<StoreEpi, false, true, true>(ta, tb, g, sp, s)
-               : launch_umma<StoreEpi, false, true, false>(ta, tb, g, sp, s);
-  if (!a_mn_major && !b_mn_major && !a16) return launch_umma<StoreEpi, false, false, false>(ta, tb, g, sp, s);
-  set_error("kd_gemm_bf16: this (layout, dtype) combination is not instantiated");
+  if (a_mn_major && b_mn_major) return launch_umma<StoreEpi, true, true>(ta, tb, g, sp, s);
+  if (!a_mn_major && b_mn_major) return launch_umma<StoreEpi, false, true>(ta, tb, g, sp, s);
+  if (!a_mn_major && !b_mn_major) return launch_umma<StoreEpi, false, false>(ta, tb, g, sp, s);
+  set_error("kd_gemm_bf16: the (A MN-major, B K-major) combination is not instantiated");
   return 1;
 }

