@@ -250,8 +250,7 @@ def run_ours(args):
         h_dev.copy_(h_host, non_blocking=True)
         y_dev.copy_(y_host, non_blocking=True)
         l_dev.copy_(l_host, non_blocking=True)
-        hh = h_dev.requires_grad_(True)
-        hh.grad = None
+        hh = h_dev.detach().requires_grad_(True)  # fresh leaf over the staging buffer
         o = step(hh, y_dev, l_dev)
         out_host.copy_(torch.stack([x.detach().float() for x in o]), non_blocking=True)
 
