@@ -199,15 +199,19 @@ __device__ __forceinline__ void student_update(const float (&f)[N], int nvalid, 
   if (m == -CUDART_INF_F) return;  // nothing finite yet
   const float c_tau = kLog2e * inv_tau;
   const float off_one = m * kLog2e, off_tau = off_one * inv_tau;
+  // two partial sums per statistic: short dependency chains for the 2 epilogue warps per scheduler
+  float pt[2] = {0.f, 0.f}, p1[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     if (i < nvalid) {
       float et, e1;
       ExpPair<TAU2>::eval(f[i], c_tau, off_tau, off_one, et, e1);
-      st += et;
-      s1 += e1;
+      pt[i & 1] += et;
+      p1[i & 1] += e1;
     }
   }
+  st += pt[0] + pt[1];
+  s1 += p1[0] + p1[1];
 }
 
 template <bool TAU2, int N>
@@ -227,19 +231,23 @@ __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float
   if (mt == -CUDART_INF_F) return;
   const float c_tau = kLog2e * inv_tau;
   const float off_one = mt * kLog2e, off_tau = off_one * inv_tau;
+  float pt[2] = {0.f, 0.f}, p1[2] = {0.f, 0.f}, pa[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     if (i < nvalid) {
       float et, e1;
       ExpPair<TAU2>::eval(fy[i], c_tau, off_tau, off_one, et, e1);
-      tt += et;
-      t1 += e1;
+      pt[i & 1] += et;
+      p1[i & 1] += e1;
       // p = 0 contributes exactly 0 (xlogy semantics of nn.KLDivLoss, distillation_loss.py:68);
       // the clamp keeps 0 * (-inf - z) from producing NaN when the teacher holds -inf
       const float d = fmaxf(fy[i], -1e30f) - fz[i];
-      a = (et > 0.f) ? fmaf(et, d, a) : a;
+      pa[i & 1] = (et > 0.f) ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
     }
   }
+  tt += pt[0] + pt[1];
+  t1 += p1[0] + p1[1];
+  a += pa[0] + pa[1];
 }
 
 __device__ __forceinline__ void merge_student(float& m, float& s1, float& st, float m2, float s12, float st2,

@@ -30,16 +30,30 @@ namespace fused {
 using namespace umma;
 
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 128 + 32 * kEpiWarps;  // 384
-constexpr uint32_t kABytes = BM * BK * 2;       // 16 KB
-constexpr uint32_t kBBytes = BN * BK * 2;       // 32 KB
+constexpr int kEpiThreads = 32 * kEpiWarps;      // 256
+constexpr int kThreads = 128 + kEpiThreads;      // 384
+constexpr uint32_t kABytes = BM * BK * 2;        // 16 KB
+constexpr uint32_t kBBytes = BN * BK * 2;        // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kBoxMnBytes = 64 * BK * 2;   // one 64(mn) x 64(k) MN-major box = 8 KB
+constexpr uint32_t kBoxMnBytes = 64 * BK * 2;    // one 64(mn) x 64(k) MN-major box = 8 KB
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kStepCols = 64;                    // columns per epilogue step: 32 for each column half
+constexpr int kSteps = BN / kStepCols;           // 4
+constexpr uint32_t kStepBytes = BM * kStepCols * 2;  // 16 KB: [128 rows x 64 cols] of a 16-bit type, 128 B rows
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
+
+// shared-memory plan of one kernel instantiation
+template <int STAGES, int YSLOTS, int GSLOTS>
+struct SmemPlan {
+  static constexpr uint32_t kPipeOff = 0;
+  static constexpr uint32_t kYOff = STAGES * kStageBytes;
+  static constexpr uint32_t kGOff = kYOff + YSLOTS * kStepBytes;
+  static constexpr uint32_t kBarOff = kGOff + GSLOTS * kStepBytes;
+  static constexpr uint32_t kNumBars = 2 * STAGES + 4 + 2 * (YSLOTS > 0 ? YSLOTS : 1);
+  static constexpr uint32_t kBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*alignment slack*/;
+  static_assert(kBytes <= 232448, "shared memory plan exceeds 227 KB");
+};
 
 struct Geom {
   int num_m_blk, num_n_blk, num_k_blk;
@@ -56,19 +70,30 @@ __host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue policies.  Each epilogue thread owns accumulator row `row_in_tile` and the column half
-// `half` (128 columns) of every 128 x 256 tile, visited in four 32-column chunks.
+// Epilogue policies.  Each epilogue thread owns accumulator row `row_in_tile` (= its TMEM lane) and
+// the column half `half`; a 128 x 256 tile is visited in 4 steps of 64 columns, the thread taking
+// columns [64 c + 32 half, +32) of step c.
 // ---------------------------------------------------------------------------------------------
 struct EpiThread {
-  int row_in_tile;  // 0..127 (TMEM lane)
-  int half;         // 0/1
+  int row_in_tile;         // 0..127 (TMEM lane)
+  int half;                // 0/1
+  int lane;                // lane in warp
+  int epi_tid;             // 0..255
   uint32_t tmem_lane_off;  // lane field of the TMEM address
+  uint32_t y_base, g_base; // smem rings (teacher tile in, gradient tile out)
+  uint32_t yfull0, yempty0;  // first barrier of each ring set (8 bytes apart)
+  const CUtensorMap* tma_g;
 };
+
+// address of this thread's q-th 16-byte piece inside a [128 x 64] 16-bit step buffer (SWIZZLE_128B)
+__device__ __forceinline__ uint32_t step_piece_addr(uint32_t buf, const EpiThread& t, int q) {
+  return buf + (uint32_t)t.row_in_tile * 128u + ((uint32_t)((t.half * 4 + q) ^ (t.row_in_tile & 7)) << 4);
+}
 
 template <typename TY>
 __device__ __forceinline__ void load_row32(const TY* __restrict__ p, bool vec_ok, int ncols, float (&f)[32]) {
-  // ncols = number of in-range columns (<= 32); out-of-range columns read as -inf
-  if (vec_ok && ncols == 32) {
+  // direct global path; ncols = number of in-range columns (<= 32); out-of-range columns read as -inf
+  if (vec_ok && ncols >= 32) {
     if constexpr (sizeof(TY) == 2) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -96,6 +121,39 @@ __device__ __forceinline__ void load_row32(const TY* __restrict__ p, bool vec_ok
   }
 }
 
+// consumer side of the teacher-tile ring: wait for the step buffer, pull this thread's 64 bytes, release
+template <typename TY>
+struct YRing {
+  int slot = 0;
+  uint32_t phase = 0;
+  template <int SLOTS>
+  __device__ __forceinline__ void take(const EpiThread& t, int ncols, float (&fy)[32]) {
+    static_assert(sizeof(TY) == 2, "the TMA-staged teacher path is for 16-bit logits");
+    mbar_wait(t.yfull0 + 8u * slot, phase);
+    const uint32_t buf = t.y_base + (uint32_t)slot * kStepBytes;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Vec8<TY> v;
+      v.a = lds128(step_piece_addr(buf, t, q));
+      float f8[8];
+      v.unpack(f8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fy[8 * q + j] = f8[j];
+    }
+    __syncwarp();
+    if (t.lane == 0) mbar_arrive(t.yempty0 + 8u * slot);
+    if (++slot == SLOTS) {
+      slot = 0;
+      phase ^= 1u;
+    }
+    if (ncols < 32) {  // ragged vocabulary edge: TMA zero-filled the out-of-range columns
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j >= ncols) fy[j] = -CUDART_INF_F;
+    }
+  }
+};
+
 // ---- forward: online statistics -------------------------------------------------------------
 struct FwdParams {
   const int32_t* row_target;
@@ -107,15 +165,20 @@ struct FwdParams {
   float* partials;  // [num_ranges * 2][R][kRecFloats]
 };
 
-template <typename TY, bool DENSE, bool TAU2>
+template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
 struct FwdEpi {
   using Params = FwdParams;
+  static constexpr bool kUseYRing = DENSE && Y_TMA;
+  static constexpr int kStages = kUseYRing ? 3 : 4;
+  static constexpr int kYSlots = kUseYRing ? 4 : 0;
+  static constexpr int kGSlots = 0;
   const Params& p;
   EpiThread t;
   int row, target, range;
   float m, s1, st, mt, t1, tt, a, zl;
+  YRing<__nv_bfloat16> ring;  // 16-bit teacher only (TY is bf16 on this path)
 
-  __device__ FwdEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {}
+  __device__ FwdEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
 
   __device__ void begin_unit(const Geom&, int m_blk, int range_) {
     row = m_blk * BM + t.row_in_tile;
@@ -125,16 +188,23 @@ struct FwdEpi {
     s1 = st = t1 = tt = a = zl = 0.f;
   }
 
-  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc) {
-    const int col_base = g.b_n0 + n_blk * BN + t.half * (BN / 2);
+  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
+    const int col_base = g.b_n0 + n_blk * BN + t.half * 32;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < kSteps; ++c) {
       uint32_t raw[32];
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
-      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(t.half * (BN / 2) + c * 32), raw);
-      tmem_ld_wait();
-      const int col0 = col_base + c * 32;
+      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.half * 32), raw);
+      const int col0 = col_base + c * kStepCols;
       const int ncols = p.V - col0 < 32 ? p.V - col0 : 32;
+      float fy[32];
+      if (kUseYRing) ring.template take<kYSlots>(t, ncols, fy);
+      tmem_ld_wait();
+      if (c == kSteps - 1) {  // accumulator fully read: hand the TMEM buffer back before the math
+        fence_before_sync();
+        __syncwarp();
+        if (t.lane == 0) mbar_arrive(tempty_bar);
+      }
       if (target < 0 || ncols <= 0) continue;
       float fz[32];
 #pragma unroll
@@ -147,9 +217,10 @@ struct FwdEpi {
       }
       student_update<TAU2, 32>(fz, 32, p.inv_tau, m, s1, st);
       if (DENSE) {
-        float fy[32];
-        const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
-        load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
+        if (!kUseYRing) {
+          const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
+          load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
+        }
         teacher_update<TAU2, 32>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
       }
     }
@@ -162,6 +233,7 @@ struct FwdEpi {
       *reinterpret_cast<float4*>(rec + 4) = make_float4(t1, tt, a, zl);
     }
   }
+  __device__ void finish() {}
 };
 
 // ---- backward: gradient tile ------------------------------------------------------------------
@@ -176,20 +248,24 @@ struct GradParams {
   int use_kl;  // 0: CE only (no teacher)
   const int32_t* n_norm;
   const float* coef;  // device float[2]: weight of d(sum CE) and of tau^2 d(sum KL) in the returned gradient
-  __nv_bfloat16* G;  // [R][ldg] bf16 (the dtype the reference's dlogits have), column j <-> vocabulary index v0 + j
-  int64_t ldg;
-  int v0;
+  int v0;             // first vocabulary column of this chunk; scratch column j <-> vocabulary index v0 + j
 };
 
-template <typename TY, bool DENSE, bool TAU2>
+template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
 struct GradEpi {
   using Params = GradParams;
+  static constexpr bool kUseYRing = DENSE && Y_TMA;
+  static constexpr int kStages = kUseYRing ? 3 : 4;
+  static constexpr int kYSlots = kUseYRing ? 3 : 0;
+  static constexpr int kGSlots = 2;
   const Params& p;
   EpiThread t;
-  int row, target;
+  int row, target, m0;
+  uint32_t gstep = 0;
   float c1, c2, c_tau, off1, offt, offy, half_off1, k_tau;
+  YRing<__nv_bfloat16> ring;
 
-  __device__ GradEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {
+  __device__ GradEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {
     const int nn = *p.n_norm;
     const float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
     c1 = p.coef[0] * inv_n;
@@ -198,7 +274,8 @@ struct GradEpi {
   }
 
   __device__ void begin_unit(const Geom&, int m_blk, int) {
-    row = m_blk * BM + t.row_in_tile;
+    m0 = m_blk * BM;
+    row = m0 + t.row_in_tile;
     target = row < p.R ? p.row_target[row] : -1;
     if (target >= 0) {
       const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
@@ -210,28 +287,34 @@ struct GradEpi {
     }
   }
 
-  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc) {
-    const int jbase = n_blk * BN + t.half * (BN / 2);  // column inside the chunk scratch
+  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
+    const int jtile = n_blk * BN;  // first scratch column of this tile
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < kSteps; ++c) {
       uint32_t raw[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
-      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(t.half * (BN / 2) + c * 32), raw);
-      tmem_ld_wait();
-      if (row >= p.R) continue;
-      const int j0 = jbase + c * 32;
+      __syncwarp();
+      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.half * 32), raw);
+      const int j0 = jtile + c * kStepCols + t.half * 32;
       const int col0 = p.v0 + j0;
       const int ncols = p.V - col0 < 32 ? p.V - col0 : 32;
-      float gq[32];
+      float fy[32];
+      if (kUseYRing) ring.template take<kYSlots>(t, ncols, fy);
+      tmem_ld_wait();
+      if (c == kSteps - 1) {
+        fence_before_sync();
+        __syncwarp();
+        if (t.lane == 0) mbar_arrive(tempty_bar);
+      }
+      uint4 pk[4];
       if (target < 0 || ncols <= 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) gq[j] = 0.f;
+        for (int q = 0; q < 4; ++q) pk[q] = make_uint4(0, 0, 0, 0);
       } else {
-        float fy[32];
-        if (DENSE) {
+        if (DENSE && !kUseYRing) {
           const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
           load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
         }
+        float gq[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float z = __uint_as_float(raw[j]);
@@ -251,21 +334,36 @@ struct GradEpi {
           for (int j = 0; j < 32; ++j)
             if (j == (int)d) gq[j] -= c1;
         }
-      }
-      __nv_bfloat16* out = p.G + (int64_t)row * p.ldg + j0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float t8[8];
+        for (int q = 0; q < 4; ++q) {
+          float t8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t8[j] = gq[8 * q + j];
-        Vec8<__nv_bfloat16> v;
-        v.pack(t8);
-        *reinterpret_cast<uint4*>(out + 8 * q) = v.a;  // stays in L2 for the dW / dH GEMMs
+          for (int j = 0; j < 8; ++j) t8[j] = gq[8 * q + j];
+          Vec8<__nv_bfloat16> v;
+          v.pack(t8);
+          pk[q] = v.a;
+        }
       }
+      // stage the [128 x 64] bf16 step in shared memory (swizzled rows) and hand it to a TMA store;
+      // the elected thread first makes sure every earlier store has finished reading its buffer
+      const uint32_t buf = t.g_base + (gstep & 1u) * kStepBytes;
+      if (t.epi_tid == 0) bulk_wait_read_all();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts128(step_piece_addr(buf, t, q), pk[q]);
+      fence_proxy_async_smem();
+      named_bar_sync(1, kEpiThreads);
+      if (t.epi_tid == 0) {
+        tma_store_2d(t.tma_g, buf, jtile + c * kStepCols, m0);
+        bulk_commit();
+      }
+      ++gstep;
     }
   }
 
   __device__ void end_unit(const Geom&) {}
+  __device__ void finish() {
+    if (t.epi_tid == 0) bulk_wait_all();
+  }
 };
 
 // ---- plain stores: dW rows (bf16), dH accumulation (fp32 -> bf16), test hook (fp32) ------------
@@ -283,23 +381,31 @@ struct StoreParams {
 
 struct StoreEpi {
   using Params = StoreParams;
+  static constexpr int kStages = 4;
+  static constexpr int kYSlots = 0;
+  static constexpr int kGSlots = 0;
   const Params& p;
   EpiThread t;
   int row;
 
-  __device__ StoreEpi(const Params& p_, EpiThread t_) : p(p_), t(t_) {}
+  __device__ StoreEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
   __device__ void begin_unit(const Geom&, int m_blk, int) { row = m_blk * BM + t.row_in_tile; }
 
-  __device__ void tile(const Geom&, int n_blk, uint32_t tmem_acc) {
-    const int col_base = n_blk * BN + t.half * (BN / 2);
+  __device__ void tile(const Geom&, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
+    const int col_base = n_blk * BN + t.half * 32;
     const bool row_ok = row < p.m_total && row >= p.m_begin;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < kSteps; ++c) {
       uint32_t raw[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
-      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(t.half * (BN / 2) + c * 32), raw);
+      __syncwarp();
+      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.half * 32), raw);
       tmem_ld_wait();
-      const int col0 = col_base + c * 32;
+      if (c == kSteps - 1) {
+        fence_before_sync();
+        __syncwarp();
+        if (t.lane == 0) mbar_arrive(tempty_bar);
+      }
+      const int col0 = col_base + c * kStepCols;
       const int ncols = p.n_total - col0 < 32 ? p.n_total - col0 : 32;
       if (!row_ok || ncols <= 0) continue;
       float v[32];
@@ -351,6 +457,7 @@ struct StoreEpi {
     }
   }
   __device__ void end_unit(const Geom&) {}
+  __device__ void finish() {}
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -358,22 +465,32 @@ struct StoreEpi {
 //   A: K-major  -> global [M rows][K] (K contiguous), one 64(k) x 128(m) box per stage
 //      MN-major -> global [K rows][M] (M contiguous), two 64(m) x 64(k) boxes per stage
 //   B: K-major  -> global [N rows][K], one 64 x 256 box;  MN-major -> [K rows][N], four 64 x 64 boxes
+//   tma_y : teacher logits [rows][V] (16-bit), 64-column x 128-row boxes into the y ring (warp 3)
+//   tma_g : gradient scratch [rows][v_chunk] bf16, 64 x 128 boxes stored from the g ring (epilogue)
 // ---------------------------------------------------------------------------------------------
 template <class Epi, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Geom g,
+kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_g, const Geom g,
                const typename Epi::Params ep) {
+  constexpr int kStages = Epi::kStages;
+  constexpr int kYSlots = Epi::kYSlots;
+  using Plan = SmemPlan<kStages, kYSlots, Epi::kGSlots>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   const uint32_t sA = base;
   const uint32_t sB = base + kStages * kABytes;
-  const uint32_t sBar = sB + kStages * kBBytes;
+  const uint32_t sY = base + Plan::kYOff;
+  const uint32_t sG = base + Plan::kGOff;
+  const uint32_t sBar = base + Plan::kBarOff;
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return sBar + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return sBar + 8u * (2 * kStages + 2 + s); };
-  const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4);
+  const uint32_t yfull0 = sBar + 8u * (2 * kStages + 4);
+  const uint32_t yempty0 = yfull0 + 8u * (kYSlots > 0 ? kYSlots : 1);
+  const uint32_t tmem_slot = sBar + 8u * Plan::kNumBars;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
@@ -382,6 +499,8 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
     prefetch_tmap(&tma_b);
+    if (kYSlots > 0) prefetch_tmap(&tma_y);
+    if (Epi::kGSlots > 0) prefetch_tmap(&tma_g);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -389,6 +508,10 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    for (int s = 0; s < kYSlots; ++s) {
+      mbar_init(yfull0 + 8u * s, 1);
+      mbar_init(yempty0 + 8u * s, kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -402,7 +525,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (A / B operand ring) =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -477,13 +600,42 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
+  } else if (warp == 3) {
+    // ================= teacher-tile producer (y ring) =================
+    if (kYSlots > 0 && lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+        int m_blk, range, n_begin, n_end;
+        decode_unit(g, u, m_blk, range, n_begin, n_end);
+        for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+          for (int c = 0; c < kSteps; ++c) {
+            mbar_wait(yempty0 + 8u * slot, phase ^ 1u);
+            const uint32_t fb = yfull0 + 8u * slot;
+            mbar_expect_tx(fb, kStepBytes);
+            tma_load_2d(sY + slot * kStepBytes, &tma_y, g.b_n0 + n_blk * BN + c * kStepCols, m_blk * BM, fb);
+            if (++slot == kYSlots) {
+              slot = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================= epilogue =================
     EpiThread et;
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     et.row_in_tile = q * 32 + lane;
     et.half = (warp - 4) >> 2;
+    et.lane = lane;
+    et.epi_tid = threadIdx.x - 128;
     et.tmem_lane_off = (uint32_t)(q * 32) << 16;
+    et.y_base = sY;
+    et.g_base = sG;
+    et.yfull0 = yfull0;
+    et.yempty0 = yempty0;
+    et.tma_g = &tma_g;
     Epi epi(ep, et);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -494,10 +646,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
         mbar_wait(tfull_bar(acc), acc_phase);
         fence_after_sync();
-        epi.tile(g, n_blk, tmem_base + (uint32_t)(acc * BN));
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        epi.tile(g, n_blk, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc));  // releases the buffer itself
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -505,6 +654,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       epi.end_unit(g);
     }
+    epi.finish();
   }
 
   fence_before_sync();
@@ -649,12 +799,13 @@ static int sm_count() {
 }
 
 template <class Epi, bool A_MN, bool B_MN>
-static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const typename Epi::Params& ep,
-                       cudaStream_t stream) {
+static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
+                       const Geom& g, const typename Epi::Params& ep, cudaStream_t stream) {
   auto kern = kd_umma_kernel<Epi, A_MN, B_MN>;
+  constexpr uint32_t smem = SmemPlan<Epi::kStages, Epi::kYSlots, Epi::kGSlots>::kBytes;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes),
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "kd_umma smem attribute"))
       return 1;
     attr_set = true;
@@ -664,8 +815,13 @@ static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom&
     return 1;
   }
   const int grid = g.num_units < sm_count() ? g.num_units : sm_count();
-  kern<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, g, ep);
+  kern<<<grid, kThreads, smem, stream>>>(ta, tb, ty, tg, g, ep);
   return check_cuda(cudaGetLastError(), "kd_umma launch");
+}
+template <class Epi, bool A_MN, bool B_MN>
+static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const typename Epi::Params& ep,
+                       cudaStream_t stream) {
+  return launch_umma<Epi, A_MN, B_MN>(ta, tb, ta, ta, g, ep, stream);  // no y / g rings: maps unused
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -727,16 +883,35 @@ static int check_common(const void* h, int64_t h_stride, const void* W, int64_t 
 }
 
 template <bool DENSE, typename TY>
-static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const FwdParams& fp, bool tau2,
-                      cudaStream_t s) {
-  if (tau2) return launch_umma<FwdEpi<TY, DENSE, true>, false, false>(ta, tb, g, fp, s);
-  return launch_umma<FwdEpi<TY, DENSE, false>, false, false>(ta, tb, g, fp, s);
+static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* ty, const Geom& g,
+                      const FwdParams& fp, bool tau2, cudaStream_t s) {
+  if constexpr (DENSE && sizeof(TY) == 2) {
+    if (ty != nullptr) {  // teacher tile staged by TMA
+      if (tau2) return launch_umma<FwdEpi<TY, true, true, true>, false, false>(ta, tb, *ty, ta, g, fp, s);
+      return launch_umma<FwdEpi<TY, true, false, true>, false, false>(ta, tb, *ty, ta, g, fp, s);
+    }
+  }
+  if (tau2) return launch_umma<FwdEpi<TY, DENSE, true, false>, false, false>(ta, tb, g, fp, s);
+  return launch_umma<FwdEpi<TY, DENSE, false, false>, false, false>(ta, tb, g, fp, s);
 }
 template <bool DENSE, typename TY>
-static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const GradParams& gp, bool tau2,
-                       cudaStream_t s) {
-  if (tau2) return launch_umma<GradEpi<TY, DENSE, true>, false, false>(ta, tb, g, gp, s);
-  return launch_umma<GradEpi<TY, DENSE, false>, false, false>(ta, tb, g, gp, s);
+static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* ty, const CUtensorMap& tg,
+                       const Geom& g, const GradParams& gp, bool tau2, cudaStream_t s) {
+  if constexpr (DENSE && sizeof(TY) == 2) {
+    if (ty != nullptr) {
+      if (tau2) return launch_umma<GradEpi<TY, true, true, true>, false, false>(ta, tb, *ty, tg, g, gp, s);
+      return launch_umma<GradEpi<TY, true, false, true>, false, false>(ta, tb, *ty, tg, g, gp, s);
+    }
+  }
+  if (tau2) return launch_umma<GradEpi<TY, DENSE, true, false>, false, false>(ta, tb, ta, tg, g, gp, s);
+  return launch_umma<GradEpi<TY, DENSE, false, false>, false, false>(ta, tb, ta, tg, g, gp, s);
+}
+
+// teacher logits as a TMA source: 16-bit, 16-byte aligned base and row stride; else the direct-load path
+static bool make_teacher_tmap(CUtensorMap* m, const void* y, int y_dtype, int64_t y_stride, int R, int V) {
+  if (!y || y_dtype != KD_DTYPE_BF16) return false;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) != 0 || (y_stride * 2) % 16 != 0) return false;
+  return make_tmap(m, y, (uint64_t)V, (uint64_t)R, (uint64_t)y_stride, BM, "teacher logits") == 0;
 }
 
 }  // namespace fused
@@ -802,11 +977,13 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
   fp.partials = partials;
   const bool tau2 = tau == 2.0f;
   int rc;
+  CUtensorMap ty;
+  const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&ty, y, y_dtype, y_stride, R, V);
   if (teacher_kind == KD_TEACHER_DENSE) {
-    rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, g, fp, tau2, s)
-                                  : launch_fwd<true, float>(ta, tb, g, fp, tau2, s);
+    rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, y_tma ? &ty : nullptr, g, fp, tau2, s)
+                                  : launch_fwd<true, float>(ta, tb, nullptr, g, fp, tau2, s);
   } else {
-    rc = launch_fwd<false, __nv_bfloat16>(ta, tb, g, fp, tau2, s);
+    rc = launch_fwd<false, __nv_bfloat16>(ta, tb, nullptr, g, fp, tau2, s);
   }
   if (rc) return rc;
 
@@ -870,7 +1047,8 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
   const size_t ys = y_dtype == KD_DTYPE_F32 ? 4 : 2;
   const int n_chunks = cdiv(V, vc);
 
-  CUtensorMap t_h_k, t_w_k, t_g_k, t_g_mn, t_h_mn, t_w_mn;
+  CUtensorMap t_h_k, t_w_k, t_g_k, t_g_mn, t_h_mn, t_w_mn, t_y;
+  const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&t_y, y, y_dtype, y_stride, R, V);
   if (make_tmap(&t_h_k, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
   if (make_tmap(&t_w_k, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, BN, "lm_head weight")) return 1;
   if (make_tmap(&t_g_k, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)")) return 1;
@@ -904,15 +1082,14 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       gp.use_kl = teacher_kind == KD_TEACHER_NONE ? 0 : 1;
       gp.n_norm = n_norm;
       gp.coef = grad_coef;
-      gp.G = G;
-      gp.ldg = vc;
       gp.v0 = v0;
       int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
-        rc = y_dtype == KD_DTYPE_BF16 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, s)
-                                      : launch_grad<true, float>(t_h_k, t_w_k, g, gp, tau2, s);
+        rc = y_dtype == KD_DTYPE_BF16
+                 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k, g, gp, tau2, s)
+                 : launch_grad<true, float>(t_h_k, t_w_k, nullptr, t_g_k, g, gp, tau2, s);
       } else {
-        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, g, gp, tau2, s);
+        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k, g, gp, tau2, s);
       }
       if (rc) return rc;
     }
