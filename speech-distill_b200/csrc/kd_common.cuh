@@ -214,7 +214,9 @@ __device__ __forceinline__ void student_update(const float (&f)[N], int nvalid, 
   s1 += p1[0] + p1[1];
 }
 
-template <bool TAU2, int N>
+// GUARD = true keeps p == 0 terms at exactly 0 even when the student logit is -inf (user-supplied logits,
+// K2); the fused path produces finite student logits and skips the select.
+template <bool TAU2, int N, bool GUARD = true>
 __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float (&fz)[N], int nvalid, float inv_tau,
                                                float& mt, float& t1, float& tt, float& a) {
   float vm = -CUDART_INF_F;
@@ -242,7 +244,11 @@ __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float
       // p = 0 contributes exactly 0 (xlogy semantics of nn.KLDivLoss, distillation_loss.py:68);
       // the clamp keeps 0 * (-inf - z) from producing NaN when the teacher holds -inf
       const float d = fmaxf(fy[i], -1e30f) - fz[i];
-      pa[i & 1] = (et > 0.f) ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
+      if (GUARD) {
+        pa[i & 1] = (et > 0.f) ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
+      } else {
+        pa[i & 1] = fmaf(et, d, pa[i & 1]);
+      }
     }
   }
   tt += pt[0] + pt[1];

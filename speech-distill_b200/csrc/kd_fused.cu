@@ -206,22 +206,31 @@ struct FwdEpi {
         if (t.lane == 0) mbar_arrive(tempty_bar);
       }
       if (target < 0 || ncols <= 0) continue;
+      if (DENSE && !kUseYRing) {
+        const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
+        load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
+      }
       float fz[32];
+      if (ncols >= 32) {  // common case: no per-element predicates in the hot loop
 #pragma unroll
-      for (int j = 0; j < 32; ++j) fz[j] = j < ncols ? __uint_as_float(raw[j]) : -CUDART_INF_F;
+        for (int j = 0; j < 32; ++j) fz[j] = __uint_as_float(raw[j]);
+      } else {            // ragged vocabulary edge (last column tile only)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) fz[j] = j < ncols ? __uint_as_float(raw[j]) : -CUDART_INF_F;
+      }
       const unsigned d = (unsigned)(target - col0);
-      if (d < 32u) {
+      if (d < 32u) {  // the label column lives in one step per row: rare
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j == (int)d) zl = fz[j];
       }
       student_update<TAU2, 32>(fz, 32, p.inv_tau, m, s1, st);
       if (DENSE) {
-        if (!kUseYRing) {
-          const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
-          load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
+        if (ncols >= 32) {
+          teacher_update<TAU2, 32, false>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
+        } else {  // masked columns hold -inf on both sides: keep their 0 * inf out of the cross term
+          teacher_update<TAU2, 32, true>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
         }
-        teacher_update<TAU2, 32>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
       }
     }
   }
@@ -326,7 +335,12 @@ struct GradEpi {
             gi = c1 * ex2(fmaf(z, kLog2e, -off1)) + c2 * ex2(fmaf(z, c_tau, -offt));
           }
           if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[j], c_tau, -offy)), gi);
-          gq[j] = j < ncols ? gi : 0.f;
+          gq[j] = gi;
+        }
+        if (ncols < 32) {  // ragged vocabulary edge: columns beyond V contribute nothing
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j >= ncols) gq[j] = 0.f;
         }
         const unsigned d = (unsigned)(target - col0);
         if (d < 32u) {
