@@ -43,15 +43,21 @@ constexpr int kSteps = BN / kStepCols;           // 4
 constexpr uint32_t kStepBytes = BM * kStepCols * 2;  // 16 KB: [128 rows x 64 cols] of a 16-bit type, 128 B rows
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
 
-// shared-memory plan of one kernel instantiation
-template <int STAGES, int YSLOTS, int GSLOTS>
+// shared-memory plan of one kernel instantiation: as many operand stages as fit beside the epilogue rings
+template <int CG, int YSLOTS, int GSLOTS>
 struct SmemPlan {
-  static constexpr uint32_t kPipeOff = 0;
-  static constexpr uint32_t kYOff = STAGES * kStageBytes;
+  static constexpr uint32_t kBBytesL = kBBytes / CG;
+  static constexpr uint32_t kStageL = kABytes + kBBytesL;
+  static constexpr uint32_t kRing = (YSLOTS + GSLOTS) * kStepBytes;
+  static constexpr uint32_t kBudget = 232448 - 1024 /*alignment slack*/ - 512 /*barriers*/;
+  static constexpr int kStagesRaw = (int)((kBudget - kRing) / kStageL);
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr uint32_t kYOff = kStages * kStageL;
   static constexpr uint32_t kGOff = kYOff + YSLOTS * kStepBytes;
   static constexpr uint32_t kBarOff = kGOff + GSLOTS * kStepBytes;
-  static constexpr uint32_t kNumBars = 2 * STAGES + 4 + 2 * (YSLOTS > 0 ? YSLOTS : 1);
-  static constexpr uint32_t kBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*alignment slack*/;
+  static constexpr uint32_t kNumBars = 2 * kStages + 4 + 2 * (YSLOTS > 0 ? YSLOTS : 1);
+  static constexpr uint32_t kBytes = kBarOff + 8 * kNumBars + 16 + 1024;
+  static_assert(kStages >= 3, "operand ring too shallow");
   static_assert(kBytes <= 232448, "shared memory plan exceeds 227 KB");
 };
 
@@ -84,6 +90,13 @@ struct EpiThread {
   uint32_t yfull0, yempty0;  // first barrier of each ring set (8 bytes apart)
   const CUtensorMap* tma_g;
 };
+
+// hand an accumulator buffer back to the MMA issuer (in the leader CTA for a CTA pair)
+template <int CG>
+__device__ __forceinline__ void release_tmem(uint32_t bar) {
+  if (CG == 2) mbar_arrive_cluster(bar);
+  else mbar_arrive(bar);
+}
 
 // address of this thread's q-th 16-byte piece inside a [128 x 64] 16-bit step buffer (SWIZZLE_128B)
 __device__ __forceinline__ uint32_t step_piece_addr(uint32_t buf, const EpiThread& t, int q) {
@@ -169,7 +182,6 @@ template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
 struct FwdEpi {
   using Params = FwdParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
-  static constexpr int kStages = kUseYRing ? 3 : 4;
   static constexpr int kYSlots = kUseYRing ? 4 : 0;
   static constexpr int kGSlots = 0;
   const Params& p;
@@ -180,14 +192,15 @@ struct FwdEpi {
 
   __device__ FwdEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
 
-  __device__ void begin_unit(const Geom&, int m_blk, int range_) {
-    row = m_blk * BM + t.row_in_tile;
+  __device__ void begin_unit(const Geom&, int m0, int range_) {
+    row = m0 + t.row_in_tile;
     range = range_;
     target = row < p.R ? p.row_target[row] : -1;
     m = mt = -CUDART_INF_F;
     s1 = st = t1 = tt = a = zl = 0.f;
   }
 
+  template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int col_base = g.b_n0 + n_blk * BN + t.half * 32;
 #pragma unroll 1
@@ -203,7 +216,7 @@ struct FwdEpi {
       if (c == kSteps - 1) {  // accumulator fully read: hand the TMEM buffer back before the math
         fence_before_sync();
         __syncwarp();
-        if (t.lane == 0) mbar_arrive(tempty_bar);
+        if (t.lane == 0) release_tmem<CG>(tempty_bar);
       }
       if (target < 0 || ncols <= 0) continue;
       if (DENSE && !kUseYRing) {
@@ -264,7 +277,6 @@ template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
 struct GradEpi {
   using Params = GradParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
-  static constexpr int kStages = kUseYRing ? 3 : 4;
   static constexpr int kYSlots = kUseYRing ? 3 : 0;
   static constexpr int kGSlots = 2;
   const Params& p;
@@ -282,8 +294,8 @@ struct GradEpi {
     c_tau = kLog2e / p.tau;
   }
 
-  __device__ void begin_unit(const Geom&, int m_blk, int) {
-    m0 = m_blk * BM;
+  __device__ void begin_unit(const Geom&, int m0_, int) {
+    m0 = m0_;
     row = m0 + t.row_in_tile;
     target = row < p.R ? p.row_target[row] : -1;
     if (target >= 0) {
@@ -296,6 +308,7 @@ struct GradEpi {
     }
   }
 
+  template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int jtile = n_blk * BN;  // first scratch column of this tile
 #pragma unroll 1
@@ -312,7 +325,7 @@ struct GradEpi {
       if (c == kSteps - 1) {
         fence_before_sync();
         __syncwarp();
-        if (t.lane == 0) mbar_arrive(tempty_bar);
+        if (t.lane == 0) release_tmem<CG>(tempty_bar);
       }
       uint4 pk[4];
       if (target < 0 || ncols <= 0) {
@@ -395,7 +408,6 @@ struct StoreParams {
 
 struct StoreEpi {
   using Params = StoreParams;
-  static constexpr int kStages = 4;
   static constexpr int kYSlots = 0;
   static constexpr int kGSlots = 0;
   const Params& p;
@@ -403,8 +415,9 @@ struct StoreEpi {
   int row;
 
   __device__ StoreEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
-  __device__ void begin_unit(const Geom&, int m_blk, int) { row = m_blk * BM + t.row_in_tile; }
+  __device__ void begin_unit(const Geom&, int m0, int) { row = m0 + t.row_in_tile; }
 
+  template <int CG>
   __device__ void tile(const Geom&, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int col_base = n_blk * BN + t.half * 32;
     const bool row_ok = row < p.m_total && row >= p.m_begin;
@@ -417,7 +430,7 @@ struct StoreEpi {
       if (c == kSteps - 1) {
         fence_before_sync();
         __syncwarp();
-        if (t.lane == 0) mbar_arrive(tempty_bar);
+        if (t.lane == 0) release_tmem<CG>(tempty_bar);
       }
       const int col0 = col_base + c * kStepCols;
       const int ncols = p.n_total - col0 < 32 ? p.n_total - col0 : 32;
@@ -475,21 +488,28 @@ struct StoreEpi {
 };
 
 // ---------------------------------------------------------------------------------------------
-// The persistent warp-specialised GEMM.
+// The persistent warp-specialised GEMM.  CG = 1: one CTA per 128 x 256 tile.  CG = 2: a CTA pair
+// (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile - each CTA stages its own 128 rows of A and
+// HALF of the B tile, the leader CTA issues one MMA for both tensor cores, and each CTA's epilogue
+// drains its own 128 accumulator rows.  The pair halves the L2 -> smem traffic of B and the smem
+// bytes per stage (32 KB instead of 48 KB), which buys the deeper operand ring the epilogue rings need.
 //   A: K-major  -> global [M rows][K] (K contiguous), one 64(k) x 128(m) box per stage
 //      MN-major -> global [K rows][M] (M contiguous), two 64(m) x 64(k) boxes per stage
-//   B: K-major  -> global [N rows][K], one 64 x 256 box;  MN-major -> [K rows][N], four 64 x 64 boxes
+//   B: K-major  -> global [N rows][K], one 64 x (256/CG) box;  MN-major -> [K rows][N], 64 x 64 boxes
 //   tma_y : teacher logits [rows][V] (16-bit), 64-column x 128-row boxes into the y ring (warp 3)
 //   tma_g : gradient scratch [rows][v_chunk] bf16, 64 x 128 boxes stored from the g ring (epilogue)
 // ---------------------------------------------------------------------------------------------
-template <class Epi, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <class Epi, bool A_MN, bool B_MN, int CG>
+__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(kThreads, 1)
 kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_g, const Geom g,
                const typename Epi::Params ep) {
-  constexpr int kStages = Epi::kStages;
+  using Plan = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots>;
+  constexpr int kStages = Plan::kStages;
   constexpr int kYSlots = Epi::kYSlots;
-  using Plan = SmemPlan<kStages, kYSlots, Epi::kGSlots>;
+  constexpr uint32_t kBBytesL = Plan::kBBytesL;      // this CTA's share of the B tile
+  constexpr uint32_t kStageBytesL = kABytes + kBBytesL;
+  constexpr int BNL = BN / CG;                       // B rows (n) staged by this CTA
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -509,6 +529,10 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
@@ -516,12 +540,12 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (kYSlots > 0) prefetch_tmap(&tma_y);
     if (Epi::kGSlots > 0) prefetch_tmap(&tma_g);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), CG);   // one arrive.expect_tx per CTA of the pair (leader's copy is the live one)
+      mbar_init(empty_bar(s), 1);   // one (multicast) MMA commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);
+      mbar_init(tempty_bar(s), kEpiWarps * CG);  // epilogue warps of both CTAs release the leader's MMA
     }
     for (int s = 0; s < kYSlots; ++s) {
       mbar_init(yfull0 + 8u * s, 1);
@@ -529,9 +553,15 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     fence_mbar_init();
   }
+  if (CG == 2) cluster_sync_all();  // peer barriers exist before any remote arrive / TMA signal
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -543,28 +573,49 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+      for (int u = unit0; u < g.num_units; u += unit_step) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
+        const int m_row = g.a_m0 + (m_blk * CG + (int)cta_rank) * BM;
         for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+          const int n_row = g.b_n0 + n_blk * BN + (int)cta_rank * BNL;
           for (int kb = 0; kb < g.num_k_blk; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t fb = full_bar(stage);
-            mbar_expect_tx(fb, kStageBytes);
-            const uint32_t a_dst = sA + stage * kABytes, b_dst = sB + stage * kBBytes;
-            if (!A_MN) {
-              tma_load_2d(a_dst, &tma_a, g.a_k0 + kb * BK, g.a_m0 + m_blk * BM, fb);
-            } else {
+            const uint32_t a_dst = sA + stage * kABytes, b_dst = sB + stage * kBBytesL;
+            if (CG == 1) {
+              const uint32_t fb = full_bar(stage);
+              mbar_expect_tx(fb, kStageBytesL);
+              if (!A_MN) {
+                tma_load_2d(a_dst, &tma_a, g.a_k0 + kb * BK, m_row, fb);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d(a_dst + j * kBoxMnBytes, &tma_a, g.a_m0 + m_blk * BM + 64 * j, g.a_k0 + kb * BK, fb);
-            }
-            if (!B_MN) {
-              tma_load_2d(b_dst, &tma_b, g.b_k0 + kb * BK, g.b_n0 + n_blk * BN, fb);
-            } else {
+                for (int j = 0; j < BM / 64; ++j)
+                  tma_load_2d(a_dst + j * kBoxMnBytes, &tma_a, m_row + 64 * j, g.a_k0 + kb * BK, fb);
+              }
+              if (!B_MN) {
+                tma_load_2d(b_dst, &tma_b, g.b_k0 + kb * BK, n_row, fb);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(b_dst + j * kBoxMnBytes, &tma_b, g.b_n0 + n_blk * BN + 64 * j, g.b_k0 + kb * BK, fb);
+                for (int j = 0; j < BNL / 64; ++j)
+                  tma_load_2d(b_dst + j * kBoxMnBytes, &tma_b, n_row + 64 * j, g.b_k0 + kb * BK, fb);
+              }
+            } else {
+              const uint32_t fb = mapa(full_bar(stage), 0);  // the leader's full barrier counts both CTAs' bytes
+              mbar_expect_tx_cluster(fb, kStageBytesL);
+              if (!A_MN) {
+                tma_load_2d_cg2(a_dst, &tma_a, g.a_k0 + kb * BK, m_row, fb);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BM / 64; ++j)
+                  tma_load_2d_cg2(a_dst + j * kBoxMnBytes, &tma_a, m_row + 64 * j, g.a_k0 + kb * BK, fb);
+              }
+              if (!B_MN) {
+                tma_load_2d_cg2(b_dst, &tma_b, g.b_k0 + kb * BK, n_row, fb);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BNL / 64; ++j)
+                  tma_load_2d_cg2(b_dst + j * kBoxMnBytes, &tma_b, n_row + 64 * j, g.b_k0 + kb * BK, fb);
+              }
             }
             if (++stage == kStages) {
               stage = 0;
@@ -575,16 +626,16 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_bf16(BM, BN, A_MN, B_MN);
+    // ================= MMA issuer (leader CTA of the pair only) =================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = instr_desc_bf16(BM * CG, BN, A_MN, B_MN);
       constexpr uint64_t a_base = A_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
       constexpr uint64_t b_base = B_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 elements
       constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+      for (int u = unit0; u < g.num_units; u += unit_step) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
@@ -594,19 +645,24 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int kb = 0; kb < g.num_k_blk; ++kb) {
             mbar_wait(full_bar(stage), phase);
             fence_after_sync();
-            const uint32_t a_src = sA + stage * kABytes, b_src = sB + stage * kBBytes;
+            const uint32_t a_src = sA + stage * kABytes, b_src = sB + stage * kBBytesL;
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
-              mma_bf16(d_tmem, smem_desc(a_base, a_src + k * a_kstep), smem_desc(b_base, b_src + k * b_kstep), idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+              const uint64_t da = smem_desc(a_base, a_src + k * a_kstep), db = smem_desc(b_base, b_src + k * b_kstep);
+              if (CG == 2) mma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+            // frees the smem slot (in both CTAs) when these MMAs retire
+            if (CG == 2) mma_commit_cg2(empty_bar(stage), 3);
+            else mma_commit(empty_bar(stage));
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          // accumulator complete -> epilogue (of both CTAs)
+          if (CG == 2) mma_commit_cg2(tfull_bar(acc), 3);
+          else mma_commit(tfull_bar(acc));
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1u;
@@ -615,19 +671,20 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp == 3) {
-    // ================= teacher-tile producer (y ring) =================
+    // ================= teacher-tile producer (y ring, local to each CTA) =================
     if (kYSlots > 0 && lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+      for (int u = unit0; u < g.num_units; u += unit_step) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
+        const int m_row = (m_blk * CG + (int)cta_rank) * BM;
         for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
           for (int c = 0; c < kSteps; ++c) {
             mbar_wait(yempty0 + 8u * slot, phase ^ 1u);
             const uint32_t fb = yfull0 + 8u * slot;
             mbar_expect_tx(fb, kStepBytes);
-            tma_load_2d(sY + slot * kStepBytes, &tma_y, g.b_n0 + n_blk * BN + c * kStepCols, m_blk * BM, fb);
+            tma_load_2d(sY + slot * kStepBytes, &tma_y, g.b_n0 + n_blk * BN + c * kStepCols, m_row, fb);
             if (++slot == kYSlots) {
               slot = 0;
               phase ^= 1u;
@@ -637,7 +694,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
+    // ================= epilogue (each CTA drains its own 128 accumulator rows) =================
     EpiThread et;
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     et.row_in_tile = q * 32 + lane;
@@ -653,14 +710,16 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     Epi epi(ep, et);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < g.num_units; u += gridDim.x) {
+    for (int u = unit0; u < g.num_units; u += unit_step) {
       int m_blk, range, n_begin, n_end;
       decode_unit(g, u, m_blk, range, n_begin, n_end);
-      epi.begin_unit(g, m_blk, range);
+      epi.begin_unit(g, (m_blk * CG + (int)cta_rank) * BM, range);
       for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
         mbar_wait(tfull_bar(acc), acc_phase);
         fence_after_sync();
-        epi.tile(g, n_blk, tmem_base + (uint32_t)(acc * BN), tempty_bar(acc));  // releases the buffer itself
+        // the policy releases the TMEM buffer itself (arrive on the leader's tempty barrier)
+        const uint32_t rel = CG == 2 ? mapa(tempty_bar(acc), 0) : tempty_bar(acc);
+        epi.template tile<CG>(g, n_blk, tmem_base + (uint32_t)(acc * BN), rel);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -671,11 +730,14 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     epi.finish();
   }
 
+  __syncwarp();
   fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still read this CTA's smem / signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -812,11 +874,21 @@ static int sm_count() {
   return n;
 }
 
-template <class Epi, bool A_MN, bool B_MN>
-static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
-                       const Geom& g, const typename Epi::Params& ep, cudaStream_t stream) {
-  auto kern = kd_umma_kernel<Epi, A_MN, B_MN>;
-  constexpr uint32_t smem = SmemPlan<Epi::kStages, Epi::kYSlots, Epi::kGSlots>::kBytes;
+// CTA-pair mode (tcgen05 cta_group::2) is the default; KD_UMMA_CTA_GROUP=1 selects the single-CTA kernels
+static int cta_group() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("KD_UMMA_CTA_GROUP");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
+template <class Epi, bool A_MN, bool B_MN, int CG>
+static int launch_umma_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
+                          const Geom& g, const typename Epi::Params& ep, cudaStream_t stream) {
+  auto kern = kd_umma_kernel<Epi, A_MN, B_MN, CG>;
+  constexpr uint32_t smem = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots>::kBytes;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -828,9 +900,16 @@ static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     set_error("kd_umma: empty problem (units=%d, k blocks=%d)", g.num_units, g.num_k_blk);
     return 1;
   }
-  const int grid = g.num_units < sm_count() ? g.num_units : sm_count();
+  const int slots = sm_count() / CG;  // persistent: one CTA (pair) per SM (pair)
+  const int grid = (g.num_units < slots ? g.num_units : slots) * CG;
   kern<<<grid, kThreads, smem, stream>>>(ta, tb, ty, tg, g, ep);
   return check_cuda(cudaGetLastError(), "kd_umma launch");
+}
+template <class Epi, bool A_MN, bool B_MN>
+static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
+                       const Geom& g, const typename Epi::Params& ep, cudaStream_t stream) {
+  if (cta_group() == 2) return launch_umma_cg<Epi, A_MN, B_MN, 2>(ta, tb, ty, tg, g, ep, stream);
+  return launch_umma_cg<Epi, A_MN, B_MN, 1>(ta, tb, ty, tg, g, ep, stream);
 }
 template <class Epi, bool A_MN, bool B_MN>
 static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom& g, const typename Epi::Params& ep,
@@ -839,6 +918,8 @@ static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const Geom&
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int tile_m() { return BM * cta_group(); }     // rows of C per work tile
+static inline int b_box_rows() { return BN / cta_group(); }  // rows of a K-major B box (per CTA)
 
 // ---- workspace layout -----------------------------------------------------------------------------
 constexpr int kFwdTilesPerRange = 4;
@@ -970,9 +1051,9 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
 
   CUtensorMap ta, tb;
   if (make_tmap(&ta, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
-  if (make_tmap(&tb, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, BN, "lm_head weight")) return 1;
+  if (make_tmap(&tb, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, b_box_rows(), "lm_head weight")) return 1;
   Geom g = {};
-  g.num_m_blk = cdiv(R, BM);
+  g.num_m_blk = cdiv(R, tile_m());
   g.num_n_blk = cdiv(V, BN);
   g.num_k_blk = cdiv(H, BK);
   g.n_per_unit = kFwdTilesPerRange;
@@ -1064,7 +1145,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
   CUtensorMap t_h_k, t_w_k, t_g_k, t_g_mn, t_h_mn, t_w_mn, t_y;
   const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&t_y, y, y_dtype, y_stride, R, V);
   if (make_tmap(&t_h_k, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
-  if (make_tmap(&t_w_k, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, BN, "lm_head weight")) return 1;
+  if (make_tmap(&t_w_k, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, b_box_rows(), "lm_head weight")) return 1;
   if (make_tmap(&t_g_k, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)")) return 1;
   if (make_tmap(&t_g_mn, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, 64, "G (MN-major)")) return 1;
   if (make_tmap(&t_h_mn, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, 64, "hidden (MN-major)")) return 1;
@@ -1078,7 +1159,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
     // ---- 1. recompute logits tile, form G ----
     {
       Geom g = {};
-      g.num_m_blk = cdiv(R, BM);
+      g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = n_blks;
       g.num_k_blk = cdiv(H, BK);
       g.b_n0 = v0;
@@ -1110,7 +1191,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
     // ---- 2. dW[v0 : v0+cols, :] = G^T h   (rows are final: every token is in this GEMM's K) ----
     if (need_dw) {
       Geom g = {};
-      g.num_m_blk = cdiv(n_blks * BN, BM);
+      g.num_m_blk = cdiv(n_blks * BN, tile_m());
       g.num_n_blk = cdiv(H, BN);
       g.num_k_blk = cdiv(R, BK);
       g.n_per_unit = 1;
@@ -1132,7 +1213,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
     // ---- 3. dH (+)= G W[v0 : v0+cols, :] ----
     if (dH) {
       Geom g = {};
-      g.num_m_blk = cdiv(R, BM);
+      g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = cdiv(H, BN);
       g.num_k_blk = n_blks * (BN / BK);
       g.b_k0 = v0;
@@ -1175,10 +1256,10 @@ extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   if (b_mn_major) {
     if (make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, "B (MN-major)")) return 1;
   } else {
-    if (make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BN, "B (K-major)")) return 1;
+    if (make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, b_box_rows(), "B (K-major)")) return 1;
   }
   Geom g = {};
-  g.num_m_blk = cdiv(M, BM);
+  g.num_m_blk = cdiv(M, tile_m());
   g.num_n_blk = cdiv(N, BN);
   g.num_k_blk = cdiv(K, BK);
   g.n_per_unit = 1;
