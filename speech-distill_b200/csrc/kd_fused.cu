@@ -30,17 +30,20 @@ namespace fused {
 using namespace umma;
 
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = 32 * kEpiWarps;      // 256
-constexpr int kThreads = 128 + kEpiThreads;      // 384
+constexpr int kEpiWarps = 16;                    // 4 per TMEM lane quadrant = 4 per warp scheduler
+constexpr int kEpiThreads = 32 * kEpiWarps;      // 512
+constexpr int kThreads = 128 + kEpiThreads;      // 640 (<= 96 registers per thread)
+constexpr int kColGroups = kEpiWarps / 4;        // column groups working on one step side by side
 constexpr uint32_t kABytes = BM * BK * 2;        // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 2;        // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kBoxMnBytes = 64 * BK * 2;    // one 64(mn) x 64(k) MN-major box = 8 KB
 constexpr uint32_t kTmemCols = 512;
-constexpr int kStepCols = 64;                    // columns per epilogue step: 32 for each column half
-constexpr int kSteps = BN / kStepCols;           // 4
-constexpr uint32_t kStepBytes = BM * kStepCols * 2;  // 16 KB: [128 rows x 64 cols] of a 16-bit type, 128 B rows
+constexpr int kStepCols = 32 * kColGroups;       // columns per epilogue step: 32 for each column group (128)
+constexpr int kSteps = BN / kStepCols;           // 2
+constexpr int kStepBoxes = kStepCols / 64;       // 64-column (128-byte row) TMA boxes per step
+constexpr uint32_t kBoxBytes = BM * 64 * 2;      // 16 KB: [128 rows x 64 cols] of a 16-bit type, swizzled 128 B rows
+constexpr uint32_t kStepBytes = kStepBoxes * kBoxBytes;  // 32 KB
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
 
 // shared-memory plan of one kernel instantiation: as many operand stages as fit beside the epilogue rings
@@ -57,7 +60,7 @@ struct SmemPlan {
   static constexpr uint32_t kBarOff = kGOff + GSLOTS * kStepBytes;
   static constexpr uint32_t kNumBars = 2 * kStages + 4 + 2 * (YSLOTS > 0 ? YSLOTS : 1);
   static constexpr uint32_t kBytes = kBarOff + 8 * kNumBars + 16 + 1024;
-  static_assert(kStages >= 3, "operand ring too shallow");
+  static_assert(kStages >= 2, "operand ring too shallow");  // 2 only for the single-CTA fallback of GradEpi
   static_assert(kBytes <= 232448, "shared memory plan exceeds 227 KB");
 };
 
@@ -82,9 +85,9 @@ __host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, in
 // ---------------------------------------------------------------------------------------------
 struct EpiThread {
   int row_in_tile;         // 0..127 (TMEM lane)
-  int half;                // 0/1
+  int cgrp;                // column group 0..kColGroups-1: columns [32 cgrp, +32) of every step
   int lane;                // lane in warp
-  int epi_tid;             // 0..255
+  int epi_tid;             // 0..kEpiThreads-1
   uint32_t tmem_lane_off;  // lane field of the TMEM address
   uint32_t y_base, g_base; // smem rings (teacher tile in, gradient tile out)
   uint32_t yfull0, yempty0;  // first barrier of each ring set (8 bytes apart)
@@ -98,74 +101,79 @@ __device__ __forceinline__ void release_tmem(uint32_t bar) {
   else mbar_arrive(bar);
 }
 
-// address of this thread's q-th 16-byte piece inside a [128 x 64] 16-bit step buffer (SWIZZLE_128B)
+// address of this thread's q-th 16-byte piece (q = 0..3: its 32 columns) inside a step buffer made of
+// kStepBoxes [128 x 64] 16-bit boxes with SWIZZLE_128B rows
 __device__ __forceinline__ uint32_t step_piece_addr(uint32_t buf, const EpiThread& t, int q) {
-  return buf + (uint32_t)t.row_in_tile * 128u + ((uint32_t)((t.half * 4 + q) ^ (t.row_in_tile & 7)) << 4);
+  return buf + (uint32_t)(t.cgrp >> 1) * kBoxBytes + (uint32_t)t.row_in_tile * 128u +
+         ((uint32_t)(((t.cgrp & 1) * 4 + q) ^ (t.row_in_tile & 7)) << 4);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 
 template <typename TY>
-__device__ __forceinline__ void load_row32(const TY* __restrict__ p, bool vec_ok, int ncols, float (&f)[32]) {
-  // direct global path; ncols = number of in-range columns (<= 32); out-of-range columns read as -inf
-  if (vec_ok && ncols >= 32) {
-    if constexpr (sizeof(TY) == 2) {
+__device__ __forceinline__ void load_row16(const TY* __restrict__ p, bool vec_ok, int ncols, float (&f)[16]) {
+  // direct global path; ncols = number of in-range columns (<= 16); out-of-range columns read as -inf
+  if (vec_ok && ncols >= 16) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        Vec8<TY> v;
-        v.load_global(p + 8 * q);
-        float t[8];
-        v.unpack(t);
+    for (int q = 0; q < 2; ++q) {
+      Vec8<TY> v;
+      v.load_global(p + 8 * q);
+      float t8[8];
+      v.unpack(t8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[8 * q + j] = t[j];
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        Vec8<float> v;
-        v.load_global(reinterpret_cast<const float*>(p) + 8 * q);
-        float t[8];
-        v.unpack(t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[8 * q + j] = t[j];
-      }
+      for (int j = 0; j < 8; ++j) f[8 * q + j] = t8[j];
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = j < ncols ? Elem<TY>::to_f(p[j]) : -CUDART_INF_F;
+    for (int j = 0; j < 16; ++j) f[j] = j < ncols ? Elem<TY>::to_f(p[j]) : -CUDART_INF_F;
   }
 }
 
 // consumer side of the teacher-tile ring: wait for the step buffer, pull this thread's 64 bytes, release
-template <typename TY>
 struct YRing {
   int slot = 0;
   uint32_t phase = 0;
   template <int SLOTS>
-  __device__ __forceinline__ void take(const EpiThread& t, int ncols, float (&fy)[32]) {
-    static_assert(sizeof(TY) == 2, "the TMA-staged teacher path is for 16-bit logits");
+  __device__ __forceinline__ void take(const EpiThread& t, uint4 (&pk)[4]) {
     mbar_wait(t.yfull0 + 8u * slot, phase);
     const uint32_t buf = t.y_base + (uint32_t)slot * kStepBytes;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      Vec8<TY> v;
-      v.a = lds128(step_piece_addr(buf, t, q));
-      float f8[8];
-      v.unpack(f8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) fy[8 * q + j] = f8[j];
-    }
+    for (int q = 0; q < 4; ++q) pk[q] = lds128(step_piece_addr(buf, t, q));
     __syncwarp();
     if (t.lane == 0) mbar_arrive(t.yempty0 + 8u * slot);
     if (++slot == SLOTS) {
       slot = 0;
       phase ^= 1u;
     }
-    if (ncols < 32) {  // ragged vocabulary edge: TMA zero-filled the out-of-range columns
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j >= ncols) fy[j] = -CUDART_INF_F;
-    }
   }
 };
+
+// 16 teacher logits of sub-chunk `sub` (0/1) from the 64 packed bytes; columns >= ncols read as -inf
+template <typename TY>
+__device__ __forceinline__ void unpack_sub(const uint4 (&pk)[4], int sub, int ncols, float (&fy)[16]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    Vec8<TY> v;
+    v.a = sub == 0 ? pk[q] : pk[2 + q];
+    float f8[8];
+    v.unpack(f8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fy[8 * q + j] = f8[j];
+  }
+  if (ncols < 16) {  // ragged vocabulary edge: TMA zero-filled the out-of-range columns
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j >= ncols) fy[j] = -CUDART_INF_F;
+  }
+}
 
 // ---- forward: online statistics -------------------------------------------------------------
 struct FwdParams {
@@ -175,20 +183,21 @@ struct FwdParams {
   int y_vec_ok;
   int R, V;
   float inv_tau;
-  float* partials;  // [num_ranges * 2][R][kRecFloats]
+  float* partials;  // [num_ranges * kColGroups][R][kRecFloats]
+  int debug_skip_math;  // KD_DEBUG_SKIP_MATH=1: bring-up knob that measures the pipeline without the epilogue math
 };
 
 template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
 struct FwdEpi {
   using Params = FwdParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
-  static constexpr int kYSlots = kUseYRing ? 4 : 0;
+  static constexpr int kYSlots = kUseYRing ? 2 : 0;
   static constexpr int kGSlots = 0;
   const Params& p;
   EpiThread t;
   int row, target, range;
   float m, s1, st, mt, t1, tt, a, zl;
-  YRing<__nv_bfloat16> ring;  // 16-bit teacher only (TY is bf16 on this path)
+  YRing ring;
 
   __device__ FwdEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
 
@@ -200,57 +209,75 @@ struct FwdEpi {
     s1 = st = t1 = tt = a = zl = 0.f;
   }
 
+  // 16 columns of one row: label pick-up, student statistics, teacher statistics
+  __device__ __forceinline__ void sub_chunk(const uint32_t (&raw)[16], float (&fy)[16], int col0, int ncols) {
+    float fz[16];
+    if (ncols >= 16) {  // common case: no per-element predicates in the hot loop
+#pragma unroll
+      for (int j = 0; j < 16; ++j) fz[j] = __uint_as_float(raw[j]);
+    } else {            // ragged vocabulary edge (last column tile only)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) fz[j] = j < ncols ? __uint_as_float(raw[j]) : -CUDART_INF_F;
+    }
+    const unsigned d = (unsigned)(target - col0);
+    if (d < 16u) {  // the label column lives in one sub-chunk per row: rare
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j == (int)d) zl = fz[j];
+    }
+    student_update<TAU2, 16>(fz, 16, p.inv_tau, m, s1, st);
+    if (DENSE) {
+      if (ncols >= 16) {
+        teacher_update<TAU2, 16, false>(fy, fz, 16, p.inv_tau, mt, t1, tt, a);
+      } else {  // masked columns hold -inf on both sides: keep their 0 * inf out of the cross term
+        teacher_update<TAU2, 16, true>(fy, fz, 16, p.inv_tau, mt, t1, tt, a);
+      }
+    }
+  }
+
   template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
-    const int col_base = g.b_n0 + n_blk * BN + t.half * 32;
+    const int col_base = g.b_n0 + n_blk * BN + t.cgrp * 32;
 #pragma unroll 1
     for (int c = 0; c < kSteps; ++c) {
-      uint32_t raw[32];
+      uint32_t raw0[16], raw1[16];
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent row predicates
-      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.half * 32), raw);
-      const int col0 = col_base + c * kStepCols;
-      const int ncols = p.V - col0 < 32 ? p.V - col0 : 32;
-      float fy[32];
-      if (kUseYRing) ring.template take<kYSlots>(t, ncols, fy);
+      const uint32_t taddr = tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.cgrp * 32);
+      tmem_ld16(taddr, raw0);
+      tmem_ld16(taddr + 16u, raw1);
+      uint4 pk[4];
+      if (kUseYRing) ring.template take<kYSlots>(t, pk);
       tmem_ld_wait();
       if (c == kSteps - 1) {  // accumulator fully read: hand the TMEM buffer back before the math
         fence_before_sync();
         __syncwarp();
         if (t.lane == 0) release_tmem<CG>(tempty_bar);
       }
-      if (target < 0 || ncols <= 0) continue;
-      if (DENSE && !kUseYRing) {
-        const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
-        load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
-      }
-      float fz[32];
-      if (ncols >= 32) {  // common case: no per-element predicates in the hot loop
+      const int col0 = col_base + c * kStepCols;
+      const int nrem = p.V - col0;
+      if (target < 0 || nrem <= 0 || p.debug_skip_math) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) fz[j] = __uint_as_float(raw[j]);
-      } else {            // ragged vocabulary edge (last column tile only)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) fz[j] = j < ncols ? __uint_as_float(raw[j]) : -CUDART_INF_F;
-      }
-      const unsigned d = (unsigned)(target - col0);
-      if (d < 32u) {  // the label column lives in one step per row: rare
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j == (int)d) zl = fz[j];
-      }
-      student_update<TAU2, 32>(fz, 32, p.inv_tau, m, s1, st);
-      if (DENSE) {
-        if (ncols >= 32) {
-          teacher_update<TAU2, 32, false>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
-        } else {  // masked columns hold -inf on both sides: keep their 0 * inf out of the cross term
-          teacher_update<TAU2, 32, true>(fy, fz, 32, p.inv_tau, mt, t1, tt, a);
+      for (int sub = 0; sub < 2; ++sub) {
+        const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
+        if (nc <= 0) break;
+        float fy[16];
+        if (DENSE) {
+          if (kUseYRing) {
+            unpack_sub<__nv_bfloat16>(pk, sub, nc, fy);
+          } else {
+            const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0 + 16 * sub;
+            load_row16<TY>(yp, p.y_vec_ok != 0, nc, fy);
+          }
         }
+        if (sub == 0) sub_chunk(raw0, fy, col0, nc);
+        else sub_chunk(raw1, fy, col0 + 16, nc);
       }
     }
   }
 
   __device__ void end_unit(const Geom&) {
     if (row < p.R) {
-      float* rec = p.partials + ((size_t)(range * 2 + t.half) * p.R + row) * kRecFloats;
+      float* rec = p.partials + ((size_t)(range * kColGroups + t.cgrp) * p.R + row) * kRecFloats;
       *reinterpret_cast<float4*>(rec) = make_float4(m, s1, st, mt);
       *reinterpret_cast<float4*>(rec + 4) = make_float4(t1, tt, a, zl);
     }
@@ -277,14 +304,13 @@ template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
 struct GradEpi {
   using Params = GradParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
-  static constexpr int kYSlots = kUseYRing ? 3 : 0;
-  static constexpr int kGSlots = 2;
+  static constexpr int kYSlots = kUseYRing ? 2 : 0;
+  static constexpr int kGSlots = 1;
   const Params& p;
   EpiThread t;
   int row, target, m0;
-  uint32_t gstep = 0;
   float c1, c2, c_tau, off1, offt, offy, half_off1, k_tau;
-  YRing<__nv_bfloat16> ring;
+  YRing ring;
 
   __device__ GradEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {
     const int nn = *p.n_norm;
@@ -308,82 +334,103 @@ struct GradEpi {
     }
   }
 
+  // gradient of 16 columns -> two packed 16-byte pieces
+  __device__ __forceinline__ void sub_chunk(const uint32_t (&raw)[16], const float (&fy)[16], int col0, int ncols,
+                                            uint4& lo, uint4& hi) {
+    float gq[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float z = __uint_as_float(raw[j]);
+      float gi;
+      if (TAU2) {
+        const float e = ex2(fmaf(z, c_tau, -half_off1));
+        gi = e * fmaf(e, c1, k_tau);
+      } else {
+        gi = c1 * ex2(fmaf(z, kLog2e, -off1)) + c2 * ex2(fmaf(z, c_tau, -offt));
+      }
+      if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[j], c_tau, -offy)), gi);
+      gq[j] = gi;
+    }
+    if (ncols < 16) {  // ragged vocabulary edge: columns beyond V contribute nothing
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j >= ncols) gq[j] = 0.f;
+    }
+    const unsigned d = (unsigned)(target - col0);
+    if (d < 16u) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j == (int)d) gq[j] -= c1;
+    }
+    float t8[8];
+    Vec8<__nv_bfloat16> v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t8[j] = gq[j];
+    v.pack(t8);
+    lo = v.a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t8[j] = gq[8 + j];
+    v.pack(t8);
+    hi = v.a;
+  }
+
   template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int jtile = n_blk * BN;  // first scratch column of this tile
 #pragma unroll 1
     for (int c = 0; c < kSteps; ++c) {
-      uint32_t raw[32];
+      uint32_t raw0[16], raw1[16];
       __syncwarp();
-      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.half * 32), raw);
-      const int j0 = jtile + c * kStepCols + t.half * 32;
-      const int col0 = p.v0 + j0;
-      const int ncols = p.V - col0 < 32 ? p.V - col0 : 32;
-      float fy[32];
-      if (kUseYRing) ring.template take<kYSlots>(t, ncols, fy);
+      const uint32_t taddr = tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.cgrp * 32);
+      tmem_ld16(taddr, raw0);
+      tmem_ld16(taddr + 16u, raw1);
+      uint4 pk[4];
+      if (kUseYRing) ring.template take<kYSlots>(t, pk);
       tmem_ld_wait();
       if (c == kSteps - 1) {
         fence_before_sync();
         __syncwarp();
         if (t.lane == 0) release_tmem<CG>(tempty_bar);
       }
-      uint4 pk[4];
-      if (target < 0 || ncols <= 0) {
+      const int j0 = jtile + c * kStepCols + t.cgrp * 32;
+      const int col0 = p.v0 + j0;
+      const int nrem = p.V - col0;
+      uint4 out[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pk[q] = make_uint4(0, 0, 0, 0);
-      } else {
-        if (DENSE && !kUseYRing) {
-          const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0;
-          load_row32<TY>(yp, p.y_vec_ok != 0, ncols, fy);
-        }
-        float gq[32];
+      for (int q = 0; q < 4; ++q) out[q] = make_uint4(0, 0, 0, 0);
+      if (target >= 0 && nrem > 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float z = __uint_as_float(raw[j]);
-          float gi;
-          if (TAU2) {
-            const float e = ex2(fmaf(z, c_tau, -half_off1));
-            gi = e * fmaf(e, c1, k_tau);
-          } else {
-            gi = c1 * ex2(fmaf(z, kLog2e, -off1)) + c2 * ex2(fmaf(z, c_tau, -offt));
+        for (int sub = 0; sub < 2; ++sub) {
+          const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
+          if (nc <= 0) break;
+          float fy[16];
+          if (DENSE) {
+            if (kUseYRing) {
+              unpack_sub<__nv_bfloat16>(pk, sub, nc, fy);
+            } else {
+              const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0 + 16 * sub;
+              load_row16<TY>(yp, p.y_vec_ok != 0, nc, fy);
+            }
           }
-          if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[j], c_tau, -offy)), gi);
-          gq[j] = gi;
-        }
-        if (ncols < 32) {  // ragged vocabulary edge: columns beyond V contribute nothing
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j >= ncols) gq[j] = 0.f;
-        }
-        const unsigned d = (unsigned)(target - col0);
-        if (d < 32u) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j == (int)d) gq[j] -= c1;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float t8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t8[j] = gq[8 * q + j];
-          Vec8<__nv_bfloat16> v;
-          v.pack(t8);
-          pk[q] = v.a;
+          if (sub == 0) sub_chunk(raw0, fy, col0, nc, out[0], out[1]);
+          else sub_chunk(raw1, fy, col0 + 16, nc, out[2], out[3]);
         }
       }
-      // stage the [128 x 64] bf16 step in shared memory (swizzled rows) and hand it to a TMA store;
-      // the elected thread first makes sure every earlier store has finished reading its buffer
-      const uint32_t buf = t.g_base + (gstep & 1u) * kStepBytes;
+      // stage the [128 x kStepCols] bf16 step in shared memory (swizzled rows) and hand it to TMA stores.
+      // One buffer: the elected thread first waits until the previous step's stores have finished
+      // reading it, a barrier publishes that, everybody writes, a second barrier publishes the writes.
       if (t.epi_tid == 0) bulk_wait_read_all();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) sts128(step_piece_addr(buf, t, q), pk[q]);
-      fence_proxy_async_smem();
       named_bar_sync(1, kEpiThreads);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts128(step_piece_addr(t.g_base, t, q), out[q]);
+      fence_proxy_async_smem();
+      named_bar_sync(2, kEpiThreads);
       if (t.epi_tid == 0) {
-        tma_store_2d(t.tma_g, buf, jtile + c * kStepCols, m0);
+#pragma unroll
+        for (int b = 0; b < kStepBoxes; ++b)
+          tma_store_2d(t.tma_g, t.g_base + b * kBoxBytes, jtile + c * kStepCols + 64 * b, m0);
         bulk_commit();
       }
-      ++gstep;
     }
   }
 
@@ -417,15 +464,66 @@ struct StoreEpi {
   __device__ StoreEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
   __device__ void begin_unit(const Geom&, int m0, int) { row = m0 + t.row_in_tile; }
 
+  __device__ __forceinline__ void store16(const uint32_t (&raw)[16], int col0, int ncols) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+    if (p.mode == kAccumF32 || p.mode == kFinalBf16) {
+      const float* acc = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
+      if (ncols >= 16 && (p.ld32 & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 o = *reinterpret_cast<const float4*>(acc + 4 * q);
+          v[4 * q] += o.x; v[4 * q + 1] += o.y; v[4 * q + 2] += o.z; v[4 * q + 3] += o.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ncols) v[j] += acc[j];
+      }
+    }
+    if (p.mode == kStoreF32 || p.mode == kAccumF32) {
+      float* dst = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
+      if (ncols >= 16 && (p.ld32 & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ncols) dst[j] = v[j];
+      }
+    } else {
+      __nv_bfloat16* dst = p.c16 + (p.row0_16 + row) * p.ld16 + col0;
+      if (ncols >= 16 && (p.ld16 & 7) == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t8[j] = v[8 * q + j];
+          Vec8<__nv_bfloat16> pk;
+          pk.pack(t8);
+          *reinterpret_cast<uint4*>(dst + 8 * q) = pk.a;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+
   template <int CG>
   __device__ void tile(const Geom&, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
-    const int col_base = n_blk * BN + t.half * 32;
+    const int col_base = n_blk * BN + t.cgrp * 32;
     const bool row_ok = row < p.m_total && row >= p.m_begin;
 #pragma unroll 1
     for (int c = 0; c < kSteps; ++c) {
-      uint32_t raw[32];
+      uint32_t raw0[16], raw1[16];
       __syncwarp();
-      tmem_ld32(tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.half * 32), raw);
+      const uint32_t taddr = tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.cgrp * 32);
+      tmem_ld16(taddr, raw0);
+      tmem_ld16(taddr + 16u, raw1);
       tmem_ld_wait();
       if (c == kSteps - 1) {
         fence_before_sync();
@@ -433,54 +531,10 @@ struct StoreEpi {
         if (t.lane == 0) release_tmem<CG>(tempty_bar);
       }
       const int col0 = col_base + c * kStepCols;
-      const int ncols = p.n_total - col0 < 32 ? p.n_total - col0 : 32;
-      if (!row_ok || ncols <= 0) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (p.mode == kAccumF32 || p.mode == kFinalBf16) {
-        const float* acc = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
-        if (ncols == 32 && (p.ld32 & 3) == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 o = *reinterpret_cast<const float4*>(acc + 4 * q);
-            v[4 * q] += o.x; v[4 * q + 1] += o.y; v[4 * q + 2] += o.z; v[4 * q + 3] += o.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) v[j] += acc[j];
-        }
-      }
-      if (p.mode == kStoreF32 || p.mode == kAccumF32) {
-        float* dst = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
-        if (ncols == 32 && (p.ld32 & 3) == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) dst[j] = v[j];
-        }
-      } else {
-        __nv_bfloat16* dst = p.c16 + (p.row0_16 + row) * p.ld16 + col0;
-        if (ncols == 32 && (p.ld16 & 7) == 0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float t8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t8[j] = v[8 * q + j];
-            Vec8<__nv_bfloat16> pk;
-            pk.pack(t8);
-            *reinterpret_cast<uint4*>(dst + 8 * q) = pk.a;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
+      const int nrem = p.n_total - col0;
+      if (!row_ok || nrem <= 0) continue;
+      store16(raw0, col0, nrem < 16 ? nrem : 16);
+      if (nrem > 16) store16(raw1, col0 + 16, nrem - 16 < 16 ? nrem - 16 : 16);
     }
   }
   __device__ void end_unit(const Geom&) {}
@@ -684,7 +738,10 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(yempty0 + 8u * slot, phase ^ 1u);
             const uint32_t fb = yfull0 + 8u * slot;
             mbar_expect_tx(fb, kStepBytes);
-            tma_load_2d(sY + slot * kStepBytes, &tma_y, g.b_n0 + n_blk * BN + c * kStepCols, m_row, fb);
+#pragma unroll
+            for (int b = 0; b < kStepBoxes; ++b)
+              tma_load_2d(sY + slot * kStepBytes + b * kBoxBytes, &tma_y,
+                          g.b_n0 + n_blk * BN + c * kStepCols + 64 * b, m_row, fb);
             if (++slot == kYSlots) {
               slot = 0;
               phase ^= 1u;
@@ -698,7 +755,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     EpiThread et;
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     et.row_in_tile = q * 32 + lane;
-    et.half = (warp - 4) >> 2;
+    et.cgrp = (warp - 4) >> 2;
     et.lane = lane;
     et.epi_tid = threadIdx.x - 128;
     et.tmem_lane_off = (uint32_t)(q * 32) << 16;
@@ -946,7 +1003,7 @@ static Workspace plan_workspace(int R, int H, int V, int v_chunk) {
   const int num_ranges = cdiv(cdiv(V, BN), kFwdTilesPerRange);
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   w.partials_off = 0;
-  w.partials_bytes = up((size_t)num_ranges * 2 * R * kRecFloats * sizeof(float));
+  w.partials_bytes = up((size_t)num_ranges * kColGroups * R * kRecFloats * sizeof(float));
   w.bsums_off = w.partials_off + w.partials_bytes;
   w.bsums_bytes = up((size_t)(kMergeBlocksMax + 1) * kNumPartialSlots * sizeof(float));
   // the backward reuses the same region from offset 0
@@ -1070,6 +1127,10 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
   fp.V = V;
   fp.inv_tau = 1.0f / tau;
   fp.partials = partials;
+  {
+    const char* e = getenv("KD_DEBUG_SKIP_MATH");
+    fp.debug_skip_math = (e && e[0] == '1') ? 1 : 0;
+  }
   const bool tau2 = tau == 2.0f;
   int rc;
   CUtensorMap ty;
@@ -1084,7 +1145,7 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
 
   MergeParams mp = {};
   mp.partials = partials;
-  mp.nrec = num_ranges * 2;
+  mp.nrec = num_ranges * kColGroups;
   mp.R = R;
   mp.V = V;
   mp.row_target = row_target;
