@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "kd_common.cuh"
@@ -993,7 +994,8 @@ static int norm_v_chunk(int v_chunk, int V) {
 struct Workspace {
   size_t partials_off, partials_bytes;  // forward records
   size_t bsums_off, bsums_bytes;        // merge block sums (+1 reduced record)
-  size_t g_off, g_bytes;                // backward gradient chunk, bf16 [R][v_chunk]
+  size_t g_off, g_bytes;                // backward gradient chunks, 2 x bf16 [R][v_chunk] (double buffered)
+  size_t g_buf_bytes;                   // one of the two
   size_t dh_off, dh_bytes;              // backward dH accumulator, fp32 [R][H]
   size_t total;
 };
@@ -1009,7 +1011,8 @@ static Workspace plan_workspace(int R, int H, int V, int v_chunk) {
   // the backward reuses the same region from offset 0
   const int vc = norm_v_chunk(v_chunk, V);
   w.g_off = 0;
-  w.g_bytes = up((size_t)R * vc * 2);
+  w.g_buf_bytes = up((size_t)R * vc * 2);
+  w.g_bytes = 2 * w.g_buf_bytes;
   w.dh_off = w.g_off + w.g_bytes;
   w.dh_bytes = up((size_t)R * H * sizeof(float));
   const size_t fwd = w.bsums_off + w.bsums_bytes, bwd = w.dh_off + w.dh_bytes;
@@ -1057,6 +1060,50 @@ static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   if (tau2) return launch_umma<GradEpi<TY, DENSE, true, false>, false, false>(ta, tb, ta, tg, g, gp, s);
   return launch_umma<GradEpi<TY, DENSE, false, false>, false, false>(ta, tb, ta, tg, g, gp, s);
+}
+
+// ---- backward pipeline: three serial chains on three streams -----------------------------------------
+//   caller's stream : grad(0) grad(1) grad(2) ...          (G chunk c -> buffer c & 1)
+//   stream W        :         dW(0)   dW(1) ...            (waits grad(c))
+//   stream H        :         dH(0)   dH(1) ...            (waits grad(c); serial: fp32 accumulation order is fixed)
+// and grad(c + 2) waits for dW(c) and dH(c) before it overwrites their buffer.  Every kernel is persistent with
+// one CTA per SM, so a kernel of the next chain fills the SMs the previous one leaves idle in its tail (and the
+// 10 CTA pairs a 64-tile dH launch never uses); results are bit-identical to the serial order.
+struct BwdPipe {
+  cudaStream_t sw = nullptr, sh = nullptr;
+  cudaEvent_t eg[2] = {nullptr, nullptr}, ew[2] = {nullptr, nullptr}, eh[2] = {nullptr, nullptr};
+  bool ready = false;
+};
+
+static bool bwd_pipe_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_BWD_STREAMS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static BwdPipe* get_bwd_pipe() {
+  constexpr int kMaxDev = 64;
+  static BwdPipe pipes[kMaxDev];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  BwdPipe& p = pipes[dev];
+  if (p.ready) return &p;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+  if (cudaStreamCreateWithPriority(&p.sw, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&p.sh, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&p.eg[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&p.ew[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&p.eh[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  p.ready = true;
+  return &p;
 }
 
 // teacher logits as a TMA source: 16-bit, 16-byte aligned base and row stride; else the direct-load path
@@ -1197,28 +1244,43 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
   const bool out32 = grad_dtype == KD_DTYPE_F32;
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
-  __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(wsp + ws.g_off);
   float* dh32 = reinterpret_cast<float*>(wsp + ws.dh_off);
   const bool tau2 = tau == 2.0f;
   const size_t ys = y_dtype == KD_DTYPE_F32 ? 4 : 2;
   const int n_chunks = cdiv(V, vc);
 
-  CUtensorMap t_h_k, t_w_k, t_g_k, t_g_mn, t_h_mn, t_w_mn, t_y;
+  CUtensorMap t_h_k, t_w_k, t_g_k[2], t_g_mn[2], t_h_mn, t_w_mn, t_y;
   const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&t_y, y, y_dtype, y_stride, R, V);
   if (make_tmap(&t_h_k, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
   if (make_tmap(&t_w_k, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, b_box_rows(), "lm_head weight")) return 1;
-  if (make_tmap(&t_g_k, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)")) return 1;
-  if (make_tmap(&t_g_mn, G, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, 64, "G (MN-major)")) return 1;
+  for (int b = 0; b < 2; ++b) {
+    const __nv_bfloat16* Gb = reinterpret_cast<const __nv_bfloat16*>(wsp + ws.g_off + b * ws.g_buf_bytes);
+    if (make_tmap(&t_g_k[b], Gb, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, BM, "G (K-major)")) return 1;
+    if (make_tmap(&t_g_mn[b], Gb, (uint64_t)vc, (uint64_t)R, (uint64_t)vc, 64, "G (MN-major)")) return 1;
+  }
   if (make_tmap(&t_h_mn, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, 64, "hidden (MN-major)")) return 1;
   if (make_tmap(&t_w_mn, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, 64, "lm_head weight (MN-major)")) return 1;
 
+  // three chains (grad on the caller's stream, dW, dH) when the pipeline is on; one serial chain otherwise
+  BwdPipe* pipe = (bwd_pipe_enabled() && n_chunks > 1) ? get_bwd_pipe() : nullptr;
+  cudaStream_t s_w = pipe ? pipe->sw : s, s_h = pipe ? pipe->sh : s;
+  bool rec_w[2] = {false, false}, rec_h[2] = {false, false};  // chunk c - 2 recorded an event on this buffer
+  bool any_w = false, any_h = false;
+  int last_w = 0, last_h = 0;
+
   for (int c = 0; c < n_chunks; ++c) {
+    const int b = c & 1;
     const int v0 = c * vc;
     const int cols = V - v0 < vc ? V - v0 : vc;
     const int n_blks = cdiv(cols, BN);  // 256-wide column blocks of this chunk (G is zero-padded to the block)
     const bool need_dw = dW != nullptr && (int64_t)(v0 + cols) > dw_row_begin;
     // ---- 1. recompute logits tile, form G ----
     {
+      if (pipe) {  // the buffer's previous readers (chunk c - 2) must be done
+        if (rec_w[b] && check_cuda(cudaStreamWaitEvent(s, pipe->ew[b], 0), "wait dW")) return 1;
+        if (rec_h[b] && check_cuda(cudaStreamWaitEvent(s, pipe->eh[b], 0), "wait dH")) return 1;
+        rec_w[b] = rec_h[b] = false;
+      }
       Geom g = {};
       g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = n_blks;
@@ -1242,15 +1304,17 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
         rc = y_dtype == KD_DTYPE_BF16
-                 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k, g, gp, tau2, s)
-                 : launch_grad<true, float>(t_h_k, t_w_k, nullptr, t_g_k, g, gp, tau2, s);
+                 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k[b], g, gp, tau2, s)
+                 : launch_grad<true, float>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
       } else {
-        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k, g, gp, tau2, s);
+        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
       }
       if (rc) return rc;
+      if (pipe && check_cuda(cudaEventRecord(pipe->eg[b], s), "record grad")) return 1;
     }
     // ---- 2. dW[v0 : v0+cols, :] = G^T h   (rows are final: every token is in this GEMM's K) ----
     if (need_dw) {
+      if (pipe && check_cuda(cudaStreamWaitEvent(s_w, pipe->eg[b], 0), "wait grad")) return 1;
       Geom g = {};
       g.num_m_blk = cdiv(n_blks * BN, tile_m());
       g.num_n_blk = cdiv(H, BN);
@@ -1269,10 +1333,16 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       sp.c32 = reinterpret_cast<float*>(dW);
       sp.ld32 = dw_stride;
       sp.row0_32 = v0;
-      if (launch_umma<StoreEpi, true, true>(t_g_mn, t_h_mn, g, sp, s)) return 1;
+      if (launch_umma<StoreEpi, true, true>(t_g_mn[b], t_h_mn, g, sp, s_w)) return 1;
+      if (pipe) {
+        if (check_cuda(cudaEventRecord(pipe->ew[b], s_w), "record dW")) return 1;
+        rec_w[b] = any_w = true;
+        last_w = b;
+      }
     }
     // ---- 3. dH (+)= G W[v0 : v0+cols, :] ----
     if (dH) {
+      if (pipe && check_cuda(cudaStreamWaitEvent(s_h, pipe->eg[b], 0), "wait grad")) return 1;
       Geom g = {};
       g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = cdiv(H, BN);
@@ -1296,8 +1366,17 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
         sp.c16 = reinterpret_cast<__nv_bfloat16*>(dH);
         sp.ld16 = dh_stride;
       }
-      if (launch_umma<StoreEpi, false, true>(t_g_k, t_w_mn, g, sp, s)) return 1;
+      if (launch_umma<StoreEpi, false, true>(t_g_k[b], t_w_mn, g, sp, s_h)) return 1;
+      if (pipe) {
+        if (check_cuda(cudaEventRecord(pipe->eh[b], s_h), "record dH")) return 1;
+        rec_h[b] = any_h = true;
+        last_h = b;
+      }
     }
+  }
+  if (pipe) {  // join: both side chains are serial, so their last events cover everything
+    if (any_w && check_cuda(cudaStreamWaitEvent(s, pipe->ew[last_w], 0), "join dW")) return 1;
+    if (any_h && check_cuda(cudaStreamWaitEvent(s, pipe->eh[last_h], 0), "join dH")) return 1;
   }
   return 0;
 }
