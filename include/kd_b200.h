@@ -42,7 +42,7 @@ extern "C" {
 #define KD_DTYPE_BF16 1
 #define KD_DTYPE_F16 2
 
-#define KD_ABI_VERSION 1
+#define KD_ABI_VERSION 2
 
 /* Teacher kinds for the fused LM-head entry points. */
 #define KD_TEACHER_NONE 0   /* CE only (stage1 warm-up, stage1.py:298-340) */
@@ -109,8 +109,12 @@ int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stre
  * Replaces lm_head (transformers Qwen3ForCausalLM.lm_head, called at train.py:54) followed by
  * DistillationLoss.forward, and their backward.  h [R,H] bf16 (R = B*T rows, row stride
  * h_stride), W [V,H] bf16 (row stride w_stride), row_target from kd_prepare_rows.
- * Teacher: dense y [R,V] (y_dtype bf16/f16/f32, row stride y_stride), sparse (topk_v, topk_i, K)
- * or none (alpha is forced to 1: plain causal-LM CE, stage1).
+ * Teacher: dense y [R,V] (y_dtype bf16/f32, row stride y_stride), sparse (topk_v fp32 [R,K] teacher
+ * log-probs at tau = 1, topk_i int32 [R,K], both contiguous, K <= 1024; duplicate indices accumulate,
+ * indices outside [0,V) are ignored) or none (alpha is forced to 1: plain causal-LM CE, stage1).
+ * The sparse form is distillation_loss.py:73-118 without the student log-softmax over [rows,V]:
+ * sum_k p_k z[i_k] is picked out of the accumulator tiles and P = scatter(i_k, p_k) is subtracted
+ * from the gradient tiles in the epilogues.
  *
  * kd_fused_linear_fwd  : sums[8] and row_stats float[R,4] = (LSE1, LSEtau, LSEteacher_tau, valid).
  * kd_fused_linear_bwd  : dH [R,H] and dW [V,H] in grad_dtype (KD_DTYPE_BF16 = what autograd hands a bf16
@@ -121,8 +125,12 @@ int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stre
  *                        (alpha * g, (1 - alpha) * g) with g the upstream grad of the total loss
  *                        (distillation_loss.py:126); n_norm as above.
  * v_chunk: vocabulary columns per backward chunk (0 = library default); the gradient scratch is
- * R x v_chunk bf16, independent of V.  workspace sized by kd_fused_workspace_bytes(). */
-size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk);
+ * 2 x R x v_chunk bf16 (double buffered), independent of V.  workspace sized by
+ * kd_fused_workspace_bytes() (K = top-k width of a sparse teacher, else 0), 256-byte aligned.
+ * The backward runs its three GEMM chains (gradient tile, dW, dH) on the caller's stream plus two
+ * internal streams that fork from and join back into it, so the call is still ordered like one
+ * stream operation; KD_BWD_STREAMS=0 in the environment keeps everything on the caller's stream. */
+size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int K);
 int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                         const float* topk_v, const int32_t* topk_i, int K,

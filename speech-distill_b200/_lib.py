@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libkd_b200.so")
 
 KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
 KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
+ABI_VERSION = 2  # KD_ABI_VERSION in include/kd_b200.h
 
 _c = ctypes
 _vp, _i32, _i64, _f32, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
@@ -30,7 +31,7 @@ SIGNATURES = {
     "kd_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "kd_topk_logprobs": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "kd_mask_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
-    "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "kd_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _i32,
                                    _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32,
@@ -61,8 +62,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.kd_version() != 1:
-        raise KdError(f"libkd_b200 ABI version {lib.kd_version()} != 1")
+    if lib.kd_version() != ABI_VERSION:
+        raise KdError(f"libkd_b200 ABI version {lib.kd_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -176,6 +176,17 @@ __device__ __forceinline__ void unpack_sub(const uint4 (&pk)[4], int sub, int nc
   }
 }
 
+// Sparse teacher as the epilogues see it (built per call by kd_sparse_prepare_kernel): for every row the K
+// entries sorted by vocabulary index, p = softmax(v / tau) over the K entries (distillation_loss.py:94), and
+// off[row][t] = number of entries with index < 256 t, so a thread finds the entries of its 256-column tile with
+// one 4-byte load (on average K / (V / 256) = 0.1 entries per row and tile at K = 64, V = 152,936).
+struct SparseView {
+  const int32_t* idx;   // [R][K] ascending; out-of-range indices are dropped to the end
+  const float* p;       // [R][K] aligned with idx
+  const uint16_t* off;  // [R][off_stride]
+  int K, off_stride;
+};
+
 // ---- forward: online statistics -------------------------------------------------------------
 struct FwdParams {
   const int32_t* row_target;
@@ -185,11 +196,13 @@ struct FwdParams {
   int R, V;
   float inv_tau;
   float* partials;  // [num_ranges * kColGroups][R][kRecFloats]
+  SparseView sp;    // sparse teacher (index-sorted entries + per-tile offsets), unused otherwise
   int debug_skip_math;  // KD_DEBUG_SKIP_MATH=1: bring-up knob that measures the pipeline without the epilogue math
 };
 
-template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
+template <typename TY, bool DENSE, bool TAU2, bool Y_TMA, bool SPARSE = false>
 struct FwdEpi {
+  static_assert(!(DENSE && SPARSE), "one teacher kind per instantiation");
   using Params = FwdParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
   static constexpr int kYSlots = kUseYRing ? 2 : 0;
@@ -239,6 +252,12 @@ struct FwdEpi {
   template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int col_base = g.b_n0 + n_blk * BN + t.cgrp * 32;
+    int e_beg = 0, e_end = 0;
+    if (SPARSE && target >= 0) {  // this row's teacher entries inside the tile
+      const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + (g.b_n0 / BN + n_blk);
+      e_beg = o[0];
+      e_end = o[1];
+    }
 #pragma unroll 1
     for (int c = 0; c < kSteps; ++c) {
       uint32_t raw0[16], raw1[16];
@@ -257,6 +276,18 @@ struct FwdEpi {
       const int col0 = col_base + c * kStepCols;
       const int nrem = p.V - col0;
       if (target < 0 || nrem <= 0 || p.debug_skip_math) continue;
+      if (SPARSE) {  // cross term sum_k p_k z[i_k] (distillation_loss.py:101-106): rare, predicated pick-up
+        for (int e = e_beg; e < e_end; ++e) {
+          const unsigned d = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col0);
+          if (d < 32u) {
+            float z = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j == (int)(d & 15u)) z = __uint_as_float(d < 16u ? raw0[j] : raw1[j]);
+            a = fmaf(p.sp.p[(size_t)row * p.sp.K + e], z, a);
+          }
+        }
+      }
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
@@ -299,10 +330,12 @@ struct GradParams {
   const int32_t* n_norm;
   const float* coef;  // device float[2]: weight of d(sum CE) and of tau^2 d(sum KL) in the returned gradient
   int v0;             // first vocabulary column of this chunk; scratch column j <-> vocabulary index v0 + j
+  SparseView sp;      // sparse teacher, see FwdParams
 };
 
-template <typename TY, bool DENSE, bool TAU2, bool Y_TMA>
+template <typename TY, bool DENSE, bool TAU2, bool Y_TMA, bool SPARSE = false>
 struct GradEpi {
+  static_assert(!(DENSE && SPARSE), "one teacher kind per instantiation");
   using Params = GradParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
   static constexpr int kYSlots = kUseYRing ? 2 : 0;
@@ -337,7 +370,7 @@ struct GradEpi {
 
   // gradient of 16 columns -> two packed 16-byte pieces
   __device__ __forceinline__ void sub_chunk(const uint32_t (&raw)[16], const float (&fy)[16], int col0, int ncols,
-                                            uint4& lo, uint4& hi) {
+                                            int e_beg, int e_end, uint4& lo, uint4& hi) {
     float gq[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -356,6 +389,17 @@ struct GradEpi {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j >= ncols) gq[j] = 0.f;
+    }
+    if (SPARSE) {  // - c2 P with P = scatter(i_k, p_k); duplicate indices accumulate
+      for (int e = e_beg; e < e_end; ++e) {
+        const unsigned ds = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col0);
+        if (ds < 16u) {
+          const float pk = c2 * p.sp.p[(size_t)row * p.sp.K + e];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j == (int)ds) gq[j] -= pk;
+        }
+      }
     }
     const unsigned d = (unsigned)(target - col0);
     if (d < 16u) {
@@ -378,6 +422,12 @@ struct GradEpi {
   template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int jtile = n_blk * BN;  // first scratch column of this tile
+    int e_beg = 0, e_end = 0;
+    if (SPARSE && target >= 0) {
+      const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + ((p.v0 + jtile) / BN);
+      e_beg = o[0];
+      e_end = o[1];
+    }
 #pragma unroll 1
     for (int c = 0; c < kSteps; ++c) {
       uint32_t raw0[16], raw1[16];
@@ -413,8 +463,8 @@ struct GradEpi {
               load_row16<TY>(yp, p.y_vec_ok != 0, nc, fy);
             }
           }
-          if (sub == 0) sub_chunk(raw0, fy, col0, nc, out[0], out[1]);
-          else sub_chunk(raw1, fy, col0 + 16, nc, out[2], out[3]);
+          if (sub == 0) sub_chunk(raw0, fy, col0, nc, e_beg, e_end, out[0], out[1]);
+          else sub_chunk(raw1, fy, col0 + 16, nc, e_beg, e_end, out[2], out[3]);
         }
       }
       // stage the [128 x kStepCols] bf16 step in shared memory (swizzled rows) and hand it to TMA stores.
@@ -810,15 +860,17 @@ struct MergeParams {
   int y_dtype;
   int64_t y_stride;
   int dense;
+  int sparse;
+  const float4* sp_rowc;  // sparse: [R] = (sum_k p_k log p_k, sum of v_k over hits, number of hits, 0)
   float inv_tau;
   float* row_stats;     // [R][4]
   float* block_sums;    // [gridDim.x][8]
 };
 
 __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p) {
-  __shared__ float sm[8][4];
+  __shared__ float sm[8][5];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ce = 0.f, kl = 0.f, tce = 0.f, nv = 0.f;
+  float ce = 0.f, kl = 0.f, tce = 0.f, nv = 0.f, hits = 0.f;
   for (int row = blockIdx.x * 8 + warp; row < p.R; row += gridDim.x * 8) {
     const int target = p.row_target[row];
     if (target < 0) {
@@ -832,6 +884,7 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
       const float4 w = *reinterpret_cast<const float4*>(rec + 4);
       merge_student(m, s1, st, x.x, x.y, x.z, p.inv_tau);
       if (p.dense) merge_teacher(mt, t1, tt, a, x.w, w.x, w.y, w.z, p.inv_tau);
+      else a += w.z;  // sparse: partial sums of p_k z[i_k]
       zl += w.w;
     }
 #pragma unroll
@@ -843,6 +896,8 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
         const float mt2 = __shfl_xor_sync(0xffffffffu, mt, o), c2 = __shfl_xor_sync(0xffffffffu, t1, o),
                     d2 = __shfl_xor_sync(0xffffffffu, tt, o), e2 = __shfl_xor_sync(0xffffffffu, a, o);
         merge_teacher(mt, t1, tt, a, mt2, c2, d2, e2, p.inv_tau);
+      } else {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
       }
       zl += __shfl_xor_sync(0xffffffffu, zl, o);
     }
@@ -860,20 +915,145 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
         else if (p.y_dtype == KD_DTYPE_BF16) yl = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.y)[off]);
         else yl = __half2float(reinterpret_cast<const __half*>(p.y)[off]);
         tce += (mt + ln_acc(t1)) - yl;
+      } else if (p.sparse) {
+        // KL_r = sum_k p_k (log p_k - log q_tau[i_k]) with log q_tau[i] = z_i / tau - LSE_tau and sum_k p_k = 1
+        const float4 rc = p.sp_rowc[row];
+        kl += rc.x - a * p.inv_tau + lset;
+        tce += rc.y;   // distillation_loss.py:110-116: teacher log-probs of the hits
+        hits += rc.z;
       }
       nv += 1.f;
       *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(lse1, lset, lsett, 1.f);
     }
   }
   if (lane == 0) {
-    sm[warp][0] = ce; sm[warp][1] = kl; sm[warp][2] = tce; sm[warp][3] = nv;
+    sm[warp][0] = ce; sm[warp][1] = kl; sm[warp][2] = tce; sm[warp][3] = nv; sm[warp][4] = hits;
   }
   __syncthreads();
   if (threadIdx.x < 8) {
     float v = 0.f;
-    if (threadIdx.x < 4)
+    if (threadIdx.x < 5)
       for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
     p.block_sums[(size_t)blockIdx.x * kNumPartialSlots + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse teacher preparation (distillation_loss.py:77-95, 108-116): one CTA per valid row.
+//   p_k = softmax(v / tau) over the K entries, sum_k p_k log p_k, label hits; entries sorted by vocabulary
+//   index (bitonic sort in shared memory) and the per-256-column-tile offsets the epilogues index with.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPrepThreads = 128;
+constexpr int kMaxFusedTopK = 1024;
+
+struct SparsePrepParams {
+  const float* v;      // [R][K] teacher log-probs at tau = 1
+  const int32_t* idx;  // [R][K]
+  const int32_t* row_target;
+  int R, K, Kp2, V, n_off;  // n_off = number of tile offsets per row (tiles + 1)
+  float inv_tau;
+  int32_t* s_idx;
+  float* s_p;
+  float4* rowc;
+  uint16_t* off;  // [R][off_stride]
+  int off_stride;
+};
+
+__global__ void __launch_bounds__(kPrepThreads) kd_sparse_prepare_kernel(const SparsePrepParams p) {
+  extern __shared__ uint8_t prep_smem[];
+  int32_t* keys = reinterpret_cast<int32_t*>(prep_smem);
+  float* vals = reinterpret_cast<float*>(prep_smem + (size_t)p.Kp2 * 4);
+  __shared__ float red[kPrepThreads / 32][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int row = blockIdx.x; row < p.R; row += gridDim.x) {
+    const int target = p.row_target[row];
+    if (target < 0) continue;  // block-uniform
+    const float* vrow = p.v + (size_t)row * p.K;
+    const int32_t* irow = p.idx + (size_t)row * p.K;
+    // max and log-sum-exp of v / tau
+    float vm = -CUDART_INF_F;
+    for (int k = tid; k < p.K; k += kPrepThreads) vm = fmaxf(vm, vrow[k]);
+    vm = warp_max(vm);
+    if (lane == 0) red[warp][0] = vm;
+    __syncthreads();
+    vm = fmaxf(fmaxf(red[0][0], red[1][0]), fmaxf(red[2][0], red[3][0]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int k = tid; k < p.K; k += kPrepThreads) sum += __expf((vrow[k] - vm) * p.inv_tau);
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp][0] = sum;
+    __syncthreads();
+    sum = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+    __syncthreads();
+    const float lk = vm * p.inv_tau + ln_acc(sum);
+    float plogp = 0.f, hit_sum = 0.f, hits = 0.f;
+    for (int k = tid; k < p.Kp2; k += kPrepThreads) {
+      int key = 0x7fffffff;
+      float pk = 0.f;
+      if (k < p.K) {
+        const float lp = vrow[k] * p.inv_tau - lk;  // log p_k
+        pk = __expf(lp);
+        if (pk > 0.f) plogp = fmaf(pk, lp, plogp);
+        const int i = irow[k];
+        if (i == target) {
+          hits += 1.f;
+          hit_sum += vrow[k];
+        }
+        if (i >= 0 && i < p.V) key = i;  // out-of-range entries sort to the end and are never visited
+      }
+      keys[k] = key;
+      vals[k] = pk;
+    }
+    plogp = warp_sum(plogp);
+    hit_sum = warp_sum(hit_sum);
+    hits = warp_sum(hits);
+    if (lane == 0) {
+      red[warp][0] = plogp;
+      red[warp][1] = hit_sum;
+      red[warp][2] = hits;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      p.rowc[row] = make_float4((red[0][0] + red[1][0]) + (red[2][0] + red[3][0]),
+                                (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]),
+                                (red[0][2] + red[1][2]) + (red[2][2] + red[3][2]), 0.f);
+    }
+    // bitonic sort by key, ascending
+    for (int k2 = 2; k2 <= p.Kp2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < p.Kp2; i += kPrepThreads) {
+          const int l = i ^ j;
+          if (l > i) {
+            const bool up = (i & k2) == 0;
+            const int32_t ki = keys[i], kl = keys[l];
+            if ((ki > kl) == up) {
+              keys[i] = kl;
+              keys[l] = ki;
+              const float t = vals[i];
+              vals[i] = vals[l];
+              vals[l] = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int k = tid; k < p.K; k += kPrepThreads) {
+      p.s_idx[(size_t)row * p.K + k] = keys[k];
+      p.s_p[(size_t)row * p.K + k] = vals[k];
+    }
+    // off[t] = number of entries with index < 256 t (lower bound in the sorted keys)
+    for (int t = tid; t < p.n_off; t += kPrepThreads) {
+      const int bound = t * BN;
+      int lo = 0, hi = p.K;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < bound) lo = mid + 1;
+        else hi = mid;
+      }
+      p.off[(size_t)row * p.off_stride + t] = (uint16_t)lo;
+    }
+    __syncthreads();  // keys / vals are rewritten by the next row
   }
 }
 
@@ -997,10 +1177,14 @@ struct Workspace {
   size_t g_off, g_bytes;                // backward gradient chunks, 2 x bf16 [R][v_chunk] (double buffered)
   size_t g_buf_bytes;                   // one of the two
   size_t dh_off, dh_bytes;              // backward dH accumulator, fp32 [R][H]
+  // sparse teacher view, rebuilt by each call (after the forward region resp. the backward region)
+  size_t sp_bytes, sp_idx_rel, sp_p_rel, sp_rowc_rel, sp_off_rel;  // offsets relative to the region start
+  int sp_off_stride, sp_n_off;
+  size_t fwd_bytes, bwd_bytes;          // end of the forward / backward regions = start of the sparse region
   size_t total;
 };
 
-static Workspace plan_workspace(int R, int H, int V, int v_chunk) {
+static Workspace plan_workspace(int R, int H, int V, int v_chunk, int K) {
   Workspace w;
   const int num_ranges = cdiv(cdiv(V, BN), kFwdTilesPerRange);
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -1015,7 +1199,20 @@ static Workspace plan_workspace(int R, int H, int V, int v_chunk) {
   w.g_bytes = 2 * w.g_buf_bytes;
   w.dh_off = w.g_off + w.g_bytes;
   w.dh_bytes = up((size_t)R * H * sizeof(float));
-  const size_t fwd = w.bsums_off + w.bsums_bytes, bwd = w.dh_off + w.dh_bytes;
+  w.fwd_bytes = w.bsums_off + w.bsums_bytes;
+  w.bwd_bytes = w.dh_off + w.dh_bytes;
+  w.sp_bytes = 0;
+  w.sp_idx_rel = w.sp_p_rel = w.sp_rowc_rel = w.sp_off_rel = 0;
+  w.sp_n_off = cdiv(V, BN) + 1;
+  w.sp_off_stride = (w.sp_n_off + 7) & ~7;
+  if (K > 0) {
+    w.sp_idx_rel = 0;
+    w.sp_p_rel = w.sp_idx_rel + up((size_t)R * K * 4);
+    w.sp_rowc_rel = w.sp_p_rel + up((size_t)R * K * 4);
+    w.sp_off_rel = w.sp_rowc_rel + up((size_t)R * 16);
+    w.sp_bytes = w.sp_off_rel + up((size_t)R * w.sp_off_stride * 2);
+  }
+  const size_t fwd = w.fwd_bytes + w.sp_bytes, bwd = w.bwd_bytes + w.sp_bytes;
   w.total = fwd > bwd ? fwd : bwd;
   return w;
 }
@@ -1106,6 +1303,43 @@ static BwdPipe* get_bwd_pipe() {
   return &p;
 }
 
+// sparse teacher: validate, run the preparation kernel into `region`, return the view for the epilogues
+static int prepare_sparse(const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target, int R, int V,
+                          float tau, const Workspace& ws, uint8_t* region, SparseView* view, const float4** rowc,
+                          cudaStream_t s, const char* who) {
+  if (!topk_v || !topk_i || K <= 0 || K > kMaxFusedTopK) {
+    set_error("%s: sparse teacher needs topk_v, topk_i and 1 <= K <= %d (K=%d)", who, kMaxFusedTopK, K);
+    return 1;
+  }
+  int Kp2 = 1;
+  while (Kp2 < K) Kp2 <<= 1;
+  SparsePrepParams pp = {};
+  pp.v = topk_v;
+  pp.idx = topk_i;
+  pp.row_target = row_target;
+  pp.R = R;
+  pp.K = K;
+  pp.Kp2 = Kp2;
+  pp.V = V;
+  pp.n_off = ws.sp_n_off;
+  pp.inv_tau = 1.0f / tau;
+  pp.s_idx = reinterpret_cast<int32_t*>(region + ws.sp_idx_rel);
+  pp.s_p = reinterpret_cast<float*>(region + ws.sp_p_rel);
+  pp.rowc = reinterpret_cast<float4*>(region + ws.sp_rowc_rel);
+  pp.off = reinterpret_cast<uint16_t*>(region + ws.sp_off_rel);
+  pp.off_stride = ws.sp_off_stride;
+  const int blocks = R < 8 * sm_count() ? R : 8 * sm_count();
+  kd_sparse_prepare_kernel<<<blocks, kPrepThreads, (size_t)Kp2 * 8, s>>>(pp);
+  if (check_cuda(cudaGetLastError(), "kd_sparse_prepare launch")) return 1;
+  view->idx = pp.s_idx;
+  view->p = pp.s_p;
+  view->off = pp.off;
+  view->K = K;
+  view->off_stride = ws.sp_off_stride;
+  if (rowc) *rowc = pp.rowc;
+  return 0;
+}
+
 // teacher logits as a TMA source: 16-bit, 16-byte aligned base and row stride; else the direct-load path
 static bool make_teacher_tmap(CUtensorMap* m, const void* y, int y_dtype, int64_t y_stride, int R, int V) {
   if (!y || y_dtype != KD_DTYPE_BF16) return false;
@@ -1119,9 +1353,9 @@ static bool make_teacher_tmap(CUtensorMap* m, const void* y, int y_dtype, int64_
 using namespace kd;
 using namespace kd::fused;
 
-extern "C" size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk) {
-  if (R <= 0 || H <= 0 || V <= 0) return 0;
-  return plan_workspace(R, H, V, v_chunk).total;
+extern "C" size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int K) {
+  if (R <= 0 || H <= 0 || V <= 0 || K < 0) return 0;
+  return plan_workspace(R, H, V, v_chunk, K).total;
 }
 
 extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
@@ -1129,22 +1363,19 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
                                    const int32_t* topk_i, int K, const int32_t* row_target, int R, int H, int V,
                                    float tau, float alpha, float* sums, float* row_stats, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  (void)alpha; (void)topk_v; (void)topk_i; (void)K;
+  (void)alpha;
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_fwd")) return 1;
   if (!row_target || !sums || !row_stats || !workspace) {
     set_error("kd_fused_linear_fwd: null pointer argument");
     return 1;
   }
-  if (teacher_kind == KD_TEACHER_SPARSE) {
-    set_error("kd_fused_linear_fwd: sparse teacher is not implemented in the fused path yet; use kd_sparse_fwd_bwd");
-    return 3;
-  }
   if (teacher_kind == KD_TEACHER_DENSE && (!y || (y_dtype != KD_DTYPE_BF16 && y_dtype != KD_DTYPE_F32))) {
     set_error("kd_fused_linear_fwd: dense teacher must be bf16 or fp32");
     return 1;
   }
-  const Workspace ws = plan_workspace(R, H, V, 0);
-  if (workspace_bytes < ws.bsums_off + ws.bsums_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+  const bool sparse = teacher_kind == KD_TEACHER_SPARSE;
+  const Workspace ws = plan_workspace(R, H, V, 0, sparse ? K : 0);
+  if (workspace_bytes < ws.fwd_bytes + ws.sp_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
     set_error("kd_fused_linear_fwd: workspace too small or not 256-byte aligned (need %zu)", ws.total);
     return 1;
   }
@@ -1181,10 +1412,17 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
   const bool tau2 = tau == 2.0f;
   int rc;
   CUtensorMap ty;
+  const float4* sp_rowc = nullptr;
   const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&ty, y, y_dtype, y_stride, R, V);
   if (teacher_kind == KD_TEACHER_DENSE) {
     rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, y_tma ? &ty : nullptr, g, fp, tau2, s)
                                   : launch_fwd<true, float>(ta, tb, nullptr, g, fp, tau2, s);
+  } else if (sparse) {
+    if (prepare_sparse(topk_v, topk_i, K, row_target, R, V, tau, ws, wsp + ws.fwd_bytes, &fp.sp, &sp_rowc, s,
+                       "kd_fused_linear_fwd"))
+      return 1;
+    rc = tau2 ? launch_umma<FwdEpi<__nv_bfloat16, false, true, false, true>, false, false>(ta, tb, g, fp, s)
+              : launch_umma<FwdEpi<__nv_bfloat16, false, false, false, true>, false, false>(ta, tb, g, fp, s);
   } else {
     rc = launch_fwd<false, __nv_bfloat16>(ta, tb, nullptr, g, fp, tau2, s);
   }
@@ -1200,6 +1438,8 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
   mp.y_dtype = y_dtype;
   mp.y_stride = y_stride;
   mp.dense = teacher_kind == KD_TEACHER_DENSE ? 1 : 0;
+  mp.sparse = sparse ? 1 : 0;
+  mp.sp_rowc = sp_rowc;
   mp.inv_tau = 1.0f / tau;
   mp.row_stats = row_stats;
   mp.block_sums = bsums;
@@ -1217,23 +1457,19 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
                                    const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                                    int64_t dw_stride, int64_t dw_row_begin, int v_chunk, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  (void)topk_v; (void)topk_i; (void)K;
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_bwd")) return 1;
   if (!row_target || !row_stats || !n_norm || !grad_coef || !workspace || (!dH && !dW)) {
     set_error("kd_fused_linear_bwd: null pointer argument");
     return 1;
-  }
-  if (teacher_kind == KD_TEACHER_SPARSE) {
-    set_error("kd_fused_linear_bwd: sparse teacher is not implemented in the fused path yet; use kd_sparse_fwd_bwd");
-    return 3;
   }
   if (teacher_kind == KD_TEACHER_DENSE && (!y || (y_dtype != KD_DTYPE_BF16 && y_dtype != KD_DTYPE_F32))) {
     set_error("kd_fused_linear_bwd: dense teacher must be bf16 or fp32");
     return 1;
   }
   const int vc = norm_v_chunk(v_chunk, V);
-  const Workspace ws = plan_workspace(R, H, V, vc);
-  if (workspace_bytes < ws.dh_off + ws.dh_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+  const bool sparse = teacher_kind == KD_TEACHER_SPARSE;
+  const Workspace ws = plan_workspace(R, H, V, vc, sparse ? K : 0);
+  if (workspace_bytes < ws.bwd_bytes + ws.sp_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
     set_error("kd_fused_linear_bwd: workspace too small or not 256-byte aligned (need %zu)", ws.total);
     return 1;
   }
@@ -1260,6 +1496,11 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
   }
   if (make_tmap(&t_h_mn, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, 64, "hidden (MN-major)")) return 1;
   if (make_tmap(&t_w_mn, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, 64, "lm_head weight (MN-major)")) return 1;
+
+  SparseView sp_view = {};
+  if (sparse && prepare_sparse(topk_v, topk_i, K, row_target, R, V, tau, ws, wsp + ws.bwd_bytes, &sp_view, nullptr, s,
+                               "kd_fused_linear_bwd"))
+    return 1;
 
   // three chains (grad on the caller's stream, dW, dH) when the pipeline is on; one serial chain otherwise
   BwdPipe* pipe = (bwd_pipe_enabled() && n_chunks > 1) ? get_bwd_pipe() : nullptr;
@@ -1301,11 +1542,17 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       gp.n_norm = n_norm;
       gp.coef = grad_coef;
       gp.v0 = v0;
+      gp.sp = sp_view;
       int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
         rc = y_dtype == KD_DTYPE_BF16
                  ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k[b], g, gp, tau2, s)
                  : launch_grad<true, float>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
+      } else if (sparse) {
+        rc = tau2 ? launch_umma<GradEpi<__nv_bfloat16, false, true, false, true>, false, false>(t_h_k, t_w_k, t_h_k,
+                                                                                                  t_g_k[b], g, gp, s)
+                  : launch_umma<GradEpi<__nv_bfloat16, false, false, false, true>, false, false>(t_h_k, t_w_k, t_h_k,
+                                                                                                   t_g_k[b], g, gp, s);
       } else {
         rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
       }

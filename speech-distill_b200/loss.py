@@ -177,41 +177,51 @@ def kd_loss_on_logits(student_logits, labels, teacher_logits=None, teacher_top_k
 # --------------------------------------------------------------------------------------------
 # K1 behind autograd: LM head + loss without materialising logits
 # --------------------------------------------------------------------------------------------
-def _fused_workspace(R, H, V, v_chunk, device):
+def _fused_workspace(R, H, V, v_chunk, device, K=0):
     lib = _lib.load()
-    return _workspace(lib.kd_fused_workspace_bytes(R, H, V, int(v_chunk)), device)
+    return _workspace(lib.kd_fused_workspace_bytes(R, H, V, int(v_chunk), int(K)), device)
 
 
-def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk):
+def _teacher_kind(y, topk):
+    if y is not None:
+        return _lib.KD_TEACHER_DENSE
+    return _lib.KD_TEACHER_SPARSE if topk is not None else _lib.KD_TEACHER_NONE
+
+
+def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None):
+    """topk = (v fp32 [R,K], i int32 [R,K]) for the sparse teacher, else None."""
     lib = _lib.load()
     R, H = h.shape
     V = W.shape[0]
     dev = h.device
-    teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
+    teacher_kind = _teacher_kind(y, topk)
+    K = topk[0].size(-1) if teacher_kind == _lib.KD_TEACHER_SPARSE else 0
     sums = torch.empty(8, dtype=torch.float32, device=dev)
     row_stats = torch.empty((R, 4), dtype=torch.float32, device=dev)
-    ws = _fused_workspace(R, H, V, v_chunk, dev)
+    ws = _fused_workspace(R, H, V, v_chunk, dev, K)
     rc = lib.kd_fused_linear_fwd(
         h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
         _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-        0, 0, 0, row_target.data_ptr(), R, H, V, float(tau), float(alpha),
-        sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), R, H, V, float(tau),
+        float(alpha), sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
     check(rc, "kd_fused_linear_fwd")
     return sums, row_stats, ws
 
 
 class _KDFusedLinear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype):
-        teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
-        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk)
+    def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype,
+                topk_v=None, topk_i=None):
+        topk = (topk_v, topk_i) if topk_v is not None else None
+        teacher_kind = _teacher_kind(y, topk)
+        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
-        eff_alpha = alpha if y is not None else 1.0
-        losses = finalize_losses(sums, tau, eff_alpha, False)
+        eff_alpha = alpha if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
+        losses = finalize_losses(sums, tau, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
         ctx.set_materialize_grads(False)
         ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk), grad_dtype)
-        ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm)
+        ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm, topk_v, topk_i)
         ctx.ws = ws
         total, task, distill, teacher = losses.unbind(0)
         ctx.mark_non_differentiable(teacher)
@@ -219,7 +229,8 @@ class _KDFusedLinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, g_task, g_distill, g_teacher):
-        h, W, y, row_target, row_stats, n_norm = ctx.saved_tensors
+        h, W, y, row_target, row_stats, n_norm, topk_v, topk_i = ctx.saved_tensors
+        topk = (topk_v, topk_i) if topk_v is not None else None
         tau, alpha, teacher_kind, dw_row_begin, v_chunk, grad_dtype = ctx.cfg
         dev = h.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
@@ -228,27 +239,29 @@ class _KDFusedLinear(torch.autograd.Function):
         w_kl = gt * (1.0 - alpha) + (zero if g_distill is None else g_distill.detach().float())
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
         dH, dW = _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin,
-                                 v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws)
-        return dH, dW, None, None, None, None, None, None, None, None, None, None
+                                 v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk)
+        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin, v_chunk,
-                    grad_dtype, need_h, need_w, ws=None):
+                    grad_dtype, need_h, need_w, ws=None, topk=None):
     lib = _lib.load()
     R, H = h.shape
     V = W.shape[0]
     dev = h.device
+    K = topk[0].size(-1) if teacher_kind == _lib.KD_TEACHER_SPARSE else 0
     dH = torch.empty((R, H), dtype=grad_dtype, device=dev) if need_h else None
     dW = None
     if need_w:
         # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
         dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
     if ws is None:
-        ws = _fused_workspace(R, H, V, v_chunk, dev)
+        ws = _fused_workspace(R, H, V, v_chunk, dev, K)
     rc = lib.kd_fused_linear_bwd(
         h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
         _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-        0, 0, 0, row_target.data_ptr(), row_stats.data_ptr(), R, H, V, float(tau),
+        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), row_stats.data_ptr(), R, H, V,
+        float(tau),
         n_norm.data_ptr(), coef.data_ptr(), dtype_code(grad_dtype), _ptr(dH), H, _ptr(dW), H,
         int(dw_row_begin), int(v_chunk), ws.data_ptr(), ws.numel(), stream_ptr(dev))
     check(rc, "kd_fused_linear_bwd")
@@ -257,29 +270,33 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
 
 def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                                    temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
-                                   grad_dtype=torch.float32):
+                                   grad_dtype=torch.float32, teacher_top_k_v=None, teacher_top_k_i=None):
     """Forward + backward in one call, outside autograd: returns (losses[4] fp32, dHidden, dWeight) with the
     gradients of ``total`` in ``grad_dtype``.  fp32 exposes the kernels' accumulators before the final
     rounding to bf16 that autograd imposes on bf16 leaves (used by the parity tests and by callers that keep
     fp32 master gradients)."""
     with torch.no_grad():
         out = fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits, speech_token_mask, temperature,
-                                   alpha, ignore_index, dw_row_begin, v_chunk, _return_ctx=True)
+                                   alpha, ignore_index, dw_row_begin, v_chunk, teacher_top_k_v=teacher_top_k_v,
+                                   teacher_top_k_i=teacher_top_k_i, _return_ctx=True)
     losses, saved = out
-    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha = saved
+    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk = saved
     coef = torch.tensor([eff_alpha, 1.0 - eff_alpha], dtype=torch.float32, device=h2.device)
     dH, dW = _fused_backward(h2, W, y, row_target, row_stats, n_norm, coef, float(temperature), teacher_kind,
-                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True)
+                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True, None, topk)
     return losses, dH.view(hidden.shape), dW
 
 
 def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                          temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
-                         reduce_fn=None, count_reduce_fn=None, grad_dtype=torch.bfloat16, _return_ctx=False):
+                         reduce_fn=None, count_reduce_fn=None, grad_dtype=torch.bfloat16, teacher_top_k_v=None,
+                         teacher_top_k_i=None, _return_ctx=False):
     """``DistillationLoss(student_logits = hidden @ lm_head_weight.T, ...)`` without the logits.
 
     hidden [B,T,H] (or [R,H] with labels [.., T]) bf16, lm_head_weight [V,H] bf16, labels [B,T].
-    teacher_logits [B,T,V] (bf16/fp32) or None for plain causal-LM cross-entropy (stage1).
+    Teacher: ``teacher_logits`` [B,T,V] (bf16/fp32), or the top-k cache ``teacher_top_k_v`` / ``teacher_top_k_i``
+    [B,T,K] (distillation_loss.py:73-118; dense wins when both are given, :56 before :73), or neither for
+    plain causal-LM cross-entropy (stage1).
     ``dw_row_begin``: first vocabulary row that receives a weight gradient (stage1.py:46-57 passes
     the old vocabulary size; rows below stay exactly zero and are never computed).
     ``grad_dtype``: torch.bfloat16 (what autograd requires for bf16 leaves) or torch.float32 - the
@@ -300,6 +317,7 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     row_target, n_valid = prepare_rows(labels, speech_token_mask, B, T, ignore_index, dev)
     n_norm = count_reduce_fn(n_valid) if count_reduce_fn is not None else n_valid
     y = None
+    topk_v = topk_i = None
     if teacher_logits is not None:
         y = teacher_logits.detach()
         if tuple(y.shape[-1:]) != (V,) or y.numel() != B * T * V:
@@ -309,16 +327,24 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
             y = y.contiguous()
         if y.dtype == torch.float16:
             y = y.float()
+    elif teacher_top_k_v is not None and teacher_top_k_i is not None:
+        K = teacher_top_k_v.size(-1)
+        if teacher_top_k_v.numel() != B * T * K or teacher_top_k_i.numel() != B * T * K:
+            raise ValueError(f"teacher top-k tensors do not match [B={B}, T={T}, K={K}]")
+        # :82-90 - values to fp32 on the student's device, indices to integer
+        topk_v = teacher_top_k_v.detach().to(device=dev, dtype=torch.float32).reshape(B * T, K).contiguous()
+        topk_i = teacher_top_k_i.detach().to(device=dev, dtype=torch.int32).reshape(B * T, K).contiguous()
+    topk = (topk_v, topk_i) if topk_v is not None else None
+    teacher_kind = _teacher_kind(y, topk)
     if _return_ctx:  # fused_linear_kd_value_and_grad: forward pieces without an autograd node
-        teacher_kind = _lib.KD_TEACHER_DENSE if y is not None else _lib.KD_TEACHER_NONE
-        sums, row_stats, _ = _fused_forward(h2, W, y, row_target, float(temperature), float(alpha), v_chunk)
+        sums, row_stats, _ = _fused_forward(h2, W, y, row_target, float(temperature), float(alpha), v_chunk, topk)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
-        eff_alpha = float(alpha) if y is not None else 1.0
-        losses = finalize_losses(sums, temperature, eff_alpha, False)
-        return losses, (h2.detach(), W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha)
+        eff_alpha = float(alpha) if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
+        losses = finalize_losses(sums, temperature, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
+        return losses, (h2.detach(), W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk)
     out = _KDFusedLinear.apply(h2, W, y, row_target, n_valid, n_norm, float(temperature), float(alpha),
-                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype)
+                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype, topk_v, topk_i)
     return out
 
 
@@ -345,13 +371,14 @@ class DistillationLoss(nn.Module):
         if student_logits is None:
             if student_hidden is None or lm_head_weight is None:
                 raise ValueError("pass student_logits, or student_hidden together with lm_head_weight")
-            if teacher_logits is None:
-                raise ValueError("Either teacher_logits or top_k must be provided")
+            if teacher_logits is None and (teacher_top_k_v is None or teacher_top_k_i is None):
+                raise ValueError("Either teacher_logits or top_k must be provided")  # distillation_loss.py:120
             out = fused_linear_kd_loss(student_hidden, lm_head_weight, labels, teacher_logits=teacher_logits,
                                        speech_token_mask=speech_token_mask, temperature=self.temperature,
-                                       alpha=self.alpha, ignore_index=self.ignore_index)
+                                       alpha=self.alpha, ignore_index=self.ignore_index,
+                                       teacher_top_k_v=teacher_top_k_v, teacher_top_k_i=teacher_top_k_i)
             ref_dtype = student_hidden.dtype
-            dense = True
+            dense = teacher_logits is not None
         else:
             out = kd_loss_on_logits(student_logits, labels, teacher_logits, teacher_top_k_v, teacher_top_k_i,
                                     speech_token_mask, self.temperature, self.alpha, self.ignore_index)

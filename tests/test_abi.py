@@ -35,7 +35,9 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in kd_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(_declared())
-    assert K.load_library().kd_version() == 1
+    header = open(os.path.join(ROOT, "include", "kd_b200.h")).read()
+    abi = int(re.search(r"#define KD_ABI_VERSION (\d+)", header).group(1))
+    assert K.load_library().kd_version() == abi == _lib.ABI_VERSION
     assert lib.kd_stream_workspace_bytes() > 0
 
 

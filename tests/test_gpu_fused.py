@@ -192,3 +192,91 @@ def test_dropin_fused_kwargs():
     out = fn(None, labels.cuda(), teacher_logits=y.cuda(), student_hidden=h.cuda(), lm_head_weight=W.cuda())
     ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_logits=y.float())
     np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-2)  # bf16 scalars
+
+
+# ---- sparse teacher inside K1 (BASELINE configs[2]: top-k cache + sparse KD, logits never materialised) -------
+def _topk_cache(y, k, dup=False, v_dtype=torch.float16):
+    """train.py:82-91 / extract_teacher_logits.py:114-129: log-probs at tau = 1, top-k, fp16 values, int32 indices."""
+    lp = torch.log_softmax(y.float(), dim=-1)
+    v, i = torch.topk(lp, k, dim=-1)
+    if dup:  # a cache with a repeated index (the reference gathers it twice and its gradient accumulates)
+        i[..., 1] = i[..., 0]
+    return v.to(v_dtype), i.int()
+
+
+@pytest.mark.parametrize("B,T,H,V,K,tau,alpha,dup", [
+    (2, 64, 64, 200, 8, 2.0, 0.5, False),        # every entry in the single (ragged) tile
+    (2, 100, 128, 1031, 64, 2.0, 0.5, True),     # ragged V, duplicate indices
+    (3, 128, 256, 5000, 100, 1.5, 0.3, False),   # K not a power of two, general tau
+    (2, 256, 1024, 20000, 64, 2.0, 0.5, False),  # student H, 3 backward chunks
+])
+def test_fused_sparse_matches_oracle(B, T, H, V, K, tau, alpha, dup):
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(131 + V, B, T, H, V)
+    tv, ti = _topk_cache(y, K, dup)
+    labels[1, 5] = int(ti[1, 4, 0])  # at least one label inside the top-k (teacher monitor hit)
+    ref, gh_ref, gw_ref = O.fused_linear_reference(h.double(), W.double(), labels, teacher_top_k_v=tv,
+                                                   teacher_top_k_i=ti, temperature=tau, alpha=alpha)
+    hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda(),
+                                  temperature=tau, alpha=alpha)
+    out[0].backward()
+    losses = [float(o) for o in out]
+    for got, want in zip(losses, [float(x) for x in ref]):
+        assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
+    _, gh32, gw32 = KD.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), temperature=tau, alpha=alpha,
+                                                      teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
+    eh32, ew32 = rel_err(gh32.cpu().numpy(), gh_ref.numpy()), rel_err(gw32.cpu().numpy(), gw_ref.numpy())
+    eh, ew = rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()), rel_err(Wc.grad.float().cpu().numpy(), gw_ref.numpy())
+    print(f"sparse dH err: bf16 {eh:.2e} fp32 {eh32:.2e} | dW err: bf16 {ew:.2e} fp32 {ew32:.2e}")
+    assert eh32 < 4e-3 and ew32 < 4e-3, (eh32, ew32)  # same bars as the dense form (bf16 G operand)
+    assert eh < 6e-3 and ew < 6e-3, (eh, ew)
+
+
+def test_fused_sparse_equals_streaming_sparse():
+    """K1 sparse and K2 sparse (materialised logits) agree, including the teacher monitor and a speech mask."""
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(177, 2, 128, 256, 4096)
+    tv, ti = _topk_cache(y, 64)
+    mask = torch.ones(2, 128)
+    mask[0, 40:60] = 0
+    out1 = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), speech_token_mask=mask.cuda(),
+                                   teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
+    z = h.cuda().float() @ W.cuda().float().t()
+    out2 = KD.kd_loss_on_logits(z, labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda(),
+                                speech_token_mask=mask.cuda())
+    np.testing.assert_allclose([float(o) for o in out1], [float(o) for o in out2], rtol=2e-4, atol=1e-6)
+
+
+def test_fused_sparse_no_hit_and_out_of_range():
+    """Label never in the top-k -> monitor exactly 0.0 (distillation_loss.py:116-118); an index outside
+    [0, V) is ignored instead of faulting (the reference's gather would raise)."""
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(19, 1, 64, 64, 700)
+    tv, ti = _topk_cache(y, 16)
+    labels[labels >= 0] = 699
+    ti[ti == 699] = 0
+    out = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
+    assert float(out[3]) == 0.0
+    ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
+    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-3, atol=1e-6)
+    ti2 = ti.clone()
+    ti2[0, 3, 5] = 100000
+    out2 = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti2.cuda())
+    assert all(np.isfinite(float(o)) for o in out2)
+
+
+def test_dropin_fused_sparse_kwargs():
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(6, 1, 64, 64, 700)
+    tv, ti = _topk_cache(y, 32)
+    fn = KD.DistillationLoss(temperature=2.0, alpha=0.5)
+    out = fn(None, labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda(), student_hidden=h.cuda(),
+             lm_head_weight=W.cuda())
+    ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
+    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-2)
+    assert out[0].dtype == torch.float32 and out[1].dtype == torch.bfloat16  # SURVEY.md a9 sparse dtypes
