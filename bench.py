@@ -34,7 +34,8 @@ def config(n_gpus):
     return {
         "workload": WORKLOAD, "B_per_gpu": B, "T": T, "H": H, "V": V, "tau": TAU, "alpha": ALPHA,
         "tokens_per_step_per_gpu": B * T, "global_batch": B * n_gpus,
-        "parallelism": f"token-shard dp{n_gpus}" if n_gpus > 1 else "single gpu",
+        "parallelism": (f"token-shard dp{n_gpus}, dW all-reduce (NCCL) "
+                        f"{os.environ.get('KD_BENCH_SYNC', 'overlap')} with the backward") if n_gpus > 1 else "single gpu",
         "l2": "inputs larger than L2 every step (teacher logits 1.25 GB + lm_head 313 MB vs 126 MB L2)",
     }
 
@@ -180,12 +181,19 @@ def run_ours(args):
         y[b] = (torch.randn(T, V, device=dev, generator=g) * 2).bfloat16()
     labels = torch.randint(0, V, (B, T), device=dev, generator=g)
     reduce_fn, count_fn = KD.make_reduce_fns()
+    # dW all-reduce: overlapped with the backward, range by range (default), or one call after it
+    sync_mode = os.environ.get("KD_BENCH_SYNC", "overlap") if world > 1 else "none"
+    sync = None
+    if sync_mode == "overlap":
+        max_ctas = int(os.environ.get("KD_BENCH_NCCL_CTAS", "16"))
+        sync = KD.GradSync(group=KD.GradSync.new_group(max_ctas), n_ranges=int(os.environ.get("KD_BENCH_RANGES", "6")),
+                           max_ctas=max_ctas if os.environ.get("KD_BENCH_SM_LIMIT", "1") == "1" else 0)
 
     def step(hh, yy, ll):
         out = K.fused_linear_kd_loss(hh, W, ll, teacher_logits=yy, temperature=TAU, alpha=ALPHA,
-                                     reduce_fn=reduce_fn, count_reduce_fn=count_fn)
+                                     reduce_fn=reduce_fn, count_reduce_fn=count_fn, grad_sync=sync)
         out[0].backward()
-        if world > 1:
+        if sync_mode == "serial":
             KD.allreduce_grad_(W.grad)
         return out
 
@@ -217,6 +225,15 @@ def run_ours(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     losses = [float(o) for o in out]
+    if os.environ.get("KD_BENCH_QUICK") == "1":  # tuning sweeps: device-resident step time only
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": float(t[0]),
+                              "value": B * T * world / (float(t[0]) * 1e-3), "sync": sync_mode}), flush=True)
+        return
 
     # ---- per-phase timing for the roofline (forward kernel = the largest single launch) ----
     # events are recorded around the C-ABI calls on the launching stream with NO host sync inside the loop,

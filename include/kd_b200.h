@@ -145,6 +145,22 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
                         void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
                         int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same backward restricted to vocabulary rows/columns [v_begin, v_end) (v_begin a multiple of 256), so a
+ * data-parallel caller can all-reduce finished dW row blocks while later ones are computed:
+ * dW rows of the range are final when the call's work completes; dH is accumulated in the workspace across
+ * calls (same workspace every call): KD_RANGE_FIRST starts the accumulation, KD_RANGE_LAST writes dH.
+ * sm_limit > 0 caps the SMs the GEMM kernels occupy (leave the rest to the collective's CTAs). */
+#define KD_RANGE_FIRST 1
+#define KD_RANGE_LAST 2
+int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                              int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
+                              const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target,
+                              const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
+                              const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
+                              int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
+                              int range_flags, int sm_limit, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* Plain bf16 GEMM on the same tcgen05 pipeline (test hook for the K1 building block), fp32 out:
  *   C[M,N] (ldc) = op(A) * op(B)^T with
  *   a_mn_major = 0: A is [M][K] (K contiguous, lda)   | 1: A is [K][M] (M contiguous, lda)

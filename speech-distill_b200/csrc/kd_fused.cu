@@ -1102,6 +1102,10 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
   return 0;
 }
 
+// SMs the persistent GEMM kernels may occupy in this call (0 = all); a data-parallel caller that overlaps the
+// dW all-reduce leaves NCCL's CTAs their own SMs, otherwise the last CTAs of every launch queue behind them
+static thread_local int tl_sm_limit = 0;
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -1138,7 +1142,9 @@ static int launch_umma_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     set_error("kd_umma: empty problem (units=%d, k blocks=%d)", g.num_units, g.num_k_blk);
     return 1;
   }
-  const int slots = sm_count() / CG;  // persistent: one CTA (pair) per SM (pair)
+  int sms = sm_count();
+  if (tl_sm_limit > 0 && tl_sm_limit < sms) sms = tl_sm_limit;
+  const int slots = sms / CG >= 1 ? sms / CG : 1;  // persistent: one CTA (pair) per SM (pair)
   const int grid = (g.num_units < slots ? g.num_units : slots) * CG;
   kern<<<grid, kThreads, smem, stream>>>(ta, tb, ty, tg, g, ep);
   return check_cuda(cudaGetLastError(), "kd_umma launch");
@@ -1457,7 +1463,32 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
                                    const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                                    int64_t dw_stride, int64_t dw_row_begin, int v_chunk, void* workspace,
                                    size_t workspace_bytes, void* stream) {
+  return kd_fused_linear_bwd_range(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K,
+                                   row_target, row_stats, R, H, V, tau, n_norm, grad_coef, grad_dtype, dH, dh_stride,
+                                   dW, dw_stride, dw_row_begin, v_chunk, 0, V, KD_RANGE_FIRST | KD_RANGE_LAST, 0,
+                                   workspace, workspace_bytes, stream);
+}
+
+struct SmLimitScope {
+  explicit SmLimitScope(int n) { tl_sm_limit = n; }
+  ~SmLimitScope() { tl_sm_limit = 0; }
+};
+
+extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
+                                         const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target,
+                                         const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
+                                         const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
+                                         int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
+                                         int range_flags, int sm_limit, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_bwd")) return 1;
+  if (v_begin < 0 || v_end > V || v_begin >= v_end || v_begin % BN != 0) {
+    set_error("kd_fused_linear_bwd_range: bad vocabulary range [%d, %d) (V=%d; begin must be a multiple of %d)",
+              v_begin, v_end, V, BN);
+    return 1;
+  }
+  SmLimitScope sm_scope(sm_limit);
   if (!row_target || !row_stats || !n_norm || !grad_coef || !workspace || (!dH && !dW)) {
     set_error("kd_fused_linear_bwd: null pointer argument");
     return 1;
@@ -1483,7 +1514,8 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
   float* dh32 = reinterpret_cast<float*>(wsp + ws.dh_off);
   const bool tau2 = tau == 2.0f;
   const size_t ys = y_dtype == KD_DTYPE_F32 ? 4 : 2;
-  const int n_chunks = cdiv(V, vc);
+  const int n_chunks = cdiv(v_end - v_begin, vc);
+  const bool range_first = (range_flags & KD_RANGE_FIRST) != 0, range_last = (range_flags & KD_RANGE_LAST) != 0;
 
   CUtensorMap t_h_k, t_w_k, t_g_k[2], t_g_mn[2], t_h_mn, t_w_mn, t_y;
   const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&t_y, y, y_dtype, y_stride, R, V);
@@ -1511,8 +1543,8 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
 
   for (int c = 0; c < n_chunks; ++c) {
     const int b = c & 1;
-    const int v0 = c * vc;
-    const int cols = V - v0 < vc ? V - v0 : vc;
+    const int v0 = v_begin + c * vc;
+    const int cols = v_end - v0 < vc ? v_end - v0 : vc;
     const int n_blks = cdiv(cols, BN);  // 256-wide column blocks of this chunk (G is zero-padded to the block)
     const bool need_dw = dW != nullptr && (int64_t)(v0 + cols) > dw_row_begin;
     // ---- 1. recompute logits tile, form G ----
@@ -1598,7 +1630,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
       g.n_per_unit = 1;
       g.num_units = g.num_m_blk * g.num_n_blk;
       StoreParams sp = {};
-      const bool first = c == 0, last = c == n_chunks - 1;
+      const bool first = range_first && c == 0, last = range_last && c == n_chunks - 1;
       sp.m_total = R;
       sp.n_total = H;
       sp.m_begin = 0;

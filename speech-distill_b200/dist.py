@@ -61,3 +61,78 @@ def allreduce_grad_(grad, group=None, bucket_rows=0):
     for h in handles:
         h.wait()
     return grad
+
+
+DEFAULT_V_CHUNK = 9472  # kDefaultVChunk of csrc/kd_fused.cu
+
+
+def plan_ranges(V, row_begin, v_chunk, n_ranges):
+    """Vocabulary ranges [v0, v1) for the overlapped dW all-reduce: whole backward chunks per range (so the
+    chunking inside the library is unchanged), at most ``n_ranges`` of them, the frozen rows below
+    ``row_begin`` (stage1) all in the first range.  Pure host logic (CPU-tested)."""
+    vc = int(v_chunk) if v_chunk and v_chunk > 0 else DEFAULT_V_CHUNK
+    vc = -(-vc // 256) * 256
+    n_chunks = -(-V // vc)
+    first_live = min(max(int(row_begin), 0) // vc, n_chunks - 1)  # chunk holding the first row with a gradient
+    live = n_chunks - first_live
+    n = max(1, min(int(n_ranges), live))
+    base, extra = divmod(live, n)
+    bounds, c = [0], first_live
+    for r in range(n):
+        c += base + (1 if r < extra else 0)
+        bounds.append(min(c * vc, V))
+    bounds[-1] = V
+    return [(bounds[i], bounds[i + 1]) for i in range(n)]
+
+
+class GradSync:
+    """SUM all-reduce of the LM-head gradient, row block by row block, overlapped with the K1 backward.
+
+    ``reduce_rows(dW, r0, r1)`` is called by the backward after each vocabulary range: the rows are final, the
+    all-reduce is enqueued asynchronously (NCCL's stream waits for the current stream at that point) and the
+    next range's GEMMs run beside it.  ``finish()`` makes the current stream wait for every all-reduce.
+    ``max_ctas`` bounds the SMs NCCL may take (process-group config where torch exposes it); the GEMM kernels
+    of the overlapped ranges are launched on ``sm_count - max_ctas`` SMs (kd_fused_linear_bwd_range sm_limit).
+    """
+
+    def __init__(self, group=None, n_ranges=6, max_ctas=16, sm_count=None):
+        self.group = group
+        self.n_ranges = int(n_ranges)
+        self.max_ctas = int(max_ctas)
+        self._sm_count = sm_count
+        self._pending = []
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    @staticmethod
+    def new_group(max_ctas=16, **kw):
+        """A NCCL process group whose collectives use at most ``max_ctas`` CTAs (falls back to the default
+        group configuration when this torch build does not expose the option)."""
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(max_ctas)
+            opts.config.min_ctas = min(int(max_ctas), 4)
+            return dist.new_group(backend="nccl", pg_options=opts, **kw)
+        except Exception:  # pragma: no cover - depends on the torch / NCCL build
+            return dist.new_group(**kw)
+
+    def ranges(self, V, row_begin, v_chunk):
+        if not self.active:
+            return [(0, V)]
+        return plan_ranges(V, row_begin, v_chunk, self.n_ranges)
+
+    def sm_limit(self):
+        if not self.active or self.max_ctas <= 0:
+            return 0
+        if self._sm_count is None:
+            self._sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        lim = self._sm_count - self.max_ctas
+        return lim - (lim % 2) if lim >= 2 else 0  # CTA pairs
+
+    def reduce_rows(self, grad, r0, r1):
+        if self.active and r1 > r0:
+            self._pending.append(dist.all_reduce(grad[r0:r1], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []

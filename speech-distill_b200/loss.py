@@ -211,7 +211,7 @@ def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None):
 class _KDFusedLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype,
-                topk_v=None, topk_i=None):
+                topk_v=None, topk_i=None, grad_sync=None):
         topk = (topk_v, topk_i) if topk_v is not None else None
         teacher_kind = _teacher_kind(y, topk)
         sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk)
@@ -223,6 +223,7 @@ class _KDFusedLinear(torch.autograd.Function):
         ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk), grad_dtype)
         ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm, topk_v, topk_i)
         ctx.ws = ws
+        ctx.grad_sync = grad_sync
         total, task, distill, teacher = losses.unbind(0)
         ctx.mark_non_differentiable(teacher)
         return total, task, distill, teacher
@@ -239,12 +240,15 @@ class _KDFusedLinear(torch.autograd.Function):
         w_kl = gt * (1.0 - alpha) + (zero if g_distill is None else g_distill.detach().float())
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
         dH, dW = _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin,
-                                 v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk)
-        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None
+                                 v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk,
+                                 ctx.grad_sync)
+        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin, v_chunk,
-                    grad_dtype, need_h, need_w, ws=None, topk=None):
+                    grad_dtype, need_h, need_w, ws=None, topk=None, grad_sync=None):
+    """kd_fused_linear_bwd, or - with ``grad_sync`` (dist.GradSync) - kd_fused_linear_bwd_range over a few
+    vocabulary ranges, handing each finished dW row block to the all-reduce while the next range runs."""
     lib = _lib.load()
     R, H = h.shape
     V = W.shape[0]
@@ -257,14 +261,25 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
         dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
     if ws is None:
         ws = _fused_workspace(R, H, V, v_chunk, dev, K)
-    rc = lib.kd_fused_linear_bwd(
-        h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
-        _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), row_stats.data_ptr(), R, H, V,
-        float(tau),
-        n_norm.data_ptr(), coef.data_ptr(), dtype_code(grad_dtype), _ptr(dH), H, _ptr(dW), H,
-        int(dw_row_begin), int(v_chunk), ws.data_ptr(), ws.numel(), stream_ptr(dev))
-    check(rc, "kd_fused_linear_bwd")
+    ranges = [(0, V)]
+    if grad_sync is not None and need_w:
+        ranges = grad_sync.ranges(V, int(dw_row_begin), int(v_chunk))
+    for n, (v0, v1) in enumerate(ranges):
+        flags = (_lib.KD_RANGE_FIRST if n == 0 else 0) | (_lib.KD_RANGE_LAST if n == len(ranges) - 1 else 0)
+        # while an all-reduce is in flight its CTAs keep their SMs: the persistent GEMMs take the others
+        sm_limit = grad_sync.sm_limit() if (grad_sync is not None and n > 0) else 0
+        rc = lib.kd_fused_linear_bwd_range(
+            h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
+            _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
+            _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), row_stats.data_ptr(),
+            R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), dtype_code(grad_dtype), _ptr(dH), H, _ptr(dW), H,
+            int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), ws.data_ptr(), ws.numel(),
+            stream_ptr(dev))
+        check(rc, "kd_fused_linear_bwd_range")
+        if grad_sync is not None and need_w:
+            grad_sync.reduce_rows(dW, max(v0, int(dw_row_begin)), v1)
+    if grad_sync is not None and need_w:
+        grad_sync.finish()
     return dH, dW
 
 
@@ -290,7 +305,7 @@ def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logit
 def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                          temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
                          reduce_fn=None, count_reduce_fn=None, grad_dtype=torch.bfloat16, teacher_top_k_v=None,
-                         teacher_top_k_i=None, _return_ctx=False):
+                         teacher_top_k_i=None, grad_sync=None, _return_ctx=False):
     """``DistillationLoss(student_logits = hidden @ lm_head_weight.T, ...)`` without the logits.
 
     hidden [B,T,H] (or [R,H] with labels [.., T]) bf16, lm_head_weight [V,H] bf16, labels [B,T].
@@ -301,6 +316,9 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     the old vocabulary size; rows below stay exactly zero and are never computed).
     ``grad_dtype``: torch.bfloat16 (what autograd requires for bf16 leaves) or torch.float32 - the
     unrounded fp32 accumulators, usable only with non-leaf / fp32-grad consumers (verification).
+    ``reduce_fn`` / ``count_reduce_fn`` / ``grad_sync``: token-shard data-parallel hooks (dist.py): all-reduce of
+    the sums record and of the valid-row count, and the dW all-reduce overlapped with the backward
+    (the weight gradient autograd receives is then already summed over ranks).
     """
     require_cuda(hidden, lm_head_weight)
     if hidden.dtype != torch.bfloat16 or lm_head_weight.dtype != torch.bfloat16:
@@ -344,7 +362,7 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
         losses = finalize_losses(sums, temperature, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
         return losses, (h2.detach(), W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk)
     out = _KDFusedLinear.apply(h2, W, y, row_target, n_valid, n_norm, float(temperature), float(alpha),
-                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype, topk_v, topk_i)
+                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype, topk_v, topk_i, grad_sync)
     return out
 
 

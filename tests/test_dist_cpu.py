@@ -67,3 +67,49 @@ def test_token_shard_reduction_matches_single_process():
     assert n == int((lab[:, 1:] != -100).sum())
     np.testing.assert_allclose(losses, [float(x) for x in ref], rtol=1e-12)
     np.testing.assert_allclose(grad, gref.numpy(), rtol=1e-9, atol=1e-15)
+
+
+def test_plan_ranges_properties():
+    """Ranges tile [0, V), start on backward-chunk boundaries, and keep stage1's frozen rows in the first one."""
+    from speech_distill_b200.dist import plan_ranges
+
+    for V, row_begin, vc, n in [(152936, 0, 0, 6), (152936, 151936, 0, 6), (5000, 0, 1024, 3), (300, 0, 0, 6),
+                                (20000, 9000, 4096, 8), (152936, 0, 37888, 4)]:
+        r = plan_ranges(V, row_begin, vc, n)
+        chunk = -(-(vc if vc > 0 else 9472) // 256) * 256
+        assert r[0][0] == 0 and r[-1][1] == V and 1 <= len(r) <= n
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(v0 % chunk == 0 and v1 > v0 for v0, v1 in r)
+        assert all(v1 > row_begin for v0, v1 in r)  # every range owns at least one live row
+
+
+def _sync_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import speech_distill_b200.dist as D
+
+    sync = D.GradSync(n_ranges=3, max_ctas=0)
+    V, H = 1000, 4
+    g = torch.full((V, H), float(rank + 1))
+    for v0, v1 in sync.ranges(V, 0, 256):
+        sync.reduce_rows(g, v0, v1)
+    sync.finish()
+    if rank == 0:
+        out_q.put((sync.ranges(V, 0, 256), g.numpy()))
+    dist.destroy_process_group()
+
+
+def test_grad_sync_reduces_every_row_block():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ranges, g = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(ranges) == 3
+    np.testing.assert_array_equal(g, np.full((1000, 4), 3.0))

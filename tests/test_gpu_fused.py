@@ -280,3 +280,50 @@ def test_dropin_fused_sparse_kwargs():
     ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
     np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-2)
     assert out[0].dtype == torch.float32 and out[1].dtype == torch.bfloat16  # SURVEY.md a9 sparse dtypes
+
+
+class _RangeStub:
+    """Stands in for dist.GradSync on one GPU: same range plan and SM limit, records the row blocks handed over."""
+
+    def __init__(self, n_ranges, sm_limit):
+        self.n_ranges, self._lim, self.blocks = n_ranges, sm_limit, []
+
+    def ranges(self, V, row_begin, v_chunk):
+        from speech_distill_b200.dist import plan_ranges
+
+        return plan_ranges(V, row_begin, v_chunk, self.n_ranges)
+
+    def sm_limit(self):
+        return self._lim
+
+    def reduce_rows(self, grad, r0, r1):
+        self.blocks.append((r0, r1))
+
+    def finish(self):
+        self.blocks.append("finish")
+
+
+@pytest.mark.parametrize("old_vocab", [0, 2700])
+def test_fused_backward_ranges_bit_identical(old_vocab):
+    """kd_fused_linear_bwd_range over several vocabulary ranges (with an SM limit) = the one-call backward,
+    bit for bit: same chunks, same accumulation order; the row blocks handed to the all-reduce tile dW."""
+    import speech_distill_b200 as KD
+
+    B, T, H, V = 2, 128, 256, 5000
+    h, W, y, labels = _case(311, B, T, H, V)
+
+    def run(sync):
+        hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+        out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), teacher_logits=y.cuda(), dw_row_begin=old_vocab,
+                                      v_chunk=1024, grad_sync=sync)
+        out[0].backward()
+        return hc.grad, Wc.grad
+
+    gh0, gw0 = run(None)
+    stub = _RangeStub(3, 100)
+    gh1, gw1 = run(stub)
+    assert torch.equal(gh0, gh1) and torch.equal(gw0, gw1)
+    assert stub.blocks[-1] == "finish"
+    blocks = stub.blocks[:-1]
+    assert blocks[0][0] == old_vocab and blocks[-1][1] == V
+    assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
