@@ -44,6 +44,10 @@ extern "C" {
 
 #define KD_ABI_VERSION 2
 
+/* OR-ed into grad_dtype of the fused backward: dH is written as fp32 (a vocab-parallel caller sums the
+ * per-slice partial dH across ranks before rounding) while dW keeps the base dtype. */
+#define KD_GRAD_DH_F32 0x100
+
 /* Teacher kinds for the fused LM-head entry points. */
 #define KD_TEACHER_NONE 0   /* CE only (stage1 warm-up, stage1.py:298-340) */
 #define KD_TEACHER_DENSE 1  /* full-vocab teacher logits (distillation_loss.py:56-71) */
@@ -149,7 +153,8 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
  * data-parallel caller can all-reduce finished dW row blocks while later ones are computed:
  * dW rows of the range are final when the call's work completes; dH is accumulated in the workspace across
  * calls (same workspace every call): KD_RANGE_FIRST starts the accumulation, KD_RANGE_LAST writes dH.
- * sm_limit > 0 caps the SMs the GEMM kernels occupy (leave the rest to the collective's CTAs). */
+ * sm_limit > 0 caps the SMs the GEMM kernels occupy (leave the rest to the collective's CTAs).
+ * v_offset: 0, or the first vocabulary index of this rank's slice in vocab-parallel mode (see below). */
 #define KD_RANGE_FIRST 1
 #define KD_RANGE_LAST 2
 int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
@@ -158,8 +163,25 @@ int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, in
                               const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
                               const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                               int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
-                              int range_flags, int sm_limit, void* workspace, size_t workspace_bytes,
-                              void* stream);
+                              int range_flags, int sm_limit, int v_offset, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ---- vocab-parallel mode: every rank holds W[v_offset : v_offset + V, :] (V = its slice) and the
+ * matching teacher columns, all ranks see the same rows.  kd_fused_linear_fwd_partial runs the forward over the
+ * slice and writes one 12-float record per row (running max / sums of the 4 soft-maxes, KL cross term, label
+ * logits owned by the slice, sparse row constants); the caller all-gathers the records [G][R][12] and
+ * kd_fused_merge_ranks applies the split-V merge rule (appendix C) -> sums[8] + row_stats[R,4], identical on every
+ * rank.  The backward is kd_fused_linear_bwd_range on the slice with the same v_offset (labels and top-k indices
+ * stay global): dW rows of the slice are final, dH is this slice's partial sum (all-reduce it in fp32). */
+int kd_fused_linear_fwd_partial(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                                int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
+                                const float* topk_v, const int32_t* topk_i, int K,
+                                const int32_t* row_target, int R, int H, int V, int v_offset, float tau,
+                                float* rank_rec, void* workspace, size_t workspace_bytes, void* stream);
+size_t kd_fused_merge_workspace_bytes(void);
+int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_target, int R, int teacher_kind,
+                         float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* Plain bf16 GEMM on the same tcgen05 pipeline (test hook for the K1 building block), fp32 out:
  *   C[M,N] (ldc) = op(A) * op(B)^T with

@@ -13,6 +13,7 @@ KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
 KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
 ABI_VERSION = 2  # KD_ABI_VERSION in include/kd_b200.h
 KD_RANGE_FIRST, KD_RANGE_LAST = 1, 2
+KD_GRAD_DH_F32 = 0x100
 
 _c = ctypes
 _vp, _i32, _i64, _f32, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
@@ -40,7 +41,11 @@ SIGNATURES = {
                                    _vp]),
     "kd_fused_linear_bwd_range": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32,
                                          _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _i32,
-                                         _i32, _i32, _i32, _vp, _sz, _vp]),
+                                         _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "kd_fused_linear_fwd_partial": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32,
+                                           _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
+    "kd_fused_merge_workspace_bytes": (_sz, []),
+    "kd_fused_merge_ranks": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
 }
 

@@ -46,6 +46,9 @@ constexpr int kStepBoxes = kStepCols / 64;       // 64-column (128-byte row) TMA
 constexpr uint32_t kBoxBytes = BM * 64 * 2;      // 16 KB: [128 rows x 64 cols] of a 16-bit type, swizzled 128 B rows
 constexpr uint32_t kStepBytes = kStepBoxes * kBoxBytes;  // 32 KB
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
+// per-row record one vocabulary slice hands to the cross-rank merge (vocab-parallel mode):
+// m, s1, st, mt | t1, tt, a, z_label | y_label, sum p log p, hit value sum, hits
+constexpr int kRankRecFloats = 12;
 
 // shared-memory plan of one kernel instantiation: as many operand stages as fit beside the epilogue rings
 template <int CG, int YSLOTS, int GSLOTS>
@@ -187,6 +190,15 @@ struct SparseView {
   int K, off_stride;
 };
 
+// label of a row in this call's column space: row_target - label_off when it falls inside [0, V), a far-away
+// sentinel when another vocabulary slice owns it (vocab-parallel); `valid` is the row predicate itself
+constexpr int kLabelElsewhere = -(1 << 30);
+__device__ __forceinline__ int local_target(int row_target, int label_off, int V, bool& valid) {
+  valid = row_target >= 0;
+  const int t = row_target - label_off;
+  return (valid && t >= 0 && t < V) ? t : kLabelElsewhere;
+}
+
 // ---- forward: online statistics -------------------------------------------------------------
 struct FwdParams {
   const int32_t* row_target;
@@ -196,6 +208,7 @@ struct FwdParams {
   int R, V;
   float inv_tau;
   float* partials;  // [num_ranges * kColGroups][R][kRecFloats]
+  int label_off;    // vocab-parallel: this call's columns are vocabulary [label_off, label_off + V)
   SparseView sp;    // sparse teacher (index-sorted entries + per-tile offsets), unused otherwise
   int debug_skip_math;  // KD_DEBUG_SKIP_MATH=1: bring-up knob that measures the pipeline without the epilogue math
 };
@@ -210,6 +223,7 @@ struct FwdEpi {
   const Params& p;
   EpiThread t;
   int row, target, range;
+  bool valid;
   float m, s1, st, mt, t1, tt, a, zl;
   YRing ring;
 
@@ -218,7 +232,7 @@ struct FwdEpi {
   __device__ void begin_unit(const Geom&, int m0, int range_) {
     row = m0 + t.row_in_tile;
     range = range_;
-    target = row < p.R ? p.row_target[row] : -1;
+    target = local_target(row < p.R ? p.row_target[row] : -1, p.label_off, p.V, valid);
     m = mt = -CUDART_INF_F;
     s1 = st = t1 = tt = a = zl = 0.f;
   }
@@ -253,7 +267,7 @@ struct FwdEpi {
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int col_base = g.b_n0 + n_blk * BN + t.cgrp * 32;
     int e_beg = 0, e_end = 0;
-    if (SPARSE && target >= 0) {  // this row's teacher entries inside the tile
+    if (SPARSE && valid) {  // this row's teacher entries inside the tile
       const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + (g.b_n0 / BN + n_blk);
       e_beg = o[0];
       e_end = o[1];
@@ -275,7 +289,7 @@ struct FwdEpi {
       }
       const int col0 = col_base + c * kStepCols;
       const int nrem = p.V - col0;
-      if (target < 0 || nrem <= 0 || p.debug_skip_math) continue;
+      if (!valid || nrem <= 0 || p.debug_skip_math) continue;
       if (SPARSE) {  // cross term sum_k p_k z[i_k] (distillation_loss.py:101-106): rare, predicated pick-up
         for (int e = e_beg; e < e_end; ++e) {
           const unsigned d = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col0);
@@ -330,6 +344,7 @@ struct GradParams {
   const int32_t* n_norm;
   const float* coef;  // device float[2]: weight of d(sum CE) and of tau^2 d(sum KL) in the returned gradient
   int v0;             // first vocabulary column of this chunk; scratch column j <-> vocabulary index v0 + j
+  int label_off;      // vocab-parallel: column v of this call is vocabulary index label_off + v
   SparseView sp;      // sparse teacher, see FwdParams
 };
 
@@ -343,6 +358,7 @@ struct GradEpi {
   const Params& p;
   EpiThread t;
   int row, target, m0;
+  bool valid;
   float c1, c2, c_tau, off1, offt, offy, half_off1, k_tau;
   YRing ring;
 
@@ -357,8 +373,8 @@ struct GradEpi {
   __device__ void begin_unit(const Geom&, int m0_, int) {
     m0 = m0_;
     row = m0 + t.row_in_tile;
-    target = row < p.R ? p.row_target[row] : -1;
-    if (target >= 0) {
+    target = local_target(row < p.R ? p.row_target[row] : -1, p.label_off, p.V, valid);
+    if (valid) {
       const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
       off1 = rs.x * kLog2e;
       offt = rs.y * kLog2e;
@@ -423,7 +439,7 @@ struct GradEpi {
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int jtile = n_blk * BN;  // first scratch column of this tile
     int e_beg = 0, e_end = 0;
-    if (SPARSE && target >= 0) {
+    if (SPARSE && valid) {
       const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + ((p.v0 + jtile) / BN);
       e_beg = o[0];
       e_end = o[1];
@@ -449,7 +465,7 @@ struct GradEpi {
       uint4 out[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) out[q] = make_uint4(0, 0, 0, 0);
-      if (target >= 0 && nrem > 0) {
+      if (valid && nrem > 0) {
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
@@ -865,6 +881,10 @@ struct MergeParams {
   float inv_tau;
   float* row_stats;     // [R][4]
   float* block_sums;    // [gridDim.x][8]
+  // vocab-parallel: when rank_rec != nullptr the kernel stops after merging this rank's column partials and
+  // writes one kRankRecFloats record per row (nothing is finalised; kd_fused_merge_ranks does that)
+  float* rank_rec;      // [R][kRankRecFloats]
+  int label_off;
 };
 
 __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p) {
@@ -874,7 +894,8 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
   for (int row = blockIdx.x * 8 + warp; row < p.R; row += gridDim.x * 8) {
     const int target = p.row_target[row];
     if (target < 0) {
-      if (lane == 0) *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0 && p.rank_rec == nullptr)
+        *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
     float m = -CUDART_INF_F, s1 = 0.f, st = 0.f, mt = -CUDART_INF_F, t1 = 0.f, tt = 0.f, a = 0.f, zl = 0.f;
@@ -901,7 +922,21 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
       }
       zl += __shfl_xor_sync(0xffffffffu, zl, o);
     }
-    if (lane == 0) {
+    if (lane == 0 && p.rank_rec != nullptr) {
+      const int tl = target - p.label_off;
+      float yl = 0.f;
+      if (p.dense && tl >= 0 && tl < p.V) {
+        const int64_t off = (int64_t)row * p.y_stride + tl;
+        if (p.y_dtype == KD_DTYPE_F32) yl = reinterpret_cast<const float*>(p.y)[off];
+        else if (p.y_dtype == KD_DTYPE_BF16) yl = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.y)[off]);
+        else yl = __half2float(reinterpret_cast<const __half*>(p.y)[off]);
+      }
+      const float4 rc = p.sparse ? p.sp_rowc[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* rec = p.rank_rec + (size_t)row * kRankRecFloats;
+      *reinterpret_cast<float4*>(rec) = make_float4(m, s1, st, mt);
+      *reinterpret_cast<float4*>(rec + 4) = make_float4(t1, tt, a, zl);
+      *reinterpret_cast<float4*>(rec + 8) = make_float4(yl, rc.x, rc.y, rc.z);
+    } else if (lane == 0) {
       const float lse1 = m + ln_acc(s1);
       const float lset = m * p.inv_tau + ln_acc(st);
       float lsett = 0.f;
@@ -926,6 +961,72 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
       *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(lse1, lset, lsett, 1.f);
     }
   }
+  if (p.rank_rec != nullptr) return;  // block-uniform
+  if (lane == 0) {
+    sm[warp][0] = ce; sm[warp][1] = kl; sm[warp][2] = tce; sm[warp][3] = nv; sm[warp][4] = hits;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = 0.f;
+    if (threadIdx.x < 5)
+      for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+    p.block_sums[(size_t)blockIdx.x * kNumPartialSlots + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vocab-parallel: merge the per-slice row records of all ranks (SURVEY.md 8e "optional mode" = the split-V
+// merge rule of appendix C across GPUs) -> row_stats + loss sums.  One thread per row, ranks in fixed order.
+// ---------------------------------------------------------------------------------------------
+struct RankMergeParams {
+  const float* rec;  // [G][R][kRankRecFloats]
+  int G, R;
+  const int32_t* row_target;
+  int dense, sparse;
+  float inv_tau;
+  float* row_stats;
+  float* block_sums;
+};
+
+__global__ void __launch_bounds__(256) kd_fused_rank_merge_kernel(const RankMergeParams p) {
+  __shared__ float sm[8][5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ce = 0.f, kl = 0.f, tce = 0.f, nv = 0.f, hits = 0.f;
+  for (int row = blockIdx.x * 256 + threadIdx.x; row < p.R; row += gridDim.x * 256) {
+    if (p.row_target[row] < 0) {
+      *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float m = -CUDART_INF_F, s1 = 0.f, st = 0.f, mt = -CUDART_INF_F, t1 = 0.f, tt = 0.f, a = 0.f, zl = 0.f, yl = 0.f;
+    float4 w8 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < p.G; ++g) {
+      const float* rec = p.rec + ((size_t)g * p.R + row) * kRankRecFloats;
+      const float4 x = *reinterpret_cast<const float4*>(rec);
+      const float4 w = *reinterpret_cast<const float4*>(rec + 4);
+      w8 = *reinterpret_cast<const float4*>(rec + 8);  // sparse row constants are identical on every rank
+      merge_student(m, s1, st, x.x, x.y, x.z, p.inv_tau);
+      if (p.dense) merge_teacher(mt, t1, tt, a, x.w, w.x, w.y, w.z, p.inv_tau);
+      else a += w.z;
+      zl += w.w;
+      yl += w8.x;
+    }
+    const float lse1 = m + ln_acc(s1);
+    const float lset = m * p.inv_tau + ln_acc(st);
+    float lsett = 0.f;
+    ce += lse1 - zl;
+    if (p.dense) {
+      lsett = mt * p.inv_tau + ln_acc(tt);
+      kl += a * p.inv_tau / tt - lsett + lset;
+      tce += (mt + ln_acc(t1)) - yl;
+    } else if (p.sparse) {
+      kl += w8.y - a * p.inv_tau + lset;
+      tce += w8.z;
+      hits += w8.w;
+    }
+    nv += 1.f;
+    *reinterpret_cast<float4*>(p.row_stats + (size_t)row * 4) = make_float4(lse1, lset, lsett, 1.f);
+  }
+  ce = warp_sum(ce); kl = warp_sum(kl); tce = warp_sum(tce); nv = warp_sum(nv); hits = warp_sum(hits);
   if (lane == 0) {
     sm[warp][0] = ce; sm[warp][1] = kl; sm[warp][2] = tce; sm[warp][3] = nv; sm[warp][4] = hits;
   }
@@ -951,6 +1052,7 @@ struct SparsePrepParams {
   const int32_t* idx;  // [R][K]
   const int32_t* row_target;
   int R, K, Kp2, V, n_off;  // n_off = number of tile offsets per row (tiles + 1)
+  int idx_off;              // vocab-parallel: entries are kept when idx - idx_off falls in [0, V)
   float inv_tau;
   int32_t* s_idx;
   float* s_p;
@@ -999,7 +1101,8 @@ __global__ void __launch_bounds__(kPrepThreads) kd_sparse_prepare_kernel(const S
           hits += 1.f;
           hit_sum += vrow[k];
         }
-        if (i >= 0 && i < p.V) key = i;  // out-of-range entries sort to the end and are never visited
+        const int il = i - p.idx_off;
+        if (i >= 0 && il >= 0 && il < p.V) key = il;  // out-of-range entries sort to the end, never visited
       }
       keys[k] = key;
       vals[k] = pk;
@@ -1311,7 +1414,7 @@ static BwdPipe* get_bwd_pipe() {
 
 // sparse teacher: validate, run the preparation kernel into `region`, return the view for the epilogues
 static int prepare_sparse(const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target, int R, int V,
-                          float tau, const Workspace& ws, uint8_t* region, SparseView* view, const float4** rowc,
+                          int v_offset, float tau, const Workspace& ws, uint8_t* region, SparseView* view, const float4** rowc,
                           cudaStream_t s, const char* who) {
   if (!topk_v || !topk_i || K <= 0 || K > kMaxFusedTopK) {
     set_error("%s: sparse teacher needs topk_v, topk_i and 1 <= K <= %d (K=%d)", who, kMaxFusedTopK, K);
@@ -1327,6 +1430,7 @@ static int prepare_sparse(const float* topk_v, const int32_t* topk_i, int K, con
   pp.K = K;
   pp.Kp2 = Kp2;
   pp.V = V;
+  pp.idx_off = v_offset;
   pp.n_off = ws.sp_n_off;
   pp.inv_tau = 1.0f / tau;
   pp.s_idx = reinterpret_cast<int32_t*>(region + ws.sp_idx_rel);
@@ -1364,14 +1468,78 @@ extern "C" size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int
   return plan_workspace(R, H, V, v_chunk, K).total;
 }
 
+static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
+                          const void* y, int y_dtype, int64_t y_stride, const float* topk_v, const int32_t* topk_i,
+                          int K, const int32_t* row_target, int R, int H, int V, int v_offset, float tau, float* sums,
+                          float* row_stats, float* rank_rec, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                                    const void* y, int y_dtype, int64_t y_stride, const float* topk_v,
                                    const int32_t* topk_i, int K, const int32_t* row_target, int R, int H, int V,
                                    float tau, float alpha, float* sums, float* row_stats, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   (void)alpha;
+  if (!sums || !row_stats) {
+    set_error("kd_fused_linear_fwd: null pointer argument");
+    return 1;
+  }
+  return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target, R,
+                        H, V, 0, tau, sums, row_stats, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int kd_fused_linear_fwd_partial(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                                           int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
+                                           const float* topk_v, const int32_t* topk_i, int K,
+                                           const int32_t* row_target, int R, int H, int V, int v_offset, float tau,
+                                           float* rank_rec, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!rank_rec || v_offset < 0) {
+    set_error("kd_fused_linear_fwd_partial: null record buffer or negative vocabulary offset");
+    return 1;
+  }
+  return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target, R,
+                        H, V, v_offset, tau, nullptr, nullptr, rank_rec, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t kd_fused_merge_workspace_bytes(void) {
+  return (size_t)(kMergeBlocksMax + 1) * kNumPartialSlots * sizeof(float);
+}
+
+extern "C" int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_target, int R, int teacher_kind,
+                                    float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  if (!rank_recs || !row_target || !sums || !row_stats || !workspace || G <= 0 || R <= 0 || !(tau > 0.f)) {
+    set_error("kd_fused_merge_ranks: bad arguments");
+    return 1;
+  }
+  if (workspace_bytes < kd_fused_merge_workspace_bytes() || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) {
+    set_error("kd_fused_merge_ranks: workspace too small or misaligned (need %zu bytes)",
+              kd_fused_merge_workspace_bytes());
+    return 1;
+  }
+  RankMergeParams mp = {};
+  mp.rec = rank_recs;
+  mp.G = G;
+  mp.R = R;
+  mp.row_target = row_target;
+  mp.dense = teacher_kind == KD_TEACHER_DENSE ? 1 : 0;
+  mp.sparse = teacher_kind == KD_TEACHER_SPARSE ? 1 : 0;
+  mp.inv_tau = 1.0f / tau;
+  mp.row_stats = row_stats;
+  mp.block_sums = reinterpret_cast<float*>(workspace);
+  int blocks = cdiv(R, 256);
+  if (blocks > kMergeBlocksMax) blocks = kMergeBlocksMax;
+  cudaStream_t s = (cudaStream_t)stream;
+  kd_fused_rank_merge_kernel<<<blocks, 256, 0, s>>>(mp);
+  if (check_cuda(cudaGetLastError(), "kd_fused_rank_merge launch")) return 1;
+  return reduce_partials(mp.block_sums, blocks, sums, s);
+}
+
+static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
+                          const void* y, int y_dtype, int64_t y_stride, const float* topk_v, const int32_t* topk_i,
+                          int K, const int32_t* row_target, int R, int H, int V, int v_offset, float tau, float* sums,
+                          float* row_stats, float* rank_rec, void* workspace, size_t workspace_bytes, void* stream) {
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_fwd")) return 1;
-  if (!row_target || !sums || !row_stats || !workspace) {
+  if (!row_target || !workspace) {
     set_error("kd_fused_linear_fwd: null pointer argument");
     return 1;
   }
@@ -1411,6 +1579,7 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
   fp.V = V;
   fp.inv_tau = 1.0f / tau;
   fp.partials = partials;
+  fp.label_off = v_offset;
   {
     const char* e = getenv("KD_DEBUG_SKIP_MATH");
     fp.debug_skip_math = (e && e[0] == '1') ? 1 : 0;
@@ -1424,7 +1593,7 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
     rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, y_tma ? &ty : nullptr, g, fp, tau2, s)
                                   : launch_fwd<true, float>(ta, tb, nullptr, g, fp, tau2, s);
   } else if (sparse) {
-    if (prepare_sparse(topk_v, topk_i, K, row_target, R, V, tau, ws, wsp + ws.fwd_bytes, &fp.sp, &sp_rowc, s,
+    if (prepare_sparse(topk_v, topk_i, K, row_target, R, V, v_offset, tau, ws, wsp + ws.fwd_bytes, &fp.sp, &sp_rowc, s,
                        "kd_fused_linear_fwd"))
       return 1;
     rc = tau2 ? launch_umma<FwdEpi<__nv_bfloat16, false, true, false, true>, false, false>(ta, tb, g, fp, s)
@@ -1449,10 +1618,13 @@ extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* 
   mp.inv_tau = 1.0f / tau;
   mp.row_stats = row_stats;
   mp.block_sums = bsums;
+  mp.rank_rec = rank_rec;
+  mp.label_off = v_offset;
   int blocks = cdiv(R, 8);
   if (blocks > kMergeBlocksMax) blocks = kMergeBlocksMax;
   kd_fused_merge_kernel<<<blocks, 256, 0, s>>>(mp);
   if (check_cuda(cudaGetLastError(), "kd_fused_merge launch")) return 1;
+  if (rank_rec != nullptr) return 0;  // vocab-parallel: the cross-rank merge finalises
   return reduce_partials(bsums, blocks, sums, s);
 }
 
@@ -1465,7 +1637,7 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
                                    size_t workspace_bytes, void* stream) {
   return kd_fused_linear_bwd_range(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K,
                                    row_target, row_stats, R, H, V, tau, n_norm, grad_coef, grad_dtype, dH, dh_stride,
-                                   dW, dw_stride, dw_row_begin, v_chunk, 0, V, KD_RANGE_FIRST | KD_RANGE_LAST, 0,
+                                   dW, dw_stride, dw_row_begin, v_chunk, 0, V, KD_RANGE_FIRST | KD_RANGE_LAST, 0, 0,
                                    workspace, workspace_bytes, stream);
 }
 
@@ -1480,8 +1652,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
                                          const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
                                          const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                                          int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
-                                         int range_flags, int sm_limit, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+                                         int range_flags, int sm_limit, int v_offset, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_bwd")) return 1;
   if (v_begin < 0 || v_end > V || v_begin >= v_end || v_begin % BN != 0) {
     set_error("kd_fused_linear_bwd_range: bad vocabulary range [%d, %d) (V=%d; begin must be a multiple of %d)",
@@ -1504,11 +1676,13 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     set_error("kd_fused_linear_bwd: workspace too small or not 256-byte aligned (need %zu)", ws.total);
     return 1;
   }
-  if (grad_dtype != KD_DTYPE_BF16 && grad_dtype != KD_DTYPE_F32) {
-    set_error("kd_fused_linear_bwd: grad_dtype must be KD_DTYPE_BF16 or KD_DTYPE_F32");
+  const int dw_dtype = grad_dtype & 0xff;
+  if (dw_dtype != KD_DTYPE_BF16 && dw_dtype != KD_DTYPE_F32) {
+    set_error("kd_fused_linear_bwd: grad_dtype must be KD_DTYPE_BF16 or KD_DTYPE_F32 (optionally | KD_GRAD_DH_F32)");
     return 1;
   }
-  const bool out32 = grad_dtype == KD_DTYPE_F32;
+  const bool out32 = dw_dtype == KD_DTYPE_F32;                            // dW
+  const bool dh_out32 = out32 || (grad_dtype & KD_GRAD_DH_F32) != 0;      // dH
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
   float* dh32 = reinterpret_cast<float*>(wsp + ws.dh_off);
@@ -1530,7 +1704,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   if (make_tmap(&t_w_mn, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, 64, "lm_head weight (MN-major)")) return 1;
 
   SparseView sp_view = {};
-  if (sparse && prepare_sparse(topk_v, topk_i, K, row_target, R, V, tau, ws, wsp + ws.bwd_bytes, &sp_view, nullptr, s,
+  if (sparse && prepare_sparse(topk_v, topk_i, K, row_target, R, V, v_offset, tau, ws, wsp + ws.bwd_bytes, &sp_view, nullptr, s,
                                "kd_fused_linear_bwd"))
     return 1;
 
@@ -1574,6 +1748,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       gp.n_norm = n_norm;
       gp.coef = grad_coef;
       gp.v0 = v0;
+      gp.label_off = v_offset;
       gp.sp = sp_view;
       int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
@@ -1634,7 +1809,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       sp.m_total = R;
       sp.n_total = H;
       sp.m_begin = 0;
-      if (out32) {  // accumulate straight into the caller's fp32 dH
+      if (dh_out32) {  // accumulate straight into the caller's fp32 dH
         sp.mode = first ? kStoreF32 : kAccumF32;
         sp.c32 = reinterpret_cast<float*>(dH);
         sp.ld32 = dh_stride;

@@ -246,7 +246,7 @@ class _KDFusedLinear(torch.autograd.Function):
 
 
 def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin, v_chunk,
-                    grad_dtype, need_h, need_w, ws=None, topk=None, grad_sync=None):
+                    grad_dtype, need_h, need_w, ws=None, topk=None, grad_sync=None, v_offset=0, dh_fp32=False):
     """kd_fused_linear_bwd, or - with ``grad_sync`` (dist.GradSync) - kd_fused_linear_bwd_range over a few
     vocabulary ranges, handing each finished dW row block to the all-reduce while the next range runs."""
     lib = _lib.load()
@@ -254,8 +254,9 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
     V = W.shape[0]
     dev = h.device
     K = topk[0].size(-1) if teacher_kind == _lib.KD_TEACHER_SPARSE else 0
-    dH = torch.empty((R, H), dtype=grad_dtype, device=dev) if need_h else None
+    dH = torch.empty((R, H), dtype=torch.float32 if dh_fp32 else grad_dtype, device=dev) if need_h else None
     dW = None
+    gcode = dtype_code(grad_dtype) | (_lib.KD_GRAD_DH_F32 if dh_fp32 else 0)
     if need_w:
         # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
         dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
@@ -272,9 +273,9 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
             h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
             _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
             _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), row_stats.data_ptr(),
-            R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), dtype_code(grad_dtype), _ptr(dH), H, _ptr(dW), H,
-            int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), ws.data_ptr(), ws.numel(),
-            stream_ptr(dev))
+            R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), gcode, _ptr(dH), H, _ptr(dW), H,
+            int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), int(v_offset), ws.data_ptr(),
+            ws.numel(), stream_ptr(dev))
         check(rc, "kd_fused_linear_bwd_range")
         if grad_sync is not None and need_w:
             grad_sync.reduce_rows(dW, max(v0, int(dw_row_begin)), v1)

@@ -113,3 +113,16 @@ def test_grad_sync_reduces_every_row_block():
         assert p.exitcode == 0
     assert len(ranges) == 3
     np.testing.assert_array_equal(g, np.full((1000, 4), 3.0))
+
+
+def test_vocab_slices_properties():
+    from speech_distill_b200.vocab_parallel import vocab_slices
+
+    for V, world in [(152936, 8), (152936, 2), (5000, 3), (1031, 4), (100, 8)]:
+        sl = vocab_slices(V, world)
+        assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == V
+        assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+        assert all(v0 % 8 == 0 for v0, v1 in sl if v1 > v0)  # 16-byte aligned slice bases for bf16 rows
+        if V >= 8 * world:
+            assert all(v1 > v0 for v0, v1 in sl)
+    assert vocab_slices(152936, 8)[0] == (0, 19200)       # 75 tiles of 256 columns per rank at BASELINE V
