@@ -185,9 +185,9 @@ def run_ours(args):
     sync_mode = os.environ.get("KD_BENCH_SYNC", "overlap") if world > 1 else "none"
     sync = None
     if sync_mode == "overlap":
-        max_ctas = int(os.environ.get("KD_BENCH_NCCL_CTAS", "16"))
+        max_ctas = int(os.environ.get("KD_BENCH_NCCL_CTAS", "32"))
         sync = KD.GradSync(group=KD.GradSync.new_group(max_ctas), n_ranges=int(os.environ.get("KD_BENCH_RANGES", "6")),
-                           max_ctas=max_ctas if os.environ.get("KD_BENCH_SM_LIMIT", "1") == "1" else 0)
+                           max_ctas=max_ctas, reserve_sms=os.environ.get("KD_BENCH_SM_LIMIT", "0") == "1")
 
     def step(hh, yy, ll):
         out = K.fused_linear_kd_loss(hh, W, ll, teacher_logits=yy, temperature=TAU, alpha=ALPHA,

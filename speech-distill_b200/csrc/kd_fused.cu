@@ -45,6 +45,7 @@ constexpr int kSteps = BN / kStepCols;           // 2
 constexpr int kStepBoxes = kStepCols / 64;       // 64-column (128-byte row) TMA boxes per step
 constexpr uint32_t kBoxBytes = BM * 64 * 2;      // 16 KB: [128 rows x 64 cols] of a 16-bit type, swizzled 128 B rows
 constexpr uint32_t kStepBytes = kStepBoxes * kBoxBytes;  // 32 KB
+constexpr int kSchedSlots = 2;  // work-unit queue depth per CTA (pair): the next unit is fetched while one runs
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
 // per-row record one vocabulary slice hands to the cross-rank merge (vocab-parallel mode):
 // m, s1, st, mt | t1, tt, a, z_label | y_label, sum p log p, hit value sum, hits
@@ -62,8 +63,10 @@ struct SmemPlan {
   static constexpr uint32_t kYOff = kStages * kStageL;
   static constexpr uint32_t kGOff = kYOff + YSLOTS * kStepBytes;
   static constexpr uint32_t kBarOff = kGOff + GSLOTS * kStepBytes;
-  static constexpr uint32_t kNumBars = 2 * kStages + 4 + 2 * (YSLOTS > 0 ? YSLOTS : 1);
-  static constexpr uint32_t kBytes = kBarOff + 8 * kNumBars + 16 + 1024;
+  static constexpr uint32_t kReqBar = 2 * kStages + 4 + 2 * (YSLOTS > 0 ? YSLOTS : 1);  // "draw the next unit"
+  static constexpr uint32_t kSchedBar0 = kReqBar + 1;  // first of the queue's full / empty barriers
+  static constexpr uint32_t kNumBars = kSchedBar0 + 2 * kSchedSlots;
+  static constexpr uint32_t kBytes = kBarOff + 8 * kNumBars + 16 /*tmem slot*/ + 16 /*unit slots*/ + 1024;
   static_assert(kStages >= 2, "operand ring too shallow");  // 2 only for the single-CTA fallback of GradEpi
   static_assert(kBytes <= 232448, "shared memory plan exceeds 227 KB");
 };
@@ -73,6 +76,7 @@ struct Geom {
   int a_m0, a_k0, b_n0, b_k0;  // element offsets added to the TMA coordinates
   int n_per_unit;              // consecutive n blocks handled by one work unit (same m block)
   int num_units;
+  int dynamic;                 // 1: work units are handed out by an atomic counter (see UnitQueue), 0: static stride
 };
 
 __host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, int& range, int& n_begin, int& n_end) {
@@ -609,6 +613,41 @@ struct StoreEpi {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Work-unit queue.  Static mode: unit u0, u0 + step, ... as a persistent kernel usually does.  Dynamic mode: one
+// thread of the (leader) CTA draws unit numbers from a global atomic counter and publishes each to both CTAs of
+// the pair through a kSchedSlots-deep shared-memory queue (st.async + mbarrier complete_tx, the TMA publish
+// mechanism); every consumer role reads the same sequence and releases the slot on the leader's "empty" barrier.
+// The next number is drawn when the operand producer has issued the last load of the current unit: early enough
+// to hide the atomic's latency behind the operand ring, late enough that nobody hoards units.
+// A CTA (pair) that starts late or shares its SM budget with another kernel (the three backward chains, NCCL)
+// simply draws fewer units, so launches overlap without tail effects.  The pair that draws the last number resets
+// the counter, which makes the counter reusable by a later launch without a memset.
+// ---------------------------------------------------------------------------------------------
+struct UnitQueue {
+  static_assert(kSchedSlots == 2, "slot / phase are decoded from the low two bits of `it`");
+  uint32_t full0;   // first local "full" barrier; the unit slots sit 16 * kSchedSlots + 16 bytes behind it
+  uint32_t empty0;  // first "empty" barrier of the leader CTA (shared::cluster address for a pair)
+  int it;           // dynamic: number of entries consumed so far; static: the next unit
+
+  // returns the next unit or -1; called by exactly one thread per consumer agent
+  template <int CG>
+  __device__ __forceinline__ int next(const Geom& g) {
+    if (!g.dynamic) {
+      const int u = it;
+      it += CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+      return u < g.num_units ? u : -1;
+    }
+    const uint32_t slot = (uint32_t)it & 1u, phase = ((uint32_t)it >> 1) & 1u;
+    ++it;
+    mbar_wait(full0 + 8u * slot, phase);
+    const int u = lds_s32(full0 + 16u * kSchedSlots + 16u + 4u * slot);
+    if (CG == 2) mbar_arrive_cluster(empty0 + 8u * slot);
+    else mbar_arrive(empty0 + 8u * slot);
+    return u;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // The persistent warp-specialised GEMM.  CG = 1: one CTA per 128 x 256 tile.  CG = 2: a CTA pair
 // (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile - each CTA stages its own 128 rows of A and
 // HALF of the B tile, the leader CTA issues one MMA for both tensor cores, and each CTA's epilogue
@@ -624,7 +663,7 @@ template <class Epi, bool A_MN, bool B_MN, int CG>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(kThreads, 1)
 kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_g, const Geom g,
-               const typename Epi::Params ep) {
+               const typename Epi::Params ep, int* __restrict__ sched_counter) {
   using Plan = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots>;
   constexpr int kStages = Plan::kStages;
   constexpr int kYSlots = Epi::kYSlots;
@@ -645,15 +684,21 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tempty_bar = [&](int s) { return sBar + 8u * (2 * kStages + 2 + s); };
   const uint32_t yfull0 = sBar + 8u * (2 * kStages + 4);
   const uint32_t yempty0 = yfull0 + 8u * (kYSlots > 0 ? kYSlots : 1);
+  const uint32_t sched_req = sBar + 8u * Plan::kReqBar;
+  const uint32_t sched_full0 = sBar + 8u * Plan::kSchedBar0;
+  const uint32_t sched_empty0 = sched_full0 + 8u * kSchedSlots;
   const uint32_t tmem_slot = sBar + 8u * Plan::kNumBars;
+  const uint32_t sched_unit0 = tmem_slot + 16u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  UnitQueue uq;
+  uq.full0 = sched_full0;
+  uq.empty0 = CG == 2 ? mapa(sched_empty0, 0) : sched_empty0;
+  uq.it = g.dynamic ? 0 : (CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
@@ -671,6 +716,12 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int s = 0; s < kYSlots; ++s) {
       mbar_init(yfull0 + 8u * s, 1);
       mbar_init(yempty0 + 8u * s, kEpiWarps);
+    }
+    mbar_init(sched_req, 1);  // the leader's operand producer, once per unit
+    for (int s = 0; s < kSchedSlots; ++s) {
+      mbar_init(sched_full0 + 8u * s, 1);  // the scheduler's arrive.expect_tx; the unit number is the 4 tx bytes
+      // consumers of both CTAs: operand producer, epilogue warps, teacher-tile producer, + the MMA issuer
+      mbar_init(sched_empty0 + 8u * s, CG * (1 + kEpiWarps + (kYSlots > 0 ? 1 : 0)) + 1);
     }
     fence_mbar_init();
   }
@@ -694,7 +745,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = unit0; u < g.num_units; u += unit_step) {
+      for (int u = uq.template next<CG>(g); u >= 0; u = uq.template next<CG>(g)) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         const int m_row = g.a_m0 + (m_blk * CG + (int)cta_rank) * BM;
@@ -744,6 +795,9 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         }
+        // all loads of this unit are in flight: now (not earlier) the scheduler may draw the next unit, so a
+        // pair never holds a unit it will not start for a long time while other pairs go idle
+        if (g.dynamic && leader) mbar_arrive(sched_req);
       }
     }
   } else if (warp == 1) {
@@ -756,7 +810,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int u = unit0; u < g.num_units; u += unit_step) {
+      for (int u = uq.template next<CG>(g); u >= 0; u = uq.template next<CG>(g)) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
@@ -791,12 +845,40 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
+  } else if (warp == 2) {
+    // ================= work-unit scheduler (leader CTA; dynamic mode only) =================
+    if (g.dynamic && lane == 0 && leader) {
+      const int npairs = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+      int slot = 0;
+      uint32_t phase = 0, req_phase = 0;
+      for (bool first = true;; first = false) {
+        if (!first) {  // the producer has issued the current unit's last load
+          mbar_wait(sched_req, req_phase);
+          req_phase ^= 1u;
+        }
+        mbar_wait(sched_empty0 + 8u * slot, phase ^ 1u);  // every consumer of both CTAs has read the old entry
+        const int drawn = atomicAdd(sched_counter, 1);
+        const int u = drawn < g.num_units ? drawn : -1;
+        if (drawn == g.num_units + npairs - 1) atomicExch(sched_counter, 0);  // last draw of the launch: re-arm
+#pragma unroll
+        for (int r = 0; r < CG; ++r) {
+          const uint32_t fb = mapa(sched_full0 + 8u * slot, (uint32_t)r);
+          mbar_expect_tx_cluster(fb, 4);
+          st_async_b32(mapa(sched_unit0 + 4u * slot, (uint32_t)r), (uint32_t)u, fb);
+        }
+        if (u < 0) break;
+        if (++slot == kSchedSlots) {
+          slot = 0;
+          phase ^= 1u;
+        }
+      }
+    }
   } else if (warp == 3) {
     // ================= teacher-tile producer (y ring, local to each CTA) =================
     if (kYSlots > 0 && lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      for (int u = unit0; u < g.num_units; u += unit_step) {
+      for (int u = uq.template next<CG>(g); u >= 0; u = uq.template next<CG>(g)) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         const int m_row = (m_blk * CG + (int)cta_rank) * BM;
@@ -834,7 +916,11 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     Epi epi(ep, et);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = unit0; u < g.num_units; u += unit_step) {
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = uq.template next<CG>(g);  // one agent per warp; static mode is warp-uniform anyway
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u < 0) break;
       int m_blk, range, n_begin, n_end;
       decode_unit(g, u, m_blk, range, n_begin, n_end);
       epi.begin_unit(g, (m_blk * CG + (int)cta_rank) * BM, range);
@@ -1229,6 +1315,34 @@ static int cta_group() {
   return v;
 }
 
+// dynamic work-unit scheduling (default) needs one zero-initialised counter per in-flight launch: a per-device
+// pool handed out round-robin; each launch re-arms its counter when it draws its last number (see UnitQueue)
+static bool sched_dynamic() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_SCHED");
+    v = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;  // KD_SCHED=static keeps the fixed stride
+  }
+  return v != 0;
+}
+
+static int* next_sched_counter() {
+  constexpr int kMaxDev = 64, kPool = 1024;
+  static int* pools[kMaxDev] = {};
+  static unsigned seq[kMaxDev] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    int* p = nullptr;
+    if (cudaMalloc(&p, kPool * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, kPool * sizeof(int)) != cudaSuccess) return nullptr;
+    pools[dev] = p;
+  }
+  return pools[dev] + (seq[dev]++ % kPool);
+}
+
 template <class Epi, bool A_MN, bool B_MN, int CG>
 static int launch_umma_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
                           const Geom& g, const typename Epi::Params& ep, cudaStream_t stream) {
@@ -1249,7 +1363,18 @@ static int launch_umma_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   if (tl_sm_limit > 0 && tl_sm_limit < sms) sms = tl_sm_limit;
   const int slots = sms / CG >= 1 ? sms / CG : 1;  // persistent: one CTA (pair) per SM (pair)
   const int grid = (g.num_units < slots ? g.num_units : slots) * CG;
-  kern<<<grid, kThreads, smem, stream>>>(ta, tb, ty, tg, g, ep);
+  Geom gg = g;
+  int* counter = nullptr;
+  gg.dynamic = 0;
+  if (sched_dynamic()) {
+    counter = next_sched_counter();
+    if (!counter) {
+      set_error("kd_umma: could not allocate the work-unit counters");
+      return 1;
+    }
+    gg.dynamic = 1;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(ta, tb, ty, tg, gg, ep, counter);
   return check_cuda(cudaGetLastError(), "kd_umma launch");
 }
 template <class Epi, bool A_MN, bool B_MN>

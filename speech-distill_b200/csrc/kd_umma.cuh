@@ -192,6 +192,19 @@ __device__ __forceinline__ void mma_commit_cg2(uint32_t bar, uint16_t cta_mask) 
       : "memory");
 }
 
+// 4 bytes into the shared memory of a CTA of the cluster, completion counted on an mbarrier of that CTA
+// (the same publish mechanism as a TMA load: the waiter sees the data once the phase completes)
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t value, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "r"(value), "r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1.
 //   K-major  tile (rows x 64 bf16, 128 B per row):   SBO = 1024 (8 rows), LBO ignored (1)

@@ -91,20 +91,24 @@ class GradSync:
     ``reduce_rows(dW, r0, r1)`` is called by the backward after each vocabulary range: the rows are final, the
     all-reduce is enqueued asynchronously (NCCL's stream waits for the current stream at that point) and the
     next range's GEMMs run beside it.  ``finish()`` makes the current stream wait for every all-reduce.
-    ``max_ctas`` bounds the SMs NCCL may take (process-group config where torch exposes it); the GEMM kernels
-    of the overlapped ranges are launched on ``sm_count - max_ctas`` SMs (kd_fused_linear_bwd_range sm_limit).
+    ``max_ctas`` bounds the SMs NCCL may take (process-group config where torch exposes it).  The GEMM kernels
+    draw their work units from an atomic counter, so the CTAs that have to wait for an SM NCCL occupies simply
+    draw fewer units; ``reserve_sms=True`` instead launches the overlapped ranges on ``sm_count - max_ctas``
+    SMs (kd_fused_linear_bwd_range sm_limit; useful with KD_SCHED=static).  Measured on 2 B200 (tools/n2_sweep.sh):
+    32 CTAs without a reservation is the fastest setting.
     """
 
-    def __init__(self, group=None, n_ranges=6, max_ctas=16, sm_count=None):
+    def __init__(self, group=None, n_ranges=6, max_ctas=32, sm_count=None, reserve_sms=False):
         self.group = group
         self.n_ranges = int(n_ranges)
         self.max_ctas = int(max_ctas)
+        self.reserve_sms = bool(reserve_sms)
         self._sm_count = sm_count
         self._pending = []
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
     @staticmethod
-    def new_group(max_ctas=16, **kw):
+    def new_group(max_ctas=32, **kw):
         """A NCCL process group whose collectives use at most ``max_ctas`` CTAs (falls back to the default
         group configuration when this torch build does not expose the option)."""
         try:
@@ -121,7 +125,7 @@ class GradSync:
         return plan_ranges(V, row_begin, v_chunk, self.n_ranges)
 
     def sm_limit(self):
-        if not self.active or self.max_ctas <= 0:
+        if not self.active or self.max_ctas <= 0 or not self.reserve_sms:
             return 0
         if self._sm_count is None:
             self._sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count

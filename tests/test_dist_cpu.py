@@ -89,7 +89,7 @@ def _sync_worker(rank, world, port, out_q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import speech_distill_b200.dist as D
 
-    sync = D.GradSync(n_ranges=3, max_ctas=0)
+    sync = D.GradSync(n_ranges=3)
     V, H = 1000, 4
     g = torch.full((V, H), float(rank + 1))
     for v0, v1 in sync.ranges(V, 0, 256):

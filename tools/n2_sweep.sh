@@ -2,7 +2,7 @@
 # tuning sweep of the overlapped dW all-reduce at N GPUs (default 2): NCCL CTAs x ranges x SM limit
 N=${1:-2}
 port=29600
-for cfg in "serial 8 6 1" "overlap 8 6 1" "overlap 8 6 0" "overlap 16 6 1" "overlap 16 6 0" "overlap 8 12 1" "overlap 16 12 1" "overlap 32 8 0" "overlap 32 8 1"; do
+for cfg in "serial 16 6 0" "overlap 16 6 0" "overlap 16 6 1" "overlap 8 6 0" "overlap 32 6 0" "overlap 16 3 0" "overlap 16 9 0"; do
   set -- $cfg
   port=$((port+1))
   KD_BENCH_QUICK=1 KD_BENCH_SYNC=$1 KD_BENCH_NCCL_CTAS=$2 KD_BENCH_RANGES=$3 KD_BENCH_SM_LIMIT=$4 \
