@@ -259,34 +259,39 @@ def run_ours(args):
     bwd_t = statistics.median(e[1].elapsed_time(e[2]) for e in evs)
 
     # ---- end to end through the public API with HOST buffers ----
+    # every step's inputs start in pinned host memory; HostPrefetcher (speech_distill_b200.io) copies step i + 1
+    # on its own stream while step i computes; the loss 4-tuple is read back to the host every step
+    from speech_distill_b200.io import HostPrefetcher
+
     h_host = h.detach().cpu().pin_memory()
     y_host = torch.empty((B, T, V), dtype=torch.bfloat16).pin_memory()
     y_host.copy_(y)
     l_host = labels.cpu().pin_memory()
-    h_dev = torch.empty_like(h_host, device=dev)
-    y_dev = torch.empty_like(y)
-    l_dev = torch.empty_like(labels)
+    host_batch = (h_host, y_host, l_host)
     out_host = torch.empty(4, dtype=torch.float32).pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 8))
+    pf = HostPrefetcher(dev)
 
-    def e2e_step():
+    def e2e_step(following):
         W.grad = None
-        h_dev.copy_(h_host, non_blocking=True)
-        y_dev.copy_(y_host, non_blocking=True)
-        l_dev.copy_(l_host, non_blocking=True)
+        h_dev, y_dev, l_dev = pf.next(following)
         hh = h_dev.detach().requires_grad_(True)  # fresh leaf over the staging buffer
         o = step(hh, y_dev, l_dev)
+        pf.release()
         out_host.copy_(torch.stack([x.detach().float() for x in o]), non_blocking=True)
 
-    e2e_step()
+    pf.submit(host_batch)
+    e2e_step(host_batch)      # warm-up (allocates both staging sets); leaves one batch in flight
+    e2e_step(host_batch)
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for i in range(e2e_steps):
+        e2e_step(host_batch)  # K steps computed, K batches copied inside the timed region
     f1.record()
     sync_all()
     e2e_ms = f0.elapsed_time(f1) / e2e_steps
+    e2e_losses = out_host.tolist()
 
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e_ms, fwd_t, bwd_t], device=dev, dtype=torch.float64)
@@ -312,8 +317,10 @@ def run_ours(args):
             "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h_host.numel() * 2 + y_host.numel() * 2 + l_host.numel() * 8,
                     "d2h_bytes_per_step": 16,
-                    "note": "pinned host h, teacher logits and labels copied to the device every step (PCIe bound: "
-                            "1.25 GB of teacher logits); loss 4-tuple read back"},
+                    "note": "pinned host h, teacher logits and labels copied to the device every step by a "
+                            "double-buffered prefetcher (copy of step i+1 overlaps compute of step i; PCIe bound: "
+                            "1.25 GB of teacher logits per step); loss 4-tuple read back every step",
+                    "losses": e2e_losses},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {
                 "kernel": "kd_umma_kernel<FwdEpi> (fused lm_head GEMM + online softmax statistics, forward)",
