@@ -183,6 +183,15 @@ int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_targe
                          float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- teacher LM head in front of the top-k compaction ---------------------------------------
+ * out[R,V] bf16 (row stride out_stride, a multiple of 8 elements, 16-byte aligned base; the padding columns
+ * V .. roundup(V, 8) - 1 of a row may be zero-filled: TMA stores whole 16-byte granules) = h[R,H] * W[V,H]^T,
+ * fp32 accumulation, one rounding to bf16 - what transformers' bf16 lm_head produces for teacher_outputs.logits
+ * (train.py:60-72, extract_teacher_logits.py:109-113).  The host mirror runs it over blocks of rows into a
+ * fixed-size scratch and feeds kd_topk_logprobs, so the teacher's [B,T,V] logits never exist as a whole. */
+int kd_linear_bf16(const void* h, int64_t h_stride, const void* W, int64_t w_stride, void* out,
+                   int64_t out_stride, int R, int H, int V, void* stream);
+
 /* Plain bf16 GEMM on the same tcgen05 pipeline (test hook for the K1 building block), fp32 out:
  *   C[M,N] (ldc) = op(A) * op(B)^T with
  *   a_mn_major = 0: A is [M][K] (K contiguous, lda)   | 1: A is [K][M] (M contiguous, lda)

@@ -46,6 +46,7 @@ SIGNATURES = {
                                            _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "kd_fused_merge_workspace_bytes": (_sz, []),
     "kd_fused_merge_ranks": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_linear_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
 }
 

@@ -150,6 +150,12 @@ struct Vec8<__half> {
   }
 };
 
+// Two packed bf16 values with -inf (0xFF80) replaced by the most negative finite bf16 below -1e30: for negative
+// floats the bit pattern grows with the magnitude, positives have a clear sign bit and stay below the bound,
+// so one unsigned 16x2 minimum does it (p = e^{(y - max)/tau} is still exactly 0 for such an entry, and
+// 0 * (y - z) is then 0 instead of NaN - the xlogy convention of nn.KLDivLoss, distillation_loss.py:68).
+__device__ __forceinline__ uint32_t clamp_neg_inf_bf16x2(uint32_t w) { return __vminu2(w, 0xF14AF14Au); }
+
 // ---- warp helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -215,7 +221,8 @@ __device__ __forceinline__ void student_update(const float (&f)[N], int nvalid, 
 }
 
 // GUARD = true keeps p == 0 terms at exactly 0 even when the student logit is -inf (user-supplied logits,
-// K2); the fused path produces finite student logits and skips the select.
+// K2).  GUARD = false (fused path: finite student logits, teacher values already clamped to >= -1e30 by the
+// caller, see clamp_neg_inf_bf16x2) runs the cross term as one subtract and one FMA per element.
 template <bool TAU2, int N, bool GUARD = true>
 __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float (&fz)[N], int nvalid, float inv_tau,
                                                float& mt, float& t1, float& tt, float& a) {
@@ -241,19 +248,20 @@ __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float
       ExpPair<TAU2>::eval(fy[i], c_tau, off_tau, off_one, et, e1);
       pt[i & 1] += et;
       p1[i & 1] += e1;
-      // p = 0 contributes exactly 0 (xlogy semantics of nn.KLDivLoss, distillation_loss.py:68);
-      // the clamp keeps 0 * (-inf - z) from producing NaN when the teacher holds -inf
-      const float d = fmaxf(fy[i], -1e30f) - fz[i];
       if (GUARD) {
+        // p = 0 contributes exactly 0 (xlogy semantics of nn.KLDivLoss, distillation_loss.py:68);
+        // the clamp keeps 0 * (-inf - z) from producing NaN when the teacher holds -inf
+        const float d = fmaxf(fy[i], -1e30f) - fz[i];
         pa[i & 1] = (et > 0.f) ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
       } else {
-        pa[i & 1] = fmaf(et, d, pa[i & 1]);
+        pa[i & 1] = fmaf(et, fy[i] - fz[i], pa[i & 1]);
       }
     }
   }
+  const float pa_sum = pa[0] + pa[1];
   tt += pt[0] + pt[1];
   t1 += p1[0] + p1[1];
-  a += pa[0] + pa[1];
+  a += pa_sum;
 }
 
 __device__ __forceinline__ void merge_student(float& m, float& s1, float& st, float m2, float s12, float st2,

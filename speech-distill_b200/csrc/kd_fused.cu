@@ -137,11 +137,11 @@ __device__ __forceinline__ void load_row16(const TY* __restrict__ p, bool vec_ok
       float t8[8];
       v.unpack(t8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[8 * q + j] = t8[j];
+      for (int j = 0; j < 8; ++j) f[8 * q + j] = fmaxf(t8[j], -1e30f);  // -inf teacher entries: see teacher_update
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = j < ncols ? Elem<TY>::to_f(p[j]) : -CUDART_INF_F;
+    for (int j = 0; j < 16; ++j) f[j] = j < ncols ? fmaxf(Elem<TY>::to_f(p[j]), -1e30f) : -CUDART_INF_F;
   }
 }
 
@@ -171,6 +171,12 @@ __device__ __forceinline__ void unpack_sub(const uint4 (&pk)[4], int sub, int nc
   for (int q = 0; q < 2; ++q) {
     Vec8<TY> v;
     v.a = sub == 0 ? pk[q] : pk[2 + q];
+    if (std::is_same<TY, __nv_bfloat16>::value) {  // -inf -> most negative finite value, two elements per op
+      v.a.x = clamp_neg_inf_bf16x2(v.a.x);
+      v.a.y = clamp_neg_inf_bf16x2(v.a.y);
+      v.a.z = clamp_neg_inf_bf16x2(v.a.z);
+      v.a.w = clamp_neg_inf_bf16x2(v.a.w);
+    }
     float f8[8];
     v.unpack(f8);
 #pragma unroll
@@ -352,9 +358,12 @@ struct GradParams {
   SparseView sp;      // sparse teacher, see FwdParams
 };
 
-template <typename TY, bool DENSE, bool TAU2, bool Y_TMA, bool SPARSE = false>
+// COPY = true turns the policy into "logits tile -> bf16 -> scratch" (no soft-max arithmetic): the teacher LM head
+// of kd_linear_bf16, which shares the swizzled smem staging + TMA store path of the gradient tile.
+template <typename TY, bool DENSE, bool TAU2, bool Y_TMA, bool SPARSE = false, bool COPY = false>
 struct GradEpi {
   static_assert(!(DENSE && SPARSE), "one teacher kind per instantiation");
+  static_assert(!COPY || (!DENSE && !SPARSE), "the copy policy has no teacher");
   using Params = GradParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
   static constexpr int kYSlots = kUseYRing ? 2 : 0;
@@ -367,6 +376,7 @@ struct GradEpi {
   YRing ring;
 
   __device__ GradEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {
+    if (COPY) return;
     const int nn = *p.n_norm;
     const float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
     c1 = p.coef[0] * inv_n;
@@ -377,6 +387,11 @@ struct GradEpi {
   __device__ void begin_unit(const Geom&, int m0_, int) {
     m0 = m0_;
     row = m0 + t.row_in_tile;
+    if (COPY) {
+      valid = row < p.R;
+      target = kLabelElsewhere;
+      return;
+    }
     target = local_target(row < p.R ? p.row_target[row] : -1, p.label_off, p.V, valid);
     if (valid) {
       const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
@@ -396,7 +411,9 @@ struct GradEpi {
     for (int j = 0; j < 16; ++j) {
       const float z = __uint_as_float(raw[j]);
       float gi;
-      if (TAU2) {
+      if (COPY) {
+        gi = z;
+      } else if (TAU2) {
         const float e = ex2(fmaf(z, c_tau, -half_off1));
         gi = e * fmaf(e, c1, k_tau);
       } else {
@@ -925,7 +942,10 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       decode_unit(g, u, m_blk, range, n_begin, n_end);
       epi.begin_unit(g, (m_blk * CG + (int)cta_rank) * BM, range);
       for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        // one warp polls the accumulator-full barrier; the other 15 wait in a hardware named barrier instead of
+        // each spinning on try_wait (the polls were 17 % of all issued instructions of the forward kernel)
+        if (warp == 4) mbar_wait(tfull_bar(acc), acc_phase);
+        named_bar_sync(3, kEpiThreads);
         fence_after_sync();
         // the policy releases the TMEM buffer itself (arrive on the leader's tempty barrier)
         const uint32_t rel = CG == 2 ? mapa(tempty_bar(acc), 0) : tempty_bar(acc);
@@ -1958,6 +1978,34 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     if (any_h && check_cuda(cudaStreamWaitEvent(s, pipe->eh[last_h], 0), "join dH")) return 1;
   }
   return 0;
+}
+
+// out[R, V] (bf16, row stride out_stride) = h[R, H] * W[V, H]^T : the LM head alone, on the K1 pipeline
+// (CTA pairs, fp32 accumulation in TMEM, tile -> swizzled smem -> TMA store).  Used for the teacher head in front
+// of the top-k compaction (train.py:60-94, extract_teacher_logits.py:109-129), block of rows by block of rows.
+extern "C" int kd_linear_bf16(const void* h, int64_t h_stride, const void* W, int64_t w_stride, void* out,
+                              int64_t out_stride, int R, int H, int V, void* stream) {
+  if (check_common(h, h_stride, W, w_stride, R, H, V, 1.0f, "kd_linear_bf16")) return 1;
+  if (!out) {
+    set_error("kd_linear_bf16: null output");
+    return 1;
+  }
+  CUtensorMap ta, tb, tg;
+  if (make_tmap(&ta, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
+  if (make_tmap(&tb, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, b_box_rows(), "lm_head weight")) return 1;
+  if (make_tmap(&tg, out, (uint64_t)V, (uint64_t)R, (uint64_t)out_stride, BM, "logits out")) return 1;
+  Geom g = {};
+  g.num_m_blk = cdiv(R, tile_m());
+  g.num_n_blk = cdiv(V, BN);
+  g.num_k_blk = cdiv(H, BK);
+  g.n_per_unit = 1;
+  g.num_units = g.num_m_blk * g.num_n_blk;
+  GradParams gp = {};
+  gp.R = R;
+  gp.V = V;
+  gp.tau = 1.0f;
+  return launch_umma<GradEpi<__nv_bfloat16, false, false, false, false, true>, false, false>(ta, tb, ta, tg, g, gp,
+                                                                                             (cudaStream_t)stream);
 }
 
 extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,

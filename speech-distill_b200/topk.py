@@ -46,3 +46,91 @@ def extract_batch(teacher_logits, attention_mask, k):
     lengths = attention_mask.sum(dim=1).tolist()
     v_cpu, i_cpu = v.cpu().numpy(), i.cpu().numpy()
     return ([v_cpu[b, : int(n)] for b, n in enumerate(lengths)], [i_cpu[b, : int(n)] for b, n in enumerate(lengths)])
+
+
+def linear_bf16(hidden, weight, out=None):
+    """``hidden @ weight.T`` in bf16 with fp32 accumulation on the K1 tensor pipeline (kd_linear_bf16).
+    hidden [R,H], weight [V,H] bf16; ``out`` [R, >=V] bf16 with a row stride that is a multiple of 8."""
+    require_cuda(hidden, weight)
+    lib = _lib.load()
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError("linear_bf16 needs bf16 operands")
+    R, H = hidden.shape
+    V = weight.shape[0]
+    if out is None:
+        ld = -(-V // 8) * 8
+        out = torch.empty((R, ld), dtype=torch.bfloat16, device=hidden.device)[:, :V]
+    check(lib.kd_linear_bf16(hidden.data_ptr(), hidden.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(),
+                             out.stride(0), R, H, V, stream_ptr(hidden.device)), "kd_linear_bf16")
+    return out
+
+
+def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024):
+    """Teacher LM head -> log_softmax -> top-k without the teacher's [B,T,V] logits
+    (train.py:60-94 on-the-fly mode, extract_teacher_logits.py:109-129).
+
+    hidden [..., H_t] bf16 (the teacher body's last hidden states), lm_head_weight [V_t, H_t] bf16;
+    ``vocab_size`` truncates the teacher vocabulary to the student's (train.py:82-83) by dropping weight rows,
+    which is the same as slicing the logits.  Rows are processed ``row_block`` at a time: the head GEMM of
+    block b + 1 (tensor-core bound) runs on the current stream while the compaction of block b (HBM bound) runs
+    on a side stream, through two fixed scratch buffers of row_block x V bf16.
+    Returns (values fp16 [..., k], indices int32 [..., k]) exactly as ``teacher_topk_logprobs`` would on the
+    bf16 logits of the same GEMM.
+    """
+    require_cuda(hidden, lm_head_weight)
+    lead = hidden.shape[:-1]
+    H = hidden.shape[-1]
+    h2 = hidden.detach().reshape(-1, H)
+    if h2.stride(-1) != 1:
+        h2 = h2.contiguous()
+    W = lm_head_weight.detach()
+    if vocab_size is not None and vocab_size < W.size(0):
+        W = W[:vocab_size]
+    if W.stride(-1) != 1:
+        W = W.contiguous()
+    V = W.size(0)
+    if not (1 <= k <= min(V, MAX_K)):
+        raise ValueError(f"k={k} must be in [1, min(V={V}, {MAX_K})]")
+    R = h2.size(0)
+    dev = h2.device
+    out_v = torch.empty((R, k), dtype=torch.float16, device=dev)
+    out_i = torch.empty((R, k), dtype=torch.int32, device=dev)
+    if R == 0:
+        return out_v.reshape(*lead, k), out_i.reshape(*lead, k)
+    rb = max(1, min(int(row_block), R))
+    ld = -(-V // 8) * 8
+    scratch = [torch.empty((rb, ld), dtype=torch.bfloat16, device=dev) for _ in range(2 if R > rb else 1)]
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    filled = [torch.cuda.Event() for _ in scratch]
+    drained = [None for _ in scratch]
+    lib = _lib.load()
+    for n, r0 in enumerate(range(0, R, rb)):
+        r1 = min(r0 + rb, R)
+        s = n % len(scratch)
+        if drained[s] is not None:
+            main.wait_event(drained[s])  # the compaction that read this scratch two blocks ago is done
+        logits = linear_bf16(h2[r0:r1], W, scratch[s][: r1 - r0, :V])
+        filled[s].record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(filled[s])
+            check(lib.kd_topk_logprobs(logits.data_ptr(), dtype_code(logits.dtype), r1 - r0, V, logits.stride(0),
+                                       int(k), out_v[r0:r1].data_ptr(), out_i[r0:r1].data_ptr(), stream_ptr(dev)),
+                  "kd_topk_logprobs")
+            ev = torch.cuda.Event()
+            ev.record(side)
+            drained[s] = ev
+    for ev in drained:
+        if ev is not None:
+            main.wait_event(ev)
+    return out_v.reshape(*lead, k), out_i.reshape(*lead, k)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]

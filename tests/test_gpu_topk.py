@@ -101,3 +101,48 @@ def test_topk_feeds_sparse_loss_like_train_py():
     v, i = K.teacher_topk_logprobs(y.cuda(), 64)
     out = K.kd_loss_on_logits(z.cuda(), lab.cuda(), teacher_top_k_v=v, teacher_top_k_i=i)
     np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-3)
+
+
+# ---- teacher LM head -> top-k without the teacher's [B,T,V] logits -------------------------
+@pytest.mark.parametrize("R,H,V", [(300, 256, 1031), (128, 512, 5000), (1000, 2048, 20000)])
+def test_linear_bf16_is_the_bf16_lm_head(R, H, V):
+    """kd_linear_bf16 = fp32-accumulated h W^T rounded once to bf16 (what HF's bf16 nn.Linear returns up to the
+    summation order): within one bf16 ulp of the fp64 product, ragged R / V handled by TMA clipping."""
+    import speech_distill_b200 as K
+
+    g = torch.Generator(device="cuda").manual_seed(R + V)
+    h = torch.randn(R, H, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V, H, device="cuda", generator=g) * (2.0 / H ** 0.5)).bfloat16()
+    guard = torch.full((R, -(-V // 8) * 8), 777.0, dtype=torch.bfloat16, device="cuda")
+    out = K.linear_bf16(h, W, guard[:, :V])
+    ref = h.double() @ W.double().t()
+    err = (out.double() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-4).all())  # half a bf16 ulp + fp32 accumulation noise near 0
+    pad = guard[:, V:]  # padding up to the 16-byte row granule: untouched or zero-filled (TMA stores whole granules)
+    assert bool(((pad == 777.0) | (pad == 0.0)).all())
+    exact = (out == ref.to(torch.bfloat16)).float().mean()
+    assert float(exact) > 0.98  # the rest are round-to-nearest ties decided by fp32 vs fp64 accumulation
+
+
+@pytest.mark.parametrize("B,T,H,V,k,rb", [(2, 100, 256, 5000, 64, 64), (3, 128, 512, 20000, 100, 1024), (1, 50, 128, 700, 16, 32)])
+def test_teacher_head_topk_equals_topk_of_its_logits(B, T, H, V, k, rb):
+    """Row-block pipeline (head GEMM on the current stream, compaction on a side stream, two scratch buffers)
+    = kd_topk_logprobs on the materialised bf16 logits of the same GEMM, bit for bit; and the deterministic
+    tie-rule spec of the oracle on those logits."""
+    import speech_distill_b200 as K
+
+    g = torch.Generator(device="cuda").manual_seed(B * T + V)
+    h = torch.randn(B, T, H, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V + 40, H, device="cuda", generator=g) * (3.0 / H ** 0.5)).bfloat16()  # teacher vocab > student's
+    v, i = K.teacher_head_topk(h, W, k, vocab_size=V, row_block=rb)
+    assert v.shape == (B, T, k) and v.dtype == torch.float16 and i.dtype == torch.int32
+    logits = K.linear_bf16(h.reshape(-1, H), W[:V])
+    v2, i2 = K.teacher_topk_logprobs(logits.reshape(B, T, V), k)
+    assert torch.equal(i, i2) and torch.equal(v, v2)
+    v_spec, i_spec = O.topk_spec(logits.cpu().reshape(B, T, V), k)
+    np.testing.assert_array_equal(i.cpu().numpy(), i_spec.numpy())
+    # against the reference pipeline on torch's own bf16 lm_head: same indices wherever its logits agree with ours
+    ref_logits = torch.nn.functional.linear(h, W[:V])
+    if torch.equal(ref_logits, logits.reshape(B, T, V)):
+        assert torch.equal(torch.topk(ref_logits.float(), k, -1).values,
+                           torch.gather(ref_logits.float(), -1, i.long()))
