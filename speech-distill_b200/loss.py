@@ -387,6 +387,16 @@ class DistillationLoss(nn.Module):
 
     def forward(self, student_logits, labels, teacher_logits=None, teacher_top_k_v=None, teacher_top_k_i=None,
                 speech_token_mask=None, student_hidden=None, lm_head_weight=None):
+        from .lazy import LazyLogits  # outputs.logits of a model patched by enable_lazy_logits
+
+        if isinstance(teacher_logits, LazyLogits):
+            # dense teacher from a patched teacher model: its logits are needed as a tensor (kd_linear_bf16)
+            teacher_logits = teacher_logits.materialize()
+        if isinstance(student_logits, LazyLogits):
+            if student_logits.log_probs:
+                raise ValueError("student_logits must be logits, not log-probabilities")
+            student_hidden, lm_head_weight = student_logits.hidden, student_logits.head_weight()
+            student_logits = None
         if student_logits is None:
             if student_hidden is None or lm_head_weight is None:
                 raise ValueError("pass student_logits, or student_hidden together with lm_head_weight")

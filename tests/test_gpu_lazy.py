@@ -1,0 +1,102 @@
+"""train.py's compute_loss, restated line by line, on models patched by enable_lazy_logits: neither the student's
+nor the teacher's [B,T,V] logits exist, results equal the stock models + the reference loss."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import kd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_qwen3(vocab, hidden, seed):
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+
+    torch.manual_seed(seed)
+    cfg = Qwen3Config(vocab_size=vocab, hidden_size=hidden, intermediate_size=2 * hidden, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, head_dim=hidden // 4, max_position_embeddings=128,
+                      tie_word_embeddings=False)
+    model = Qwen3ForCausalLM(cfg)
+    with torch.no_grad():  # logits with a spread of ~2 (a random-init head gives near-uniform, tie-ridden rows)
+        model.lm_head.weight.mul_(2.0 / (0.02 * hidden ** 0.5))
+    return model.to(device="cuda", dtype=torch.bfloat16)
+
+
+def _compute_loss(student, teacher, loss_fn, inputs, top_k):
+    """reference train.py:43-116 (DistillationTrainer.compute_loss) without the Trainer bookkeeping"""
+    inputs = dict(inputs)
+    speech_mask = inputs.pop("speech_token_mask", None)
+    teacher_top_k_v = inputs.pop("teacher_top_k_v", None)
+    teacher_top_k_i = inputs.pop("teacher_top_k_i", None)
+    outputs = student(**inputs)                                     # :54
+    student_logits = outputs.logits                                  # :55
+    labels = inputs.pop("labels", None)                              # :56
+    teacher_logits = None
+    if teacher_top_k_v is None and teacher is not None:              # :60
+        with torch.no_grad():
+            teacher_logits = teacher(**inputs).logits                # :69-70
+    if teacher_logits is not None and teacher_top_k_v is None and top_k > 0:   # :75-80
+        with torch.no_grad():
+            vocab_size = student_logits.size(-1)                     # :83
+            teacher_logits_truncated = teacher_logits[..., :vocab_size]
+            teacher_logprobs = F.log_softmax(teacher_logits_truncated, dim=-1)
+            teacher_top_k_v, teacher_top_k_i = torch.topk(teacher_logprobs, k=top_k, dim=-1)
+            teacher_top_k_v = teacher_top_k_v.to(torch.float16)      # :90
+            teacher_top_k_i = teacher_top_k_i.to(torch.int32)        # :91
+        teacher_logits = None
+    return loss_fn(student_logits=student_logits, labels=labels, teacher_logits=teacher_logits,
+                   teacher_top_k_v=teacher_top_k_v, teacher_top_k_i=teacher_top_k_i, speech_token_mask=speech_mask)
+
+
+@pytest.mark.parametrize("top_k", [16, 0])
+def test_compute_loss_flow_on_lazy_models(top_k):
+    import speech_distill_b200 as K
+
+    V, Vt, B, T = 1000, 1040, 2, 48
+    student, teacher = _tiny_qwen3(V, 64, 1), _tiny_qwen3(Vt if top_k > 0 else V, 128, 2)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, V, (B, T), generator=g).cuda()
+    labels = ids.clone()
+    labels[:, :10] = -100
+    mask = torch.ones(B, T)
+    mask[1, 30:] = 0
+    inputs = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": labels,
+              "speech_token_mask": mask.cuda()}
+    loss_fn = K.DistillationLoss(temperature=2.0, alpha=0.5)
+
+    # stock models (logits materialised, K2) first, then the patched ones (K1 + head top-k)
+    out_stock = _compute_loss(student, teacher, loss_fn, inputs, top_k)
+    out_stock[0].backward()
+    g_head = student.lm_head.weight.grad.clone()
+    g_emb = student.model.embed_tokens.weight.grad.clone()
+    student.zero_grad(set_to_none=True)
+
+    K.enable_lazy_logits(student)
+    K.enable_lazy_logits(teacher)
+    probe = student(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels)
+    assert isinstance(probe.logits, K.LazyLogits) and probe.loss is None and probe.logits.shape == (B, T, V)
+    out_lazy = _compute_loss(student, teacher, loss_fn, inputs, top_k)
+    out_lazy[0].backward()
+
+    a = [float(x) for x in out_lazy]
+    b = [float(x) for x in out_stock]
+    np.testing.assert_allclose(a, b, rtol=2e-2, atol=1e-3)  # bf16 scalars (reference dtypes); bf16 vs fp32 logits
+    gh = student.lm_head.weight.grad.float()
+    assert float((gh - g_head.float()).abs().max() / g_head.float().abs().max()) < 3e-2
+    ge = student.model.embed_tokens.weight.grad.float()
+    assert float((ge - g_emb.float()).abs().max() / g_emb.float().abs().max()) < 5e-2  # dH flows into the body
+
+    # and against the oracle on the stock student's logits (fp32 reference loss)
+    student.forward = student._kd_original_forward
+    teacher.forward = teacher._kd_original_forward
+    with torch.no_grad():
+        z = student(input_ids=ids).logits.float().cpu()
+        y = teacher(input_ids=ids).logits[..., :V].float().cpu()
+    if top_k > 0:
+        tv, ti = O.topk_logprobs_reference(y.bfloat16().cuda(), top_k)  # bf16 log-softmax as the reference runs it
+        ref = O.reference_loss(z, labels.cpu(), teacher_top_k_v=tv.cpu(), teacher_top_k_i=ti.cpu(),
+                               speech_token_mask=mask)
+    else:
+        ref = O.reference_loss(z, labels.cpu(), teacher_logits=y, speech_token_mask=mask)
+    np.testing.assert_allclose(a[:3], [float(x) for x in ref][:3], rtol=3e-2, atol=2e-3)
