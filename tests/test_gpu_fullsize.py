@@ -1,0 +1,117 @@
+"""K1 / K2 / K3 at BASELINE.json's full sizes.  The oracle (reference loss restated in torch) is run on the GPU in
+fp32 as the checker - it needs seconds there - plus size-independent properties: linearity in the upstream
+gradient (bit-exact for a power of two), row independence of dH, sums over vocabulary slices."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kd_oracle as O
+
+pytestmark = pytest.mark.gpu
+V_FULL, H_STUDENT = 152936, 1024
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def _inputs(B, T, seed, masked=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    h = torch.randn(B, T, H_STUDENT, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V_FULL, H_STUDENT, device="cuda", generator=g) * (2.0 / H_STUDENT ** 0.5)).bfloat16()
+    y = torch.empty(B, T, V_FULL, device="cuda", dtype=torch.bfloat16)
+    for b in range(B):
+        y[b] = (torch.randn(T, V_FULL, device="cuda", generator=g) * 2).bfloat16()
+    labels = torch.randint(0, V_FULL, (B, T), device="cuda", generator=g)
+    if masked:  # text prefix + padded tail, the collator's pattern (data.py:246-251)
+        labels[:, : T // 4] = -100
+        labels[0, -T // 10:] = -100
+    return h, W, y, labels
+
+
+def test_k1_dense_configs1_full_size_vs_oracle():
+    """BASELINE configs[1]: B=8, T=512, H=1024, V=152,936, dense bf16 teacher, tau=2, alpha=0.5."""
+    import speech_distill_b200 as K
+
+    h, W, y, labels = _inputs(8, 512, 2024)
+    ref, gh_ref, gw_ref = O.fused_linear_reference(h.float(), W.float(), labels, teacher_logits=y.float(),
+                                                   temperature=2.0, alpha=0.5)
+    hc, Wc = h.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    out = K.fused_linear_kd_loss(hc, Wc, labels, teacher_logits=y, temperature=2.0, alpha=0.5)
+    out[0].backward()
+    for got, want in zip(out, ref):
+        assert abs(float(got) - float(want)) <= 1e-3 * max(1.0, abs(float(want)))  # north_star tolerance
+        assert abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))  # what fp32 statistics deliver
+    _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h, W, labels, teacher_logits=y, temperature=2.0, alpha=0.5)
+    assert rel_err(gh32, gh_ref) < 4e-3 and rel_err(gw32, gw_ref) < 4e-3    # bf16 G operand
+    assert rel_err(hc.grad.float(), gh_ref) < 6e-3 and rel_err(Wc.grad.float(), gw_ref) < 6e-3
+    cos = torch.nn.functional.cosine_similarity(Wc.grad.float().flatten(), gw_ref.flatten(), dim=0)
+    assert float(cos) > 0.99999
+
+    # linearity in the upstream gradient: d(4 * total) = 4 * d(total), bit for bit (power of two)
+    h4, W4 = h.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    out4 = K.fused_linear_kd_loss(h4, W4, labels, teacher_logits=y, temperature=2.0, alpha=0.5)
+    (out4[0] * 4.0).backward()
+    assert torch.equal(h4.grad, hc.grad * 4) and torch.equal(W4.grad, Wc.grad * 4)
+
+    # row independence: dH of the first 3 sequences computed alone (other tile schedule, other N) = same rows
+    # up to the 1/N factor; compare after rescaling by the valid-row counts.  The gradient tile is rounded to
+    # bf16 after the 1/N scaling, so the two runs round different numbers: equality holds to the bf16-G level
+    n_all = int((labels[:, 1:] != -100).sum())
+    n_sub = int((labels[:3, 1:] != -100).sum())
+    _, gh_sub, _ = K.fused_linear_kd_value_and_grad(h[:3].contiguous(), W, labels[:3].contiguous(),
+                                                    teacher_logits=y[:3].contiguous(), temperature=2.0, alpha=0.5)
+    assert rel_err(gh_sub * (n_sub / n_all), gh32[:3]) < 6e-3
+
+
+def test_k1_sparse_configs2_full_size_vs_oracle():
+    """BASELINE configs[2] (loss part): B=16, T=512, top-k=64 cache from a teacher, sparse KD, V=152,936."""
+    import speech_distill_b200 as K
+
+    h, W, y, labels = _inputs(16, 512, 77)
+    tv, ti = K.teacher_topk_logprobs(y, 64)
+    del y
+    ref, gh_ref, gw_ref = O.fused_linear_reference(h.float(), W.float(), labels, teacher_top_k_v=tv,
+                                                   teacher_top_k_i=ti, temperature=2.0, alpha=0.5)
+    losses, gh32, gw32 = K.fused_linear_kd_value_and_grad(h, W, labels, temperature=2.0, alpha=0.5,
+                                                          teacher_top_k_v=tv, teacher_top_k_i=ti)
+    for got, want in zip(losses, ref):
+        assert abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))
+    assert rel_err(gh32, gh_ref) < 4e-3 and rel_err(gw32, gw_ref) < 4e-3
+
+
+def test_stage1_configs3_full_size_masked_rows():
+    """BASELINE configs[3]: CE with the frozen-vocabulary mask, B=8, T=2048, 1,000 new rows: rows < V_old of dW are
+    exactly zero and never computed; the live rows and dH match the oracle."""
+    import speech_distill_b200 as K
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, T, old = 8, 2048, V_FULL - 1000
+    h = torch.randn(B, T, H_STUDENT, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V_FULL, H_STUDENT, device="cuda", generator=g) * (2.0 / H_STUDENT ** 0.5)).bfloat16()
+    labels = torch.randint(old - 500, V_FULL, (B, T), device="cuda", generator=g)  # mostly speech tokens
+    loss_ref, gh_ref, gw_ref = O.stage1_ce_reference(h.float(), W.float(), labels, old)
+    hc, Wc = h.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    loss = K.fused_linear_cross_entropy(hc, Wc, labels, old_vocab_size=old)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-5 * float(loss_ref)
+    assert float(Wc.grad[:old].abs().max()) == 0.0
+    assert rel_err(Wc.grad[old:].float(), gw_ref[old:]) < 6e-3
+    assert rel_err(hc.grad.float(), gh_ref) < 6e-3
+
+
+def test_teacher_head_topk_configs2_full_size():
+    """BASELINE configs[2] (teacher part): SoulX-1.7B head, hidden 2048, B=16, T=512 -> top-64; the row-block
+    pipeline equals the compaction of the materialised logits of the same GEMM, bit for bit."""
+    import speech_distill_b200 as K
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Ht, R = 2048, 16 * 512
+    h = torch.randn(R, Ht, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V_FULL, Ht, device="cuda", generator=g) * (2.5 / Ht ** 0.5)).bfloat16()
+    v, i = K.teacher_head_topk(h, W, 64)
+    logits = K.linear_bf16(h, W)
+    v2, i2 = K.teacher_topk_logprobs(logits, 64)
+    assert torch.equal(i, i2) and torch.equal(v, v2)
+    sel = torch.gather(logits.float(), -1, i.long())
+    assert torch.equal(sel, torch.topk(logits.float(), 64, -1).values)  # a valid top-k of those logits
