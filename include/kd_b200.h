@@ -109,6 +109,21 @@ int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t ro
  * stage1.py:53-57 / 67-71: grad[:old_vocab] = 0, in place on a [V,H] gradient. */
 int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stream);
 
+/* ---- valid-row compaction (optional front end of K1) ----------------------------------------
+ * distillation_loss.py:37-45 drops the rows whose label is ignored (text prefix, padding: data.py:246-251)
+ * with a boolean gather; kd_compact_rows does it on the device without a host sync:
+ *   perm[j]     original row of the j-th valid row (j < N, order preserved), -1 behind
+ *   inv[r]      rank of row r among the valid rows, -1 if the row is not scored
+ *   target_c[j] row_target[perm[j]], -1 behind            n_valid (optional) = N
+ * kd_gather_rows: dst[j,:] = src[map[j],:] (rows of row_bytes bytes; strides in bytes) for map[j] >= 0, zeros
+ * (zero_fill != 0) or untouched otherwise - hidden / teacher rows in with map = perm, dH back with map = inv.
+ * The fused entry points below take n_rows = device pointer to N (or NULL): with compacted operands every GEMM
+ * tile behind row N is skipped and the dW contraction stops at the last live row block. */
+int kd_compact_rows(const int32_t* row_target, int R, int32_t* perm, int32_t* inv, int32_t* target_c,
+                    int32_t* n_valid, void* stream);
+int kd_gather_rows(const void* src, int64_t src_stride_bytes, const int32_t* map, int R, void* dst,
+                   int64_t dst_stride_bytes, int64_t row_bytes, int zero_fill, void* stream);
+
 /* ---- K1: fused LM head + KD (logits never materialised) ------------------------------------
  * Replaces lm_head (transformers Qwen3ForCausalLM.lm_head, called at train.py:54) followed by
  * DistillationLoss.forward, and their backward.  h [R,H] bf16 (R = B*T rows, row stride
@@ -138,14 +153,14 @@ size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int K);
 int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                         const float* topk_v, const int32_t* topk_i, int K,
-                        const int32_t* row_target, int R, int H, int V, float tau, float alpha,
-                        float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
+                        const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, float tau,
+                        float alpha, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
                         void* stream);
 int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                         const float* topk_v, const int32_t* topk_i, int K,
-                        const int32_t* row_target, const float* row_stats, int R, int H, int V,
-                        float tau, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
+                        const int32_t* row_target, const int32_t* n_rows, const float* row_stats, int R, int H,
+                        int V, float tau, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
                         void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
                         int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -160,7 +175,8 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
 int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                               int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                               const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target,
-                              const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
+                              const int32_t* n_rows, const float* row_stats, int R, int H, int V, float tau,
+                              const int32_t* n_norm,
                               const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                               int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
                               int range_flags, int sm_limit, int v_offset, void* workspace,
@@ -176,8 +192,8 @@ int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, in
 int kd_fused_linear_fwd_partial(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                                 int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                                 const float* topk_v, const int32_t* topk_i, int K,
-                                const int32_t* row_target, int R, int H, int V, int v_offset, float tau,
-                                float* rank_rec, void* workspace, size_t workspace_bytes, void* stream);
+                                const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, int v_offset,
+                                float tau, float* rank_rec, void* workspace, size_t workspace_bytes, void* stream);
 size_t kd_fused_merge_workspace_bytes(void);
 int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_target, int R, int teacher_kind,
                          float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,

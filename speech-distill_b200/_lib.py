@@ -34,16 +34,18 @@ SIGNATURES = {
     "kd_topk_logprobs": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "kd_mask_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
     "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
-    "kd_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _i32,
+    "kd_compact_rows": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "kd_gather_rows": (_i32, [_vp, _i64, _vp, _i32, _vp, _i64, _i64, _i32, _vp]),
+    "kd_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32,
                                    _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
-    "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32,
+    "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
                                    _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz,
                                    _vp]),
-    "kd_fused_linear_bwd_range": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32,
-                                         _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _i32,
-                                         _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
-    "kd_fused_linear_fwd_partial": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32,
-                                           _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
+    "kd_fused_linear_bwd_range": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp,
+                                         _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32,
+                                         _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "kd_fused_linear_fwd_partial": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp,
+                                           _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "kd_fused_merge_workspace_bytes": (_sz, []),
     "kd_fused_merge_ranks": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "kd_linear_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),

@@ -77,6 +77,11 @@ struct Geom {
   int n_per_unit;              // consecutive n blocks handled by one work unit (same m block)
   int num_units;
   int dynamic;                 // 1: work units are handed out by an atomic counter (see UnitQueue), 0: static stride
+  // valid-row compaction (kd_rows.cu): *n_rows = number of live rows (device memory, no host sync).
+  // rows_dim = 1: the M dimension is rows -> units whose first row is >= *n_rows are skipped;
+  // rows_dim = 2: the K dimension is rows (dW = G^T h) -> only the first ceil(*n_rows / 64) k-blocks are run.
+  const int32_t* n_rows;
+  int rows_dim;
 };
 
 __host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, int& range, int& n_begin, int& n_end) {
@@ -640,6 +645,14 @@ struct StoreEpi {
 // simply draws fewer units, so launches overlap without tail effects.  The pair that draws the last number resets
 // the counter, which makes the counter reusable by a later launch without a memset.
 // ---------------------------------------------------------------------------------------------
+// a unit is dead when row compaction left no live row in its M tile (rows_dim 1) or no live k-block (rows_dim 2)
+template <int CG>
+__device__ __forceinline__ bool unit_live(const Geom& g, int u, int n_rows_live) {
+  if (g.rows_dim == 1) return (u % g.num_m_blk) * (CG * BM) < n_rows_live;
+  if (g.rows_dim == 2) return n_rows_live > 0;
+  return true;
+}
+
 struct UnitQueue {
   static_assert(kSchedSlots == 2, "slot / phase are decoded from the low two bits of `it`");
   uint32_t full0;   // first local "full" barrier; the unit slots sit 16 * kSchedSlots + 16 bytes behind it
@@ -648,11 +661,14 @@ struct UnitQueue {
 
   // returns the next unit or -1; called by exactly one thread per consumer agent
   template <int CG>
-  __device__ __forceinline__ int next(const Geom& g) {
+  __device__ __forceinline__ int next(const Geom& g, int n_rows_live) {
     if (!g.dynamic) {
-      const int u = it;
-      it += CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-      return u < g.num_units ? u : -1;
+      for (;;) {  // static stride; dead units (row compaction) are stepped over by every consumer alike
+        const int u = it;
+        it += CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+        if (u >= g.num_units) return -1;
+        if (unit_live<CG>(g, u, n_rows_live)) return u;
+      }
     }
     const uint32_t slot = (uint32_t)it & 1u, phase = ((uint32_t)it >> 1) & 1u;
     ++it;
@@ -712,6 +728,10 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
+  const int n_rows_live = g.n_rows != nullptr ? *g.n_rows : 0x7fffffff;
+  // k-blocks actually run: all of them, or (dW with compacted rows) those that hold live rows
+  const int num_k_live = g.rows_dim == 2 && (n_rows_live + BK - 1) / BK < g.num_k_blk ? (n_rows_live + BK - 1) / BK
+                                                                                        : g.num_k_blk;
   UnitQueue uq;
   uq.full0 = sched_full0;
   uq.empty0 = CG == 2 ? mapa(sched_empty0, 0) : sched_empty0;
@@ -762,13 +782,13 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = uq.template next<CG>(g); u >= 0; u = uq.template next<CG>(g)) {
+      for (int u = uq.template next<CG>(g, n_rows_live); u >= 0; u = uq.template next<CG>(g, n_rows_live)) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         const int m_row = g.a_m0 + (m_blk * CG + (int)cta_rank) * BM;
         for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
           const int n_row = g.b_n0 + n_blk * BN + (int)cta_rank * BNL;
-          for (int kb = 0; kb < g.num_k_blk; ++kb) {
+          for (int kb = 0; kb < num_k_live; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = sA + stage * kABytes, b_dst = sB + stage * kBBytesL;
             if (CG == 1) {
@@ -827,14 +847,14 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int u = uq.template next<CG>(g); u >= 0; u = uq.template next<CG>(g)) {
+      for (int u = uq.template next<CG>(g, n_rows_live); u >= 0; u = uq.template next<CG>(g, n_rows_live)) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-          for (int kb = 0; kb < g.num_k_blk; ++kb) {
+          for (int kb = 0; kb < num_k_live; ++kb) {
             mbar_wait(full_bar(stage), phase);
             fence_after_sync();
             const uint32_t a_src = sA + stage * kABytes, b_src = sB + stage * kBBytesL;
@@ -874,9 +894,12 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           req_phase ^= 1u;
         }
         mbar_wait(sched_empty0 + 8u * slot, phase ^ 1u);  // every consumer of both CTAs has read the old entry
-        const int drawn = atomicAdd(sched_counter, 1);
-        const int u = drawn < g.num_units ? drawn : -1;
-        if (drawn == g.num_units + npairs - 1) atomicExch(sched_counter, 0);  // last draw of the launch: re-arm
+        int u;
+        do {  // dead units (row compaction) are drawn and dropped right here
+          const int drawn = atomicAdd(sched_counter, 1);
+          u = drawn < g.num_units ? drawn : -1;
+          if (drawn == g.num_units + npairs - 1) atomicExch(sched_counter, 0);  // last draw of the launch: re-arm
+        } while (u >= 0 && !unit_live<CG>(g, u, n_rows_live));
 #pragma unroll
         for (int r = 0; r < CG; ++r) {
           const uint32_t fb = mapa(sched_full0 + 8u * slot, (uint32_t)r);
@@ -895,7 +918,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (kYSlots > 0 && lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      for (int u = uq.template next<CG>(g); u >= 0; u = uq.template next<CG>(g)) {
+      for (int u = uq.template next<CG>(g, n_rows_live); u >= 0; u = uq.template next<CG>(g, n_rows_live)) {
         int m_blk, range, n_begin, n_end;
         decode_unit(g, u, m_blk, range, n_begin, n_end);
         const int m_row = (m_blk * CG + (int)cta_rank) * BM;
@@ -935,7 +958,7 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t acc_phase = 0;
     for (;;) {
       int u = 0;
-      if (lane == 0) u = uq.template next<CG>(g);  // one agent per warp; static mode is warp-uniform anyway
+      if (lane == 0) u = uq.template next<CG>(g, n_rows_live);  // one agent per warp; static mode is warp-uniform anyway
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u < 0) break;
       int m_blk, range, n_begin, n_end;
@@ -1615,34 +1638,36 @@ extern "C" size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int
 
 static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                           const void* y, int y_dtype, int64_t y_stride, const float* topk_v, const int32_t* topk_i,
-                          int K, const int32_t* row_target, int R, int H, int V, int v_offset, float tau, float* sums,
-                          float* row_stats, float* rank_rec, void* workspace, size_t workspace_bytes, void* stream);
+                          int K, const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, int v_offset,
+                          float tau, float* sums, float* row_stats, float* rank_rec, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                                    const void* y, int y_dtype, int64_t y_stride, const float* topk_v,
-                                   const int32_t* topk_i, int K, const int32_t* row_target, int R, int H, int V,
-                                   float tau, float alpha, float* sums, float* row_stats, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   const int32_t* topk_i, int K, const int32_t* row_target, const int32_t* n_rows,
+                                   int R, int H, int V, float tau, float alpha, float* sums, float* row_stats,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   (void)alpha;
   if (!sums || !row_stats) {
     set_error("kd_fused_linear_fwd: null pointer argument");
     return 1;
   }
-  return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target, R,
-                        H, V, 0, tau, sums, row_stats, nullptr, workspace, workspace_bytes, stream);
+  return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target,
+                        n_rows, R, H, V, 0, tau, sums, row_stats, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int kd_fused_linear_fwd_partial(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                                            int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                                            const float* topk_v, const int32_t* topk_i, int K,
-                                           const int32_t* row_target, int R, int H, int V, int v_offset, float tau,
-                                           float* rank_rec, void* workspace, size_t workspace_bytes, void* stream) {
+                                           const int32_t* row_target, const int32_t* n_rows, int R, int H, int V,
+                                           int v_offset, float tau, float* rank_rec, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
   if (!rank_rec || v_offset < 0) {
     set_error("kd_fused_linear_fwd_partial: null record buffer or negative vocabulary offset");
     return 1;
   }
-  return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target, R,
-                        H, V, v_offset, tau, nullptr, nullptr, rank_rec, workspace, workspace_bytes, stream);
+  return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target,
+                        n_rows, R, H, V, v_offset, tau, nullptr, nullptr, rank_rec, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t kd_fused_merge_workspace_bytes(void) {
@@ -1681,8 +1706,9 @@ extern "C" int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t
 
 static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                           const void* y, int y_dtype, int64_t y_stride, const float* topk_v, const int32_t* topk_i,
-                          int K, const int32_t* row_target, int R, int H, int V, int v_offset, float tau, float* sums,
-                          float* row_stats, float* rank_rec, void* workspace, size_t workspace_bytes, void* stream) {
+                          int K, const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, int v_offset,
+                          float tau, float* sums, float* row_stats, float* rank_rec, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_fwd")) return 1;
   if (!row_target || !workspace) {
     set_error("kd_fused_linear_fwd: null pointer argument");
@@ -1713,6 +1739,8 @@ static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_
   g.n_per_unit = kFwdTilesPerRange;
   const int num_ranges = cdiv(g.num_n_blk, g.n_per_unit);
   g.num_units = g.num_m_blk * num_ranges;
+  g.n_rows = n_rows;
+  g.rows_dim = n_rows ? 1 : 0;
 
   FwdParams fp = {};
   fp.row_target = row_target;
@@ -1775,13 +1803,13 @@ static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_
 
 extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                                    const void* y, int y_dtype, int64_t y_stride, const float* topk_v,
-                                   const int32_t* topk_i, int K, const int32_t* row_target, const float* row_stats,
-                                   int R, int H, int V, float tau, const int32_t* n_norm,
+                                   const int32_t* topk_i, int K, const int32_t* row_target, const int32_t* n_rows,
+                                   const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
                                    const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                                    int64_t dw_stride, int64_t dw_row_begin, int v_chunk, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   return kd_fused_linear_bwd_range(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K,
-                                   row_target, row_stats, R, H, V, tau, n_norm, grad_coef, grad_dtype, dH, dh_stride,
+                                   row_target, n_rows, row_stats, R, H, V, tau, n_norm, grad_coef, grad_dtype, dH, dh_stride,
                                    dW, dw_stride, dw_row_begin, v_chunk, 0, V, KD_RANGE_FIRST | KD_RANGE_LAST, 0, 0,
                                    workspace, workspace_bytes, stream);
 }
@@ -1794,7 +1822,8 @@ struct SmLimitScope {
 extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                                          int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                                          const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target,
-                                         const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
+                                         const int32_t* n_rows, const float* row_stats, int R, int H, int V, float tau,
+                                         const int32_t* n_norm,
                                          const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                                          int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
                                          int range_flags, int sm_limit, int v_offset, void* workspace,
@@ -1880,6 +1909,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       g.b_n0 = v0;
       g.n_per_unit = 1;
       g.num_units = g.num_m_blk * g.num_n_blk;
+      g.n_rows = n_rows;
+      g.rows_dim = n_rows ? 1 : 0;
       GradParams gp = {};
       gp.row_target = row_target;
       gp.row_stats = row_stats;
@@ -1920,6 +1951,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       g.num_k_blk = cdiv(R, BK);
       g.n_per_unit = 1;
       g.num_units = g.num_m_blk * g.num_n_blk;
+      g.n_rows = n_rows;
+      g.rows_dim = n_rows ? 2 : 0;  // K runs over rows: stop at the last live k-block
       StoreParams sp = {};
       sp.mode = out32 ? kStoreF32 : kStoreBf16;
       sp.m_total = cols;
@@ -1949,6 +1982,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       g.b_k0 = v0;
       g.n_per_unit = 1;
       g.num_units = g.num_m_blk * g.num_n_blk;
+      g.n_rows = n_rows;
+      g.rows_dim = n_rows ? 1 : 0;
       StoreParams sp = {};
       const bool first = range_first && c == 0, last = range_last && c == n_chunks - 1;
       sp.m_total = R;

@@ -188,8 +188,38 @@ def _teacher_kind(y, topk):
     return _lib.KD_TEACHER_SPARSE if topk is not None else _lib.KD_TEACHER_NONE
 
 
-def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None):
-    """topk = (v fp32 [R,K], i int32 [R,K]) for the sparse teacher, else None."""
+def compact_rows(row_target):
+    """kd_compact_rows: (perm, inv, target_c, n_valid) - valid rows first, order preserved, no host sync."""
+    lib = _lib.load()
+    R = row_target.numel()
+    dev = row_target.device
+    perm = torch.empty(R, dtype=torch.int32, device=dev)
+    inv = torch.empty(R, dtype=torch.int32, device=dev)
+    target_c = torch.empty(R, dtype=torch.int32, device=dev)
+    n_valid = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.kd_compact_rows(row_target.data_ptr(), R, perm.data_ptr(), inv.data_ptr(), target_c.data_ptr(),
+                              n_valid.data_ptr(), stream_ptr(dev)), "kd_compact_rows")
+    return perm, inv, target_c, n_valid
+
+
+_compact = compact_rows  # the public functions below have a keyword argument of the same name
+
+
+def gather_rows(src, row_map, zero_fill=True):
+    """kd_gather_rows on a 2-D tensor with unit inner stride: out[j] = src[row_map[j]] (zeros where row_map < 0)."""
+    lib = _lib.load()
+    R = row_map.numel()
+    out = torch.empty((R, src.size(1)), dtype=src.dtype, device=src.device)
+    es = src.element_size()
+    check(lib.kd_gather_rows(src.data_ptr(), src.stride(0) * es, row_map.data_ptr(), R, out.data_ptr(),
+                             out.stride(0) * es, src.size(1) * es, int(bool(zero_fill)), stream_ptr(src.device)),
+          "kd_gather_rows")
+    return out
+
+
+def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None, n_rows=None):
+    """topk = (v fp32 [R,K], i int32 [R,K]) for the sparse teacher, else None; n_rows = device count of live
+    (compacted) rows or None."""
     lib = _lib.load()
     R, H = h.shape
     V = W.shape[0]
@@ -202,8 +232,8 @@ def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None):
     rc = lib.kd_fused_linear_fwd(
         h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
         _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), R, H, V, float(tau),
-        float(alpha), sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), _ptr(n_rows), R, H, V,
+        float(tau), float(alpha), sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
     check(rc, "kd_fused_linear_fwd")
     return sums, row_stats, ws
 
@@ -211,17 +241,25 @@ def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None):
 class _KDFusedLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype,
-                topk_v=None, topk_i=None, grad_sync=None):
+                topk_v=None, topk_i=None, grad_sync=None, compact=False):
+        inv = n_rows = None
+        if compact:  # valid rows to the front; every GEMM tile behind them is skipped (kd_rows.cu)
+            perm, inv, row_target, n_rows = compact_rows(row_target)
+            h = gather_rows(h, perm)
+            if y is not None:
+                y = gather_rows(y, perm, zero_fill=False)
+            if topk_v is not None:
+                topk_v, topk_i = gather_rows(topk_v, perm), gather_rows(topk_i, perm)
         topk = (topk_v, topk_i) if topk_v is not None else None
         teacher_kind = _teacher_kind(y, topk)
-        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk)
+        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk, n_rows)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
         eff_alpha = alpha if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
         losses = finalize_losses(sums, tau, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
         ctx.set_materialize_grads(False)
         ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk), grad_dtype)
-        ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm, topk_v, topk_i)
+        ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm, topk_v, topk_i, inv, n_rows)
         ctx.ws = ws
         ctx.grad_sync = grad_sync
         total, task, distill, teacher = losses.unbind(0)
@@ -230,7 +268,7 @@ class _KDFusedLinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, g_task, g_distill, g_teacher):
-        h, W, y, row_target, row_stats, n_norm, topk_v, topk_i = ctx.saved_tensors
+        h, W, y, row_target, row_stats, n_norm, topk_v, topk_i, inv, n_rows = ctx.saved_tensors
         topk = (topk_v, topk_i) if topk_v is not None else None
         tau, alpha, teacher_kind, dw_row_begin, v_chunk, grad_dtype = ctx.cfg
         dev = h.device
@@ -241,12 +279,15 @@ class _KDFusedLinear(torch.autograd.Function):
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
         dH, dW = _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin,
                                  v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk,
-                                 ctx.grad_sync)
-        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None, None
+                                 ctx.grad_sync, n_rows=n_rows)
+        if inv is not None and dH is not None:
+            dH = gather_rows(dH, inv)  # back to the original row order; rows that are not scored get zeros
+        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin, v_chunk,
-                    grad_dtype, need_h, need_w, ws=None, topk=None, grad_sync=None, v_offset=0, dh_fp32=False):
+                    grad_dtype, need_h, need_w, ws=None, topk=None, grad_sync=None, v_offset=0, dh_fp32=False,
+                    n_rows=None):
     """kd_fused_linear_bwd, or - with ``grad_sync`` (dist.GradSync) - kd_fused_linear_bwd_range over a few
     vocabulary ranges, handing each finished dW row block to the all-reduce while the next range runs."""
     lib = _lib.load()
@@ -258,8 +299,10 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
     dW = None
     gcode = dtype_code(grad_dtype) | (_lib.KD_GRAD_DH_F32 if dh_fp32 else 0)
     if need_w:
-        # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
-        dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
+        # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero; with compacted
+        # rows and no live row at all the dW GEMM has nothing to contract and is skipped: zeros as well
+        dW = (torch.zeros if (dw_row_begin > 0 or n_rows is not None) else torch.empty)((V, H), dtype=grad_dtype,
+                                                                                         device=dev)
     if ws is None:
         ws = _fused_workspace(R, H, V, v_chunk, dev, K)
     ranges = [(0, V)]
@@ -272,8 +315,8 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
         rc = lib.kd_fused_linear_bwd_range(
             h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
             _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
-            _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), row_stats.data_ptr(),
-            R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), gcode, _ptr(dH), H, _ptr(dW), H,
+            _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), _ptr(n_rows),
+            row_stats.data_ptr(), R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), gcode, _ptr(dH), H, _ptr(dW), H,
             int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), int(v_offset), ws.data_ptr(),
             ws.numel(), stream_ptr(dev))
         check(rc, "kd_fused_linear_bwd_range")
@@ -286,7 +329,8 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
 
 def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                                    temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
-                                   grad_dtype=torch.float32, teacher_top_k_v=None, teacher_top_k_i=None):
+                                   grad_dtype=torch.float32, teacher_top_k_v=None, teacher_top_k_i=None,
+                                   compact_rows=None):
     """Forward + backward in one call, outside autograd: returns (losses[4] fp32, dHidden, dWeight) with the
     gradients of ``total`` in ``grad_dtype``.  fp32 exposes the kernels' accumulators before the final
     rounding to bf16 that autograd imposes on bf16 leaves (used by the parity tests and by callers that keep
@@ -294,19 +338,21 @@ def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logit
     with torch.no_grad():
         out = fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits, speech_token_mask, temperature,
                                    alpha, ignore_index, dw_row_begin, v_chunk, teacher_top_k_v=teacher_top_k_v,
-                                   teacher_top_k_i=teacher_top_k_i, _return_ctx=True)
+                                   teacher_top_k_i=teacher_top_k_i, compact_rows=compact_rows, _return_ctx=True)
     losses, saved = out
-    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk = saved
+    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk, inv, n_rows = saved
     coef = torch.tensor([eff_alpha, 1.0 - eff_alpha], dtype=torch.float32, device=h2.device)
     dH, dW = _fused_backward(h2, W, y, row_target, row_stats, n_norm, coef, float(temperature), teacher_kind,
-                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True, None, topk)
+                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True, None, topk, n_rows=n_rows)
+    if inv is not None:
+        dH = gather_rows(dH, inv)
     return losses, dH.view(hidden.shape), dW
 
 
 def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                          temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
                          reduce_fn=None, count_reduce_fn=None, grad_dtype=torch.bfloat16, teacher_top_k_v=None,
-                         teacher_top_k_i=None, grad_sync=None, _return_ctx=False):
+                         teacher_top_k_i=None, grad_sync=None, compact_rows=None, _return_ctx=False):
     """``DistillationLoss(student_logits = hidden @ lm_head_weight.T, ...)`` without the logits.
 
     hidden [B,T,H] (or [R,H] with labels [.., T]) bf16, lm_head_weight [V,H] bf16, labels [B,T].
@@ -317,6 +363,10 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     the old vocabulary size; rows below stay exactly zero and are never computed).
     ``grad_dtype``: torch.bfloat16 (what autograd requires for bf16 leaves) or torch.float32 - the
     unrounded fp32 accumulators, usable only with non-leaf / fp32-grad consumers (verification).
+    ``compact_rows``: move the scored rows to the front on the device and skip every GEMM tile behind them
+    (the reference's boolean row gather, distillation_loss.py:37-45, without its host sync).  Default (None):
+    on for the top-k cache and for plain CE, where only [R,H] / [R,K] rows move; off for a dense teacher, whose
+    [R,V] rows would have to be copied (worth it from roughly 15 % ignored rows on: pass True).
     ``reduce_fn`` / ``count_reduce_fn`` / ``grad_sync``: token-shard data-parallel hooks (dist.py): all-reduce of
     the sums record and of the valid-row count, and the dW all-reduce overlapped with the backward
     (the weight gradient autograd receives is then already summed over ranks).
@@ -355,15 +405,27 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
         topk_i = teacher_top_k_i.detach().to(device=dev, dtype=torch.int32).reshape(B * T, K).contiguous()
     topk = (topk_v, topk_i) if topk_v is not None else None
     teacher_kind = _teacher_kind(y, topk)
+    compact = bool(compact_rows) if compact_rows is not None else teacher_kind != _lib.KD_TEACHER_DENSE
     if _return_ctx:  # fused_linear_kd_value_and_grad: forward pieces without an autograd node
-        sums, row_stats, _ = _fused_forward(h2, W, y, row_target, float(temperature), float(alpha), v_chunk, topk)
+        inv = n_rows = None
+        hd = h2.detach()
+        if compact:
+            perm, inv, row_target, n_rows = _compact(row_target)
+            hd = gather_rows(hd, perm)
+            if y is not None:
+                y = gather_rows(y, perm, zero_fill=False)
+            if topk is not None:
+                topk = (gather_rows(topk[0], perm), gather_rows(topk[1], perm))
+        sums, row_stats, _ = _fused_forward(hd, W.detach(), y, row_target, float(temperature), float(alpha), v_chunk,
+                                            topk, n_rows)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
         eff_alpha = float(alpha) if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
         losses = finalize_losses(sums, temperature, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
-        return losses, (h2.detach(), W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk)
+        return losses, (hd, W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk, inv, n_rows)
     out = _KDFusedLinear.apply(h2, W, y, row_target, n_valid, n_norm, float(temperature), float(alpha),
-                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype, topk_v, topk_i, grad_sync)
+                               int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype, topk_v, topk_i, grad_sync,
+                               compact)
     return out
 
 

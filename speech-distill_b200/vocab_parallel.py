@@ -55,7 +55,7 @@ def forward_partial(h2, W_slice, y_slice, topk, row_target, v_offset, tau, v_chu
         h2.data_ptr(), h2.stride(0), W_slice.data_ptr(), W_slice.stride(0), teacher_kind,
         _ptr(y_slice), dtype_code(y_slice.dtype) if y_slice is not None else 0,
         y_slice.stride(0) if y_slice is not None else 0,
-        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), R, H, V, int(v_offset),
+        _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), 0, R, H, V, int(v_offset),
         float(tau), rec.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
     check(rc, "kd_fused_linear_fwd_partial")
     return rec, ws

@@ -327,3 +327,70 @@ def test_fused_backward_ranges_bit_identical(old_vocab):
     blocks = stub.blocks[:-1]
     assert blocks[0][0] == old_vocab and blocks[-1][1] == V
     assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+
+# ---- valid-row compaction ---------------------------------------------------------------
+def test_compact_rows_and_gather_kernels():
+    from speech_distill_b200 import loss as KL
+
+    g = torch.Generator().manual_seed(3)
+    rt = torch.randint(0, 50, (3000,), generator=g).int()
+    rt[torch.rand(3000, generator=g) < 0.4] = -1
+    perm, inv, tc, n = KL.compact_rows(rt.cuda())
+    valid = (rt >= 0).nonzero().flatten()
+    N = int(n)
+    assert N == valid.numel()
+    assert torch.equal(perm[:N].cpu().long(), valid) and bool((perm[N:] == -1).all())
+    assert torch.equal(tc[:N].cpu(), rt[valid]) and bool((tc[N:] == -1).all())
+    want_inv = torch.full((3000,), -1, dtype=torch.int32)
+    want_inv[valid] = torch.arange(N, dtype=torch.int32)
+    assert torch.equal(inv.cpu(), want_inv)
+    for width, dtype in ((64, torch.bfloat16), (33, torch.float32), (7, torch.int32)):   # 16-byte and byte-wise paths
+        src = (torch.randn(3000, width, generator=g) * 100).to(dtype).cuda()
+        out = KL.gather_rows(src, perm)
+        assert torch.equal(out[:N], src[valid.cuda()]) and bool((out[N:] == 0).all())
+        back = KL.gather_rows(out, inv)
+        assert torch.equal(back[valid.cuda()], src[valid.cuda()]) and bool((back[(rt < 0).cuda()] == 0).all())
+
+
+@pytest.mark.parametrize("teacher", ["dense", "sparse", "none"])
+def test_fused_with_compacted_rows_equals_uncompacted(teacher):
+    """Compaction only reorders rows: same losses (fp32 summation order aside), dH rows bit-identical after the
+    scatter back, dW equal up to the order of the fp32 row sum.  70 % of the rows are not scored."""
+    import speech_distill_b200 as KD
+
+    B, T, H, V = 4, 160, 256, 5000
+    h, W, y, labels = _case(411, B, T, H, V, mask=False)
+    g = torch.Generator().manual_seed(1)
+    labels[torch.rand(B, T, generator=g) < 0.7] = -100
+    kw = {}
+    if teacher == "dense":
+        kw = dict(teacher_logits=y.cuda())
+    elif teacher == "sparse":
+        tv, ti = _topk_cache(y, 32)
+        kw = dict(teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
+    res = {}
+    for compact in (False, True):
+        hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+        out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), v_chunk=1024, compact_rows=compact, **kw)
+        out[0].backward()
+        res[compact] = ([float(o) for o in out], hc.grad, Wc.grad)
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=2e-6, atol=1e-7)
+    assert torch.equal(res[True][1], res[False][1])
+    assert rel_err(res[True][2].float().cpu().numpy(), res[False][2].float().cpu().numpy()) < 4e-3  # bf16 outputs
+    # rows that are not scored get exactly zero gradient (a10)
+    dead = (labels[:, 1:] == -100)
+    assert float(res[True][1][:, :-1][dead.cuda()].abs().max()) == 0.0
+
+
+def test_fused_compacted_no_valid_row():
+    """N == 0 (distillation_loss.py:47-53): four zeros, zero gradients, nothing divides by zero."""
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(9, 2, 64, 64, 700)
+    labels[:] = -100
+    hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), teacher_logits=y.cuda(), compact_rows=True)
+    out[0].backward()
+    assert [float(o) for o in out] == [0.0, 0.0, 0.0, 0.0]
+    assert float(hc.grad.abs().max()) == 0.0 and float(Wc.grad.abs().max()) == 0.0
