@@ -123,6 +123,9 @@ int kd_compact_rows(const int32_t* row_target, int R, int32_t* perm, int32_t* in
                     int32_t* n_valid, void* stream);
 int kd_gather_rows(const void* src, int64_t src_stride_bytes, const int32_t* map, int R, void* dst,
                    int64_t dst_stride_bytes, int64_t row_bytes, int zero_fill, void* stream);
+/* Zero-fills dst (16-byte aligned, bytes % 16 == 0) iff *n_rows == 0, else returns at once: with no live row the
+ * dW contraction is skipped and dW would stay unwritten (N == 0 must give zero gradients, :47-53). */
+int kd_zero_if_empty(void* dst, int64_t bytes, const int32_t* n_rows, void* stream);
 
 /* ---- K1: fused LM head + KD (logits never materialised) ------------------------------------
  * Replaces lm_head (transformers Qwen3ForCausalLM.lm_head, called at train.py:54) followed by

@@ -36,6 +36,7 @@ SIGNATURES = {
     "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "kd_compact_rows": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "kd_gather_rows": (_i32, [_vp, _i64, _vp, _i32, _vp, _i64, _i64, _i32, _vp]),
+    "kd_zero_if_empty": (_i32, [_vp, _i64, _vp, _vp]),
     "kd_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32,
                                    _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32,

@@ -81,9 +81,28 @@ __global__ void __launch_bounds__(256) kd_gather_rows_kernel(const uint8_t* __re
   }
 }
 
+// zero `n16` 16-byte pieces at `dst` iff *n_rows == 0: with no live row the dW GEMM has nothing to contract and is
+// skipped, but the caller still expects a zero gradient (distillation_loss.py:47-53); otherwise exit at once
+__global__ void __launch_bounds__(256) kd_zero_if_empty_kernel(uint4* __restrict__ dst, int64_t n16,
+                                                              const int32_t* __restrict__ n_rows) {
+  if (*n_rows > 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = make_uint4(0, 0, 0, 0);
+}
+
 }  // namespace kd
 
 using namespace kd;
+
+extern "C" int kd_zero_if_empty(void* dst, int64_t bytes, const int32_t* n_rows, void* stream) {
+  if (!dst || !n_rows || bytes < 0 || (bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) {
+    set_error("kd_zero_if_empty: bad arguments (16-byte aligned buffer and size required)");
+    return 1;
+  }
+  if (bytes == 0) return 0;
+  kd_zero_if_empty_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), bytes >> 4, n_rows);
+  return check_cuda(cudaGetLastError(), "kd_zero_if_empty launch");
+}
 
 extern "C" int kd_compact_rows(const int32_t* row_target, int R, int32_t* perm, int32_t* inv, int32_t* target_c,
                                int32_t* n_valid, void* stream) {

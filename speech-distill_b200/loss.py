@@ -299,10 +299,12 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
     dW = None
     gcode = dtype_code(grad_dtype) | (_lib.KD_GRAD_DH_F32 if dh_fp32 else 0)
     if need_w:
-        # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero; with compacted
-        # rows and no live row at all the dW GEMM has nothing to contract and is skipped: zeros as well
-        dW = (torch.zeros if (dw_row_begin > 0 or n_rows is not None) else torch.empty)((V, H), dtype=grad_dtype,
-                                                                                         device=dev)
+        # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
+        dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
+        if n_rows is not None and dw_row_begin <= 0:
+            # compacted rows and not a single live one: the dW GEMM is skipped, the gradient is zero (:47-53)
+            check(lib.kd_zero_if_empty(dW.data_ptr(), dW.numel() * dW.element_size(), n_rows.data_ptr(),
+                                       stream_ptr(dev)), "kd_zero_if_empty")
     if ws is None:
         ws = _fused_workspace(R, H, V, v_chunk, dev, K)
     ranges = [(0, V)]
