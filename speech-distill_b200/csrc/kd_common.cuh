@@ -60,6 +60,25 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
                : "l"(p));
   return r;
 }
+// L2 eviction policies (createpolicy) for the two-sweep row kernel of K2: the first sweep marks a row's lines
+// evict_last so they survive until the second sweep, which reads them evict_first (dead afterwards)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_hint(const void* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
 __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -74,6 +93,10 @@ struct Vec8<float> {
   __device__ __forceinline__ void load_global(const float* p) {
     a = ldg_stream(p);
     b = ldg_stream(p + 4);
+  }
+  __device__ __forceinline__ void load_global_hint(const float* p, uint64_t pol) {
+    a = ldg_hint(p, pol);
+    b = ldg_hint(p + 4, pol);
   }
   __device__ __forceinline__ void load_shared(const float* p) {
     a = *reinterpret_cast<const uint4*>(p);
@@ -101,6 +124,7 @@ template <>
 struct Vec8<__nv_bfloat16> {
   uint4 a;
   __device__ __forceinline__ void load_global(const __nv_bfloat16* p) { a = ldg_stream(p); }
+  __device__ __forceinline__ void load_global_hint(const __nv_bfloat16* p, uint64_t pol) { a = ldg_hint(p, pol); }
   __device__ __forceinline__ void load_shared(const __nv_bfloat16* p) { a = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void store_shared(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = a; }
   __device__ __forceinline__ void store_global(__nv_bfloat16* p) const { stg_stream(p, a); }
@@ -127,6 +151,7 @@ template <>
 struct Vec8<__half> {
   uint4 a;
   __device__ __forceinline__ void load_global(const __half* p) { a = ldg_stream(p); }
+  __device__ __forceinline__ void load_global_hint(const __half* p, uint64_t pol) { a = ldg_hint(p, pol); }
   __device__ __forceinline__ void load_shared(const __half* p) { a = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void store_shared(__half* p) const { *reinterpret_cast<uint4*>(p) = a; }
   __device__ __forceinline__ void store_global(__half* p) const { stg_stream(p, a); }

@@ -14,6 +14,9 @@
 //   G  = c1 (e^{z-LSE1} - [v=l]) + c2 (e^{z/tau-LSE_tau} - P),  c1 = alpha g/N, c2 = (1-alpha) tau g/N
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "kd_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -366,6 +369,328 @@ __global__ void __launch_bounds__(kStreamThreads) kd_stream_kernel(const StreamP
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K2, row-per-CTA form (default).  One CTA owns a whole row: sweep 1 streams z and y from HBM (16-byte loads,
+// the next 16 elements' loads in flight while 16 are being reduced) into the online statistics, one block
+// reduction gives the row's log-sum-exps, sweep 2 re-reads the row - 612 KB for bf16 z + y, still resident in
+// the 126 MB L2 because only ~148 rows are in flight - and streams the gradient out with evict-first stores.
+// HBM traffic stays at the algorithmic 6 B / element; compared with the cluster form above there is no shared-
+// memory stash, no DSMEM exchange and 8x fewer reductions per row (the cluster form spends ~2/3 of its issued
+// instructions on them and is latency-bound at 18 us per row).
+// ------------------------------------------------------------------------------------------
+constexpr int kRowThreadsMax = 1024;
+
+struct RowShared {
+  Stats7 warp_stats[kRowThreadsMax / 32];
+  Stats7 row_stats;
+  float sp_lk;
+  int next_row;
+};
+
+template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
+__global__ void __launch_bounds__(kRowThreads, 1) kd_stream_row_kernel(const StreamParams p, int* __restrict__ row_counter) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ RowShared sh;
+  float* sp_p = reinterpret_cast<float*>(dyn_smem);  // sparse teacher only: p_k and i_k of the current row
+  int32_t* sp_i = reinterpret_cast<int32_t*>(sp_p + p.K);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inv_tau = 1.0f / p.tau;
+  const int V = p.V;
+  const bool vec_ok = p.vec_ok != 0;
+  const int nvec = vec_ok ? V / 8 : 0;  // 16-byte pieces of a row; [8 nvec, V) is the scalar tail
+  const int n_rows = p.B * p.T;
+  float norm = 0.f;
+  if (GRAD) {
+    const int nn = *p.n_norm;
+    norm = nn > 0 ? p.grad_scale / (float)nn : 0.f;
+  }
+  const float c1 = p.alpha * norm;
+  const float c2 = (1.f - p.alpha) * p.tau * norm;
+  double acc_ce = 0.0, acc_kl = 0.0, acc_t = 0.0;
+  int acc_n = 0, acc_hits = 0;
+  // sweep 1 keeps the row's lines in L2 (evict_last) only when a second sweep will read them
+  const uint64_t pol_keep = GRAD ? l2_policy_evict_last() : l2_policy_evict_first();
+  const uint64_t pol_drop = l2_policy_evict_first();
+
+  for (;;) {
+    // rows are drawn from a counter: rows that are not scored cost a fifth of a scored one
+    if (tid == 0) sh.next_row = atomicAdd(row_counter, 1);
+    __syncthreads();
+    const int row = sh.next_row;
+    if (row >= n_rows) break;
+    const int b = row / p.T, t = row - b * p.T;
+    const int target = p.row_target[row];
+    TZ* out_row = GRAD ? reinterpret_cast<TZ*>(p.dlogits) + (size_t)row * V : nullptr;
+    if (target < 0) {  // zero gradient, nothing to read
+      if (GRAD) {
+        constexpr int kPer16 = 16 / sizeof(TZ);
+        if (vec_ok) {
+          const uint4 zero4 = make_uint4(0, 0, 0, 0);
+          const int n16 = V / kPer16;
+          for (int i = tid; i < n16; i += kRowThreads) stg_stream(out_row + (size_t)i * kPer16, zero4);
+          for (int i = n16 * kPer16 + tid; i < V; i += kRowThreads) out_row[i] = Elem<TZ>::from_f(0.f);
+        } else {
+          for (int i = tid; i < V; i += kRowThreads) out_row[i] = Elem<TZ>::from_f(0.f);
+        }
+      }
+      __syncthreads();  // sh.next_row is rewritten by the next draw
+      continue;
+    }
+    const TZ* zrow = reinterpret_cast<const TZ*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
+    const TY* yrow = DENSE ? reinterpret_cast<const TY*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st : nullptr;
+
+    // ---------------- sweep 1: HBM -> registers, online statistics, 16 elements per update ----------------
+    Stats7 s;
+    s.m = s.mt = -CUDART_INF_F;
+    s.s1 = s.st = s.t1 = s.tt = s.a = 0.f;
+    {
+      // thread `tid` takes pieces tid, tid + T, ... in pairs (q, q + kRowThreads); the pair after next is loaded
+      // before the current one is reduced
+      Vec8<TZ> z0, z1, nz0, nz1;
+      Vec8<TY> y0, y1, ny0, ny1;
+      int q = tid;
+      auto load_pair = [&](int qq, Vec8<TZ>& a, Vec8<TZ>& bb, Vec8<TY>& c, Vec8<TY>& d) {
+        if (qq < nvec) {
+          a.load_global_hint(zrow + (size_t)qq * 8, pol_keep);
+          if (DENSE) c.load_global_hint(yrow + (size_t)qq * 8, pol_keep);
+        }
+        if (qq + kRowThreads < nvec) {
+          bb.load_global_hint(zrow + (size_t)(qq + kRowThreads) * 8, pol_keep);
+          if (DENSE) d.load_global_hint(yrow + (size_t)(qq + kRowThreads) * 8, pol_keep);
+        }
+      };
+      load_pair(q, z0, z1, y0, y1);
+      for (; q < nvec; q += 2 * kRowThreads) {
+        load_pair(q + 2 * kRowThreads, nz0, nz1, ny0, ny1);
+        float fz[16], fy[16];
+        const bool two = q + kRowThreads < nvec;
+        {
+          float t8[8];
+          z0.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fz[j] = t8[j];
+          if (two) {
+            z1.unpack(t8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fz[8 + j] = t8[j];
+          }
+          if (DENSE) {
+            y0.unpack(t8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fy[j] = t8[j];
+            if (two) {
+              y1.unpack(t8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fy[8 + j] = t8[j];
+            }
+          }
+        }
+        if (two) {
+          student_update<TAU2, 16>(fz, 16, inv_tau, s.m, s.s1, s.st);
+          if (DENSE) teacher_update<TAU2, 16>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
+        } else {
+          student_update<TAU2, 16>(fz, 8, inv_tau, s.m, s.s1, s.st);
+          if (DENSE) teacher_update<TAU2, 16>(fy, fz, 8, inv_tau, s.mt, s.t1, s.tt, s.a);
+        }
+        z0 = nz0; z1 = nz1;
+        if (DENSE) { y0 = ny0; y1 = ny1; }
+      }
+      for (int i = nvec * 8 + tid; i < V; i += kRowThreads) {  // scalar tail / unaligned rows
+        float fz[8], fy[8];
+        fz[0] = Elem<TZ>::to_f(zrow[i]);
+        student_update<TAU2, 8>(fz, 1, inv_tau, s.m, s.s1, s.st);
+        if (DENSE) {
+          fy[0] = Elem<TY>::to_f(yrow[i]);
+          teacher_update<TAU2, 8>(fy, fz, 1, inv_tau, s.mt, s.t1, s.tt, s.a);
+        }
+      }
+    }
+    // ---------------- block reduction ----------------
+    s = warp_merge<DENSE>(s, inv_tau);
+    if (lane == 0) sh.warp_stats[warp] = s;
+    if (!DENSE && warp == 1) {  // sparse teacher: p_k = softmax(v / tau) over the K entries (:94-95)
+      const float* vrow = p.topk_v + (size_t)row * p.K;
+      const int32_t* irow = p.topk_i + (size_t)row * p.K;
+      float vm = -CUDART_INF_F;
+      for (int k = lane; k < p.K; k += 32) vm = fmaxf(vm, vrow[k]);
+      vm = warp_max(vm);
+      float sum = 0.f;
+      for (int k = lane; k < p.K; k += 32) sum += ex2((vrow[k] - vm) * kLog2e * inv_tau);
+      sum = warp_sum(sum);
+      const float lk = vm * inv_tau + ln_acc(sum);
+      for (int k = lane; k < p.K; k += 32) {
+        sp_p[k] = __expf(vrow[k] * inv_tau - lk);
+        sp_i[k] = irow[k];
+      }
+      if (lane == 0) sh.sp_lk = lk;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      Stats7 w;
+      if (lane < kRowThreads / 32) {
+        w = sh.warp_stats[lane];
+      } else {
+        w.m = w.mt = -CUDART_INF_F;
+        w.s1 = w.st = w.t1 = w.tt = w.a = 0.f;
+      }
+      w = warp_merge<DENSE>(w, inv_tau);
+      if (lane == 0) sh.row_stats = w;
+    }
+    __syncthreads();
+    const Stats7 f = sh.row_stats;
+    const float lse1 = f.m + ln_acc(f.s1);
+    const float lset = f.m * inv_tau + ln_acc(f.st);
+    const float lsett = DENSE ? f.mt * inv_tau + ln_acc(f.tt) : 0.f;
+    const float sp_lk = DENSE ? 0.f : sh.sp_lk;
+
+    // ---------------- per-row scalars ----------------
+    if (DENSE) {
+      if (tid == 0) {
+        const float zl = Elem<TZ>::to_f(zrow[target]);
+        const float yl = Elem<TY>::to_f(yrow[target]);
+        acc_ce += (double)(lse1 - zl);
+        acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
+        acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
+        acc_n += 1;
+      }
+    } else if (warp == 0) {
+      // KL_r = sum_k p_k (log p_k - z_{i_k}/tau) + LSE_tau ; monitor hits (distillation_loss.py:104-116)
+      const float* vrow = p.topk_v + (size_t)row * p.K;
+      float part = 0.f, hsum = 0.f;
+      int hits = 0;
+      for (int k = lane; k < p.K; k += 32) {
+        const int idx = sp_i[k];
+        const float pk = sp_p[k];
+        const float vk = vrow[k];
+        if (idx >= 0 && idx < V) {
+          const float zk = Elem<TZ>::to_f(zrow[idx]);
+          part += pk * ((vk * inv_tau - sp_lk) - zk * inv_tau);
+        }
+        if (idx == target) {
+          hits += 1;
+          hsum += vk;
+        }
+      }
+      part = warp_sum(part);
+      hsum = warp_sum(hsum);
+      hits = __reduce_add_sync(0xffffffffu, hits);
+      if (lane == 0) {
+        const float zl = Elem<TZ>::to_f(zrow[target]);
+        acc_ce += (double)(lse1 - zl);
+        acc_kl += (double)(part + lset);
+        acc_t += (double)hsum;
+        acc_hits += hits;
+        acc_n += 1;
+      }
+    }
+
+    // ---------------- sweep 2: gradient; z and y come back from L2 ----------------
+    if (GRAD) {
+      const float c_tau = kLog2e * inv_tau;
+      const float off1 = lse1 * kLog2e, offt = lset * kLog2e, offy = lsett * kLog2e;
+      const float half_off1 = off1 * 0.5f;
+      const float k_tau = c2 * ex2(half_off1 - offt);  // tau = 2: e^{z/2 - LSE_tau} = E e^{LSE1/2 - LSE_tau}
+      auto grad8 = [&](const float(&fz)[8], const float(&fy)[8], int base, int nvalid, float(&g)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < nvalid) {
+            float gi;
+            if (TAU2) {
+              const float e = ex2(fmaf(fz[i], c_tau, -half_off1));
+              gi = e * fmaf(e, c1, k_tau);
+            } else {
+              gi = c1 * ex2(fmaf(fz[i], kLog2e, -off1)) + c2 * ex2(fmaf(fz[i], c_tau, -offt));
+            }
+            if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
+            g[i] = gi;
+          }
+        }
+        const unsigned d = (unsigned)(target - base);
+        if (d < (unsigned)nvalid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((int)d == i) g[i] -= c1;
+        }
+      };
+      {
+        Vec8<TZ> z0, z1, nz0, nz1;
+        Vec8<TY> y0, y1, ny0, ny1;
+        int q = tid;
+        auto load_pair = [&](int qq, Vec8<TZ>& a, Vec8<TZ>& bb, Vec8<TY>& c, Vec8<TY>& d) {
+          if (qq < nvec) {
+            a.load_global_hint(zrow + (size_t)qq * 8, pol_drop);
+            if (DENSE) c.load_global_hint(yrow + (size_t)qq * 8, pol_drop);
+          }
+          if (qq + kRowThreads < nvec) {
+            bb.load_global_hint(zrow + (size_t)(qq + kRowThreads) * 8, pol_drop);
+            if (DENSE) d.load_global_hint(yrow + (size_t)(qq + kRowThreads) * 8, pol_drop);
+          }
+        };
+        load_pair(q, z0, z1, y0, y1);
+        for (; q < nvec; q += 2 * kRowThreads) {
+          load_pair(q + 2 * kRowThreads, nz0, nz1, ny0, ny1);
+          float fz[8], fy[8], g[8];
+          z0.unpack(fz);
+          if (DENSE) y0.unpack(fy);
+          grad8(fz, fy, q * 8, 8, g);
+          Vec8<TZ> vo;
+          vo.pack(g);
+          vo.store_global(out_row + (size_t)q * 8);
+          if (q + kRowThreads < nvec) {
+            z1.unpack(fz);
+            if (DENSE) y1.unpack(fy);
+            grad8(fz, fy, (q + kRowThreads) * 8, 8, g);
+            vo.pack(g);
+            vo.store_global(out_row + (size_t)(q + kRowThreads) * 8);
+          }
+          z0 = nz0; z1 = nz1;
+          if (DENSE) { y0 = ny0; y1 = ny1; }
+        }
+        for (int i = nvec * 8 + tid; i < V; i += kRowThreads) {
+          float fz[8], fy[8], g[8];
+          fz[0] = Elem<TZ>::to_f(zrow[i]);
+          if (DENSE) fy[0] = Elem<TY>::to_f(yrow[i]);
+          grad8(fz, fy, i, 1, g);
+          out_row[i] = Elem<TZ>::from_f(g[0]);
+        }
+      }
+      if (!DENSE) {
+        // scatter part of the sparse gradient: G[i_k] -= c2 * (sum of p_j with i_j == i_k), exact in fp32 and
+        // written once per distinct index, after the sweep's own stores (CTA barrier)
+        __syncthreads();
+        for (int k = tid; k < p.K; k += kRowThreads) {
+          const int idx = sp_i[k];
+          if (idx < 0 || idx >= V) continue;
+          float ptot = 0.f;
+          bool first = true;
+          for (int j = 0; j < p.K; ++j) {
+            if (sp_i[j] == idx) {
+              ptot += sp_p[j];
+              if (j < k) first = false;
+            }
+          }
+          if (!first) continue;
+          const float zk = Elem<TZ>::to_f(zrow[idx]);
+          float gi = c1 * ex2(fmaf(zk, kLog2e, -off1)) + c2 * (ex2(fmaf(zk, c_tau, -offt)) - ptot);
+          if (idx == target) gi -= c1;
+          out_row[idx] = Elem<TZ>::from_f(gi);
+        }
+      }
+    }
+    __syncthreads();  // sh.* and sp_* are rewritten by the next row
+  }
+  if (tid == 0) {
+    float* out = p.partials + (size_t)blockIdx.x * kNumPartialSlots;
+    out[0] = (float)acc_ce;
+    out[1] = (float)acc_kl;
+    out[2] = (float)acc_t;
+    out[3] = (float)acc_n;
+    out[4] = (float)acc_hits;
+    out[5] = out[6] = out[7] = 0.f;
+  }
+}
+
 // deterministic fixed-order reduction of the per-cluster partial records -> sums[8]
 __global__ void kd_reduce_partials_kernel(const float* __restrict__ partials, int n, float* __restrict__ sums) {
   __shared__ double sm[kNumPartialSlots][33];
@@ -466,8 +791,62 @@ __global__ void kd_zero_rows_kernel(T* __restrict__ x, int64_t n) {
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxClusters = 1024;
 
+// KD_STREAM=cluster selects the cluster / shared-memory-stash form; the row-per-CTA form is the default
+static bool stream_row_form() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_STREAM");
+    v = (e && e[0] == 'c') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static int stream_row_threads() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("KD_STREAM_THREADS");
+    v = e ? atoi(e) : 512;  // measured: 512 (126 registers, no spills) > 768 > 1024 (64 registers, spills)
+    if (v != 1024 && v != 768) v = 512;
+  }
+  return v;
+}
+
+template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
+static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream);
+
+template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
+static int launch_stream_rows(const StreamParams& p0, cudaStream_t stream) {
+  // KD_STREAM_THREADS = 768 / 1024: experiment knob, headline instantiation only
+  if (std::is_same<TZ, __nv_bfloat16>::value && std::is_same<TY, __nv_bfloat16>::value && DENSE && TAU2) {
+    const int t = stream_row_threads();
+    if (t == 1024) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 1024>(p0, stream);
+    if (t == 768) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 768>(p0, stream);
+  }
+  return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 512>(p0, stream);
+}
+
+template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
+static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream) {
+  StreamParams p = p0;
+  auto kern = kd_stream_row_kernel<TZ, TY, DENSE, TAU2, GRAD, kRowThreads>;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_rows = p.B * p.T;
+  int grid = sms < n_rows ? sms : n_rows;  // one CTA per SM: ~148 rows in flight keep z + y of a row in L2
+  if (grid > kMaxClusters) grid = kMaxClusters;
+  // the row counter sits behind the reduced record in the workspace
+  int* counter = reinterpret_cast<int*>(p.partials + (size_t)(kMaxClusters + 1) * kNumPartialSlots);
+  if (check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), stream), "row counter")) return 1;
+  const size_t dyn = DENSE ? 0 : (size_t)p.K * 8;
+  kern<<<grid, kRowThreads, dyn, stream>>>(p, counter);
+  if (check_cuda(cudaGetLastError(), "kd_stream_row launch")) return 1;
+  return reduce_partials(p.partials, grid, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
+}
+
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
 static int launch_stream(const StreamParams& p0, cudaStream_t stream) {
+  if (stream_row_form()) return launch_stream_rows<TZ, TY, DENSE, TAU2, GRAD>(p0, stream);
   StreamParams p = p0;
   auto kern = kd_stream_kernel<TZ, TY, DENSE, TAU2, GRAD>;
   int dev = 0, sms = 0, max_optin = 0;
@@ -599,7 +978,7 @@ static int stream_common(StreamParams& p, int z_dtype, int y_dtype, bool dense, 
 using namespace kd;
 
 extern "C" size_t kd_stream_workspace_bytes(void) {
-  return (size_t)(kMaxClusters + 1) * kNumPartialSlots * sizeof(float);
+  return (size_t)(kMaxClusters + 1) * kNumPartialSlots * sizeof(float) + 16 /* row counter */;
 }
 
 extern "C" int kd_prepare_rows(const int64_t* labels, const uint8_t* mask, int B, int T, int64_t ignore_index,

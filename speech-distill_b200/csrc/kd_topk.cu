@@ -14,6 +14,8 @@
 // tie-break and equals torch.topk(log_softmax(x)) index-for-index on tie-free rows
 // (hard part 4).  Rows whose candidate list overflows (massive ties, constant
 // rows) take an exact but slow bisection path.
+#include <cstdlib>
+
 #include "kd_common.cuh"
 
 namespace kd {
@@ -79,19 +81,36 @@ __device__ void bitonic_desc_u32(uint32_t* a, int n) {
   __syncthreads();
 }
 
+constexpr int kTopkUnroll = 4;  // independent 16-byte loads in flight per thread (the loops are latency-bound)
+
 template <typename T, typename F>
 __device__ __forceinline__ void for_each_elem(const T* __restrict__ row, int V, bool vec_ok, F&& fn) {
   const int tid = threadIdx.x;
   const int vhi = vec_ok ? (V & ~7) : 0;
-  for (int i = tid * 8; i < vhi; i += kTopkThreads * 8) {
+  const uint64_t pol_drop = l2_policy_evict_first();  // second (and later) reads: the lines are dead afterwards
+  constexpr int kStep = kTopkThreads * 8;
+  int i = tid * 8;
+  for (; i + (kTopkUnroll - 1) * kStep < vhi; i += kTopkUnroll * kStep) {
+    Vec8<T> v[kTopkUnroll];
+#pragma unroll
+    for (int u = 0; u < kTopkUnroll; ++u) v[u].load_global_hint(row + i + u * kStep, pol_drop);
+#pragma unroll
+    for (int u = 0; u < kTopkUnroll; ++u) {
+      float f[8];
+      v[u].unpack(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fn(f[j], i + u * kStep + j);
+    }
+  }
+  for (; i < vhi; i += kStep) {
     Vec8<T> v;
-    v.load_global(row + i);
+    v.load_global_hint(row + i, pol_drop);
     float f[8];
     v.unpack(f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) fn(f[j], i + j);
   }
-  for (int i = vhi + tid; i < V; i += kTopkThreads) fn(Elem<T>::to_f(row[i]), i);
+  for (int i2 = vhi + tid; i2 < V; i2 += kTopkThreads) fn(Elem<T>::to_f(row[i2]), i2);
 }
 
 // block-wide count of elements satisfying pred (two alternating counters avoid a reset barrier)
@@ -122,9 +141,9 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
     float m = -CUDART_INF_F, s = 0.f;
     {
       const int vhi = vec_ok ? (V & ~7) : 0;
-      for (int i = tid * 8; i < vhi; i += kTopkThreads * 8) {
-        Vec8<T> v;
-        v.load_global(row + i);
+      const uint64_t pol_keep = l2_policy_evict_last();  // the row is read again from L2 in pass 2
+      constexpr int kStep = kTopkThreads * 8;
+      auto update8 = [&](const Vec8<T>& v) {
         float f[8];
         v.unpack(f);
         float vm = f[0];
@@ -136,9 +155,27 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
         }
         if (m != -CUDART_INF_F) {
           const float off = m * kLog2e;
+          float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s += ex2(fmaf(f[j], kLog2e, -off));
+          for (int j = 0; j < 8; j += 2) {
+            p0 += ex2(fmaf(f[j], kLog2e, -off));
+            p1 += ex2(fmaf(f[j + 1], kLog2e, -off));
+          }
+          s += p0 + p1;
         }
+      };
+      int i = tid * 8;
+      for (; i + (kTopkUnroll - 1) * kStep < vhi; i += kTopkUnroll * kStep) {
+        Vec8<T> v[kTopkUnroll];
+#pragma unroll
+        for (int u = 0; u < kTopkUnroll; ++u) v[u].load_global_hint(row + i + u * kStep, pol_keep);
+#pragma unroll
+        for (int u = 0; u < kTopkUnroll; ++u) update8(v[u]);
+      }
+      for (; i < vhi; i += kStep) {
+        Vec8<T> v;
+        v.load_global_hint(row + i, pol_keep);
+        update8(v);
       }
       for (int i = vhi + tid; i < V; i += kTopkThreads) {
         const float x = Elem<T>::to_f(row[i]);
@@ -249,7 +286,21 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   if (R == 0) return 0;
   const size_t es = dtype == KD_DTYPE_F32 ? 4 : 2;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * es) % 16 == 0) ? 1 : 0;
-  const int grid = (int)(R < 148 * 64 ? R : 148 * 64);
+  // persistent: a few CTAs per SM loop over the rows, so that the rows in flight (306 KB each for bf16 at
+  // V = 152,936) stay L2-resident between the two passes; KD_TOPK_CTAS_PER_SM overrides the default of 3
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("KD_TOPK_CTAS_PER_SM");
+    per_sm = e ? atoi(e) : 3;
+    if (per_sm < 1 || per_sm > 64) per_sm = 3;
+  }
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = (int)(R < (int64_t)sms * per_sm ? R : (int64_t)sms * per_sm);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case KD_DTYPE_F32:
