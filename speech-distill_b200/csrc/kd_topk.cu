@@ -35,7 +35,8 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 
 struct TopkShared {
   uint64_t cand[kTopkCap];
-  uint32_t tmax[kTopkThreads];
+  uint64_t xch[2 * kTopkThreads];  // cross-warp exchange of block_sort_desc (u32 keys use the same storage)
+  uint32_t thr;
   float red_m[kTopkThreads / 32];
   float red_s[kTopkThreads / 32];
   int count;
@@ -83,6 +84,43 @@ __device__ void bitonic_desc_u32(uint32_t* a, int n) {
 
 constexpr int kTopkUnroll = 4;  // independent 16-byte loads in flight per thread (the loops are latency-bound)
 
+// Descending bitonic sort of one key per thread over the whole CTA (kTopkThreads keys): afterwards thread i holds
+// the i-th largest.  Exchanges inside a warp are shuffles (no barrier); the 10 stages whose partner sits in
+// another warp go through a double-buffered shared-memory array with one barrier each (the all-smem version
+// needs one barrier for each of its 45 stages).
+__device__ __forceinline__ uint32_t shfl_xor_key(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int m) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((uint64_t)hi << 32) | lo;
+}
+template <typename KeyT>
+__device__ __forceinline__ KeyT block_sort_desc(KeyT key, KeyT* xch /* [2][kTopkThreads] */) {
+  const int tid = threadIdx.x;
+  int buf = 0;
+#pragma unroll 1
+  for (int size = 2; size <= kTopkThreads; size <<= 1) {
+    const bool desc = (tid & size) == 0;
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      KeyT other;
+      if (stride < 32) {
+        other = shfl_xor_key(key, stride);
+      } else {
+        xch[buf * kTopkThreads + tid] = key;
+        __syncthreads();
+        other = xch[buf * kTopkThreads + (tid ^ stride)];
+        buf ^= 1;  // the next cross-warp stage writes the other buffer: no second barrier needed
+      }
+      const bool lower = (tid & stride) == 0;            // this thread keeps the "first" element of the pair
+      const bool take_max = lower == desc;
+      const KeyT mx = key > other ? key : other, mn = key > other ? other : key;
+      key = take_max ? mx : mn;
+    }
+  }
+  return key;
+}
+
 template <typename T, typename F>
 __device__ __forceinline__ void for_each_elem(const T* __restrict__ row, int V, bool vec_ok, F&& fn) {
   const int tid = threadIdx.x;
@@ -111,6 +149,78 @@ __device__ __forceinline__ void for_each_elem(const T* __restrict__ row, int V, 
     for (int j = 0; j < 8; ++j) fn(f[j], i + j);
   }
   for (int i2 = vhi + tid; i2 < V; i2 += kTopkThreads) fn(Elem<T>::to_f(row[i2]), i2);
+}
+
+// any element of 8 packed 16-bit values >= thr (NaN counts as >=)?  Two elements per HSETP2; fp32 rows compare
+// element-wise.  Only vectors that pass are unpacked.
+template <typename T>
+__device__ __forceinline__ bool any_ge(const Vec8<T>& v, float thr);
+template <>
+__device__ __forceinline__ bool any_ge<__nv_bfloat16>(const Vec8<__nv_bfloat16>& v, float thr) {
+  const __nv_bfloat162 t2 = __float2bfloat162_rn(thr);
+  const uint32_t w[4] = {v.a.x, v.a.y, v.a.z, v.a.w};
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) any |= !__hblt2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]), t2);
+  return any;
+}
+template <>
+__device__ __forceinline__ bool any_ge<__half>(const Vec8<__half>& v, float thr) {
+  const __half2 t2 = __float2half2_rn(thr);
+  const uint32_t w[4] = {v.a.x, v.a.y, v.a.z, v.a.w};
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) any |= !__hblt2(*reinterpret_cast<const __half2*>(&w[i]), t2);
+  return any;
+}
+template <>
+__device__ __forceinline__ bool any_ge<float>(const Vec8<float>& v, float thr) {
+  float f[8];
+  v.unpack(f);
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) any |= !(f[j] < thr);
+  return any;
+}
+
+// pass 2: append every element with key >= t0 to the shared-memory candidate list
+template <typename T>
+__device__ __forceinline__ void collect_candidates(const T* __restrict__ row, int V, bool vec_ok, uint32_t t0,
+                                                   TopkShared& sh) {
+  const int tid = threadIdx.x;
+  const int vhi = vec_ok ? (V & ~7) : 0;
+  const float t0f = key_to_float(t0);  // exactly representable in T: it is one of the row's elements
+  const uint64_t pol_drop = l2_policy_evict_first();
+  auto push = [&](float x, int idx) {
+    const uint32_t key = order_key(x);
+    if (key >= t0) {
+      const int slot = atomicAdd(&sh.count, 1);
+      if (slot < kTopkCap) sh.cand[slot] = ((uint64_t)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)idx);
+    }
+  };
+  auto visit = [&](const Vec8<T>& v, int base) {
+    if (any_ge<T>(v, t0f)) {  // rare: ~k of the V / 8 vectors of a row
+      float f[8];
+      v.unpack(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) push(f[j], base + j);
+    }
+  };
+  constexpr int kStep = kTopkThreads * 8;
+  int i = tid * 8;
+  for (; i + (kTopkUnroll - 1) * kStep < vhi; i += kTopkUnroll * kStep) {
+    Vec8<T> v[kTopkUnroll];
+#pragma unroll
+    for (int u = 0; u < kTopkUnroll; ++u) v[u].load_global_hint(row + i + u * kStep, pol_drop);
+#pragma unroll
+    for (int u = 0; u < kTopkUnroll; ++u) visit(v[u], i + u * kStep);
+  }
+  for (; i < vhi; i += kStep) {
+    Vec8<T> v;
+    v.load_global_hint(row + i, pol_drop);
+    visit(v, i);
+  }
+  for (int i2 = vhi + tid; i2 < V; i2 += kTopkThreads) push(Elem<T>::to_f(row[i2]), i2);
 }
 
 // block-wide count of elements satisfying pred (two alternating counters avoid a reset barrier)
@@ -166,11 +276,38 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
       };
       int i = tid * 8;
       for (; i + (kTopkUnroll - 1) * kStep < vhi; i += kTopkUnroll * kStep) {
+        // 32 elements per online update: one maximum / rescale decision for all four vectors, then the
+        // exponentials back to back (the 8-element form spent a third of its instructions on the branches)
         Vec8<T> v[kTopkUnroll];
 #pragma unroll
         for (int u = 0; u < kTopkUnroll; ++u) v[u].load_global_hint(row + i + u * kStep, pol_keep);
+        float f[kTopkUnroll][8];
+        float vm = -CUDART_INF_F;
 #pragma unroll
-        for (int u = 0; u < kTopkUnroll; ++u) update8(v[u]);
+        for (int u = 0; u < kTopkUnroll; ++u) {
+          v[u].unpack(f[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vm = fmaxf(vm, f[u][j]);
+        }
+        if (vm > m) {
+          s *= exp_diff(m, vm, kLog2e);
+          m = vm;
+        }
+        if (m != -CUDART_INF_F) {
+          const float off = m * kLog2e;
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+          for (int u = 0; u < kTopkUnroll; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              p0 += ex2(fmaf(f[u][j], kLog2e, -off));
+              p1 += ex2(fmaf(f[u][j + 1], kLog2e, -off));
+              p2 += ex2(fmaf(f[u][j + 2], kLog2e, -off));
+              p3 += ex2(fmaf(f[u][j + 3], kLog2e, -off));
+            }
+          }
+          s += (p0 + p1) + (p2 + p3);
+        }
       }
       for (; i < vhi; i += kStep) {
         Vec8<T> v;
@@ -186,7 +323,6 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
         if (m != -CUDART_INF_F) s += ex2((x - m) * kLog2e);
       }
     }
-    sh.tmax[tid] = order_key(m);
     // block LSE
     float wm = warp_max(m);
     float ws = warp_sum(s * exp_diff(m, wm, kLog2e));
@@ -207,16 +343,14 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
       }
     }
     // ---- threshold: k-th largest thread maximum ---------------------------------------------
-    bitonic_desc_u32(sh.tmax, kTopkThreads);
-    const uint32_t t0 = sh.tmax[k - 1];
+    {
+      const uint32_t sorted = block_sort_desc<uint32_t>(order_key(m), reinterpret_cast<uint32_t*>(sh.xch));
+      if (tid == k - 1) sh.thr = sorted;
+    }
+    __syncthreads();
+    const uint32_t t0 = sh.thr;
     // ---- pass 2: collect candidates ----------------------------------------------------------
-    for_each_elem(row, V, vec_ok, [&](float x, int idx) {
-      const uint32_t key = order_key(x);
-      if (key >= t0) {
-        const int slot = atomicAdd(&sh.count, 1);
-        if (slot < kTopkCap) sh.cand[slot] = ((uint64_t)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)idx);
-      }
-    });
+    collect_candidates<T>(row, V, vec_ok, t0, sh);
     __syncthreads();
     int count = sh.count;
     if (count > kTopkCap) {
@@ -250,20 +384,26 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
       __syncthreads();
       count = sh.count;  // == k
     }
-    // ---- sort candidates, emit the first k ---------------------------------------------------
-    int n = 32;
-    while (n < count) n <<= 1;
-    for (int i = count + tid; i < n; i += kTopkThreads) sh.cand[i] = 0ull;  // pads sort last
-    bitonic_desc_u64(sh.cand, n);
+    // ---- order the candidates, emit the first k ----------------------------------------------
     const float lm = sh.lse_m, ll = sh.lse_log;
-    for (int j = tid; j < k; j += kTopkThreads) {
-      const uint64_t c = sh.cand[j];
+    auto emit = [&](uint64_t c, int j) {
       const float x = key_to_float((uint32_t)(c >> 32));
       const int idx = (int)(0xffffffffu - (uint32_t)(c & 0xffffffffu));
       const float lp = (x - lm) - ll;
       const float lp_r = Elem<T>::to_f(Elem<T>::from_f(lp));  // log_softmax returns the logits' dtype
       out_v[r * k + j] = __float2half_rn(lp_r);
       out_i[r * k + j] = idx;
+    };
+    if (count <= kTopkThreads) {  // typical: one candidate per thread, sorted in registers
+      const uint64_t mine = tid < count ? sh.cand[tid] : 0ull;  // pads sort last
+      const uint64_t sorted = block_sort_desc<uint64_t>(mine, sh.xch);
+      if (tid < k) emit(sorted, tid);
+    } else {
+      int n = 32;
+      while (n < count) n <<= 1;
+      for (int i = count + tid; i < n; i += kTopkThreads) sh.cand[i] = 0ull;
+      bitonic_desc_u64(sh.cand, n);
+      for (int j = tid; j < k; j += kTopkThreads) emit(sh.cand[j], j);
     }
     __syncthreads();
   }
@@ -287,12 +427,12 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   const size_t es = dtype == KD_DTYPE_F32 ? 4 : 2;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * es) % 16 == 0) ? 1 : 0;
   // persistent: a few CTAs per SM loop over the rows, so that the rows in flight (306 KB each for bf16 at
-  // V = 152,936) stay L2-resident between the two passes; KD_TOPK_CTAS_PER_SM overrides the default of 3
+  // V = 152,936) stay L2-resident between the two passes; KD_TOPK_CTAS_PER_SM overrides the default of 4
   static int per_sm = 0;
   if (per_sm == 0) {
     const char* e = getenv("KD_TOPK_CTAS_PER_SM");
-    per_sm = e ? atoi(e) : 3;
-    if (per_sm < 1 || per_sm > 64) per_sm = 3;
+    per_sm = e ? atoi(e) : 4;
+    if (per_sm < 1 || per_sm > 64) per_sm = 4;
   }
   int sms = 148;
   {
