@@ -202,6 +202,22 @@ int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_targe
                          float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- stage-1 names: causal-LM cross-entropy through the LM head, no teacher --------
+ * What TRL's SFTTrainer asks of the model in stage1.py:329-340 (transformers ForCausalLMLoss, or Liger's
+ * fused-linear-CE under use_liger_kernel, :315), with stage1.py:46-57's frozen-vocabulary mask folded into the
+ * dW GEMM: pass dw_row_begin = V - num_new_tokens and rows below it are never computed (zero-fill dW once).
+ * Thin forwards of kd_fused_linear_fwd / _bwd with KD_TEACHER_NONE, tau = alpha = 1; grad_coef[0] is the
+ * upstream gradient of the mean CE. */
+int kd_ce_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                           const int32_t* row_target, const int32_t* n_rows, int R, int H, int V,
+                           float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int kd_ce_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                           const int32_t* row_target, const int32_t* n_rows, const float* row_stats, int R,
+                           int H, int V, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
+                           void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
+                           int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- teacher LM head in front of the top-k compaction ---------------------------------------
  * out[R,V] bf16 (row stride out_stride, a multiple of 8 elements, 16-byte aligned base; the padding columns
  * V .. roundup(V, 8) - 1 of a row may be zero-filled: TMA stores whole 16-byte granules) = h[R,H] * W[V,H]^T,

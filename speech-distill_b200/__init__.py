@@ -13,7 +13,7 @@ from .loss import (DistillationLoss, fused_linear_kd_loss, fused_linear_kd_value
                    kd_loss_on_logits)
 from .cache import collate_teacher_topk, pad_logits  # noqa: F401
 from .dist import GradSync, allreduce_grad_, make_reduce_fns, plan_ranges  # noqa: F401
-from .lazy import LazyLogits, enable_lazy_logits  # noqa: F401
+from .lazy import LazyLogits, enable_fused_ce, enable_lazy_logits  # noqa: F401
 from .stage1 import freeze_model_weights, fused_linear_cross_entropy, mask_old_rows_  # noqa: F401
 from .vocab_parallel import fused_linear_kd_loss_vocab_parallel, vocab_slices  # noqa: F401
 from .topk import extract_batch, linear_bf16, teacher_head_topk, teacher_topk_logprobs  # noqa: F401
@@ -21,6 +21,6 @@ from .topk import extract_batch, linear_bf16, teacher_head_topk, teacher_topk_lo
 __all__ = [
     "DistillationLoss", "kd_loss_on_logits", "fused_linear_kd_loss", "fused_linear_kd_value_and_grad",
     "teacher_topk_logprobs", "teacher_head_topk", "linear_bf16", "extract_batch",
-    "fused_linear_kd_loss_vocab_parallel", "vocab_slices", "pad_logits", "collate_teacher_topk", "LazyLogits", "enable_lazy_logits", "GradSync", "make_reduce_fns", "allreduce_grad_", "plan_ranges",
+    "fused_linear_kd_loss_vocab_parallel", "vocab_slices", "pad_logits", "collate_teacher_topk", "LazyLogits", "enable_lazy_logits", "enable_fused_ce", "GradSync", "make_reduce_fns", "allreduce_grad_", "plan_ranges",
     "freeze_model_weights", "fused_linear_cross_entropy", "mask_old_rows_", "KdError", "load_library", "LIB_PATH",
 ]

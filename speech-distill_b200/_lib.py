@@ -49,6 +49,9 @@ SIGNATURES = {
                                            _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "kd_fused_merge_workspace_bytes": (_sz, []),
     "kd_fused_merge_ranks": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_ce_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_ce_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64,
+                                      _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     "kd_linear_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
 }

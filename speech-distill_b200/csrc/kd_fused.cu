@@ -1544,6 +1544,7 @@ static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 // one CTA per SM, so a kernel of the next chain fills the SMs the previous one leaves idle in its tail (and the
 // 10 CTA pairs a 64-tile dH launch never uses); results are bit-identical to the serial order.
 struct BwdPipe {
+  std::mutex enqueue;  // the streams and events are per device: one backward is enqueued at a time
   cudaStream_t sw = nullptr, sh = nullptr;
   cudaEvent_t eg[2] = {nullptr, nullptr}, ew[2] = {nullptr, nullptr}, eh[2] = {nullptr, nullptr};
   bool ready = false;
@@ -1884,6 +1885,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
 
   // three chains (grad on the caller's stream, dW, dH) when the pipeline is on; one serial chain otherwise
   BwdPipe* pipe = (bwd_pipe_enabled() && n_chunks > 1) ? get_bwd_pipe() : nullptr;
+  std::unique_lock<std::mutex> pipe_lock;
+  if (pipe) pipe_lock = std::unique_lock<std::mutex>(pipe->enqueue);  // host threads sharing a device take turns
   cudaStream_t s_w = pipe ? pipe->sw : s, s_h = pipe ? pipe->sh : s;
   bool rec_w[2] = {false, false}, rec_h[2] = {false, false};  // chunk c - 2 recorded an event on this buffer
   bool any_w = false, any_h = false;
@@ -2013,6 +2016,25 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     if (any_h && check_cuda(cudaStreamWaitEvent(s, pipe->eh[last_h], 0), "join dH")) return 1;
   }
   return 0;
+}
+
+// Stage-1 entry points named in SURVEY.md 8b: causal-LM cross-entropy through the LM head (no teacher) with the
+// frozen-vocabulary mask folded into the dW GEMM (dw_row_begin = V_old).  Thin forwards of the general calls.
+extern "C" int kd_ce_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                                      const int32_t* row_target, const int32_t* n_rows, int R, int H, int V,
+                                      float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  return kd_fused_linear_fwd(h, h_stride, W, w_stride, KD_TEACHER_NONE, nullptr, 0, 0, nullptr, nullptr, 0, row_target,
+                             n_rows, R, H, V, 1.0f, 1.0f, sums, row_stats, workspace, workspace_bytes, stream);
+}
+extern "C" int kd_ce_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
+                                      const int32_t* row_target, const int32_t* n_rows, const float* row_stats, int R,
+                                      int H, int V, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
+                                      void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
+                                      int v_chunk, void* workspace, size_t workspace_bytes, void* stream) {
+  return kd_fused_linear_bwd(h, h_stride, W, w_stride, KD_TEACHER_NONE, nullptr, 0, 0, nullptr, nullptr, 0, row_target,
+                             n_rows, row_stats, R, H, V, 1.0f, n_norm, grad_coef, grad_dtype, dH, dh_stride, dW,
+                             dw_stride, dw_row_begin, v_chunk, workspace, workspace_bytes, stream);
 }
 
 // out[R, V] (bf16, row stride out_stride) = h[R, H] * W[V, H]^T : the LM head alone, on the K1 pipeline

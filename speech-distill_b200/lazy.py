@@ -158,3 +158,53 @@ def enable_lazy_logits(model):
     model._kd_original_forward = model.forward
     model.forward = forward
     return model
+
+
+def enable_fused_ce(model, num_new_tokens=0):
+    """Stage-1 counterpart of ``enable_lazy_logits`` (reference ``stage1.py:298-340``: TRL ``SFTTrainer`` calls the
+    model with ``labels`` and takes ``outputs.loss``, computed by transformers' ``ForCausalLMLoss`` or by Liger's
+    fused-linear-CE when ``use_liger_kernel=True``, ``stage1.py:315``).
+
+    The patched forward runs the transformer body, then - when ``labels`` (or ``shift_labels``) are given - the fused
+    LM-head cross-entropy kernels with ``dw_row_begin = V - num_new_tokens`` (the rows ``freeze_model_weights``
+    masks, ``stage1.py:46-57``: they are never computed and stay exactly zero), and returns the loss with
+    ``logits=LazyLogits``.  Same reduction as ``ForCausalLMLoss``: mean over the scored tokens, or
+    sum / ``num_items_in_batch`` when the trainer passes it (gradient accumulation)."""
+    from .loss import IGNORE_INDEX, fused_linear_kd_loss, prepare_rows  # noqa: F401
+
+    body = getattr(model, "model", None) or model.base_model
+    head = model.get_output_embeddings()
+    if head is None or getattr(head, "bias", None) is not None:
+        raise ValueError("enable_fused_ce needs a bias-free output embedding (lm_head)")
+    from transformers.modeling_outputs import CausalLMOutputWithPast
+
+    def forward(input_ids=None, attention_mask=None, labels=None, shift_labels=None, num_items_in_batch=None, **kw):
+        for drop in ("logits_to_keep", "num_logits_to_keep"):
+            kw.pop(drop, None)
+        out = body(input_ids=input_ids, attention_mask=attention_mask, **kw)
+        hidden = out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
+        loss = None
+        if labels is not None or shift_labels is not None:
+            if shift_labels is not None:
+                # already shifted (TRL with padding-free batches): undo the shift the kernels apply (row t scores
+                # labels[t + 1]) by prepending one ignored position
+                lab = torch.nn.functional.pad(shift_labels, (1, 0), value=IGNORE_INDEX)[..., : shift_labels.size(-1)]
+            else:
+                lab = labels
+            old_vocab = head.weight.size(0) - int(num_new_tokens) if num_new_tokens else 0
+            total, _, _, _ = fused_linear_kd_loss(hidden, head.weight, lab, teacher_logits=None, temperature=1.0,
+                                                  alpha=1.0, ignore_index=IGNORE_INDEX, dw_row_begin=old_vocab)
+            loss = total
+            if num_items_in_batch is not None:  # ForCausalLMLoss: reduction "sum" / num_items_in_batch
+                B, T = lab.shape[0], lab.shape[-1]
+                _, n_valid = prepare_rows(lab, None, B, T, IGNORE_INDEX, hidden.device)
+                n_items = num_items_in_batch.to(hidden.device) if torch.is_tensor(num_items_in_batch) else num_items_in_batch
+                loss = total * (n_valid.to(torch.float32).reshape(()) / n_items)
+        return CausalLMOutputWithPast(loss=loss, logits=LazyLogits(hidden, head.weight),
+                                      past_key_values=getattr(out, "past_key_values", None),
+                                      hidden_states=getattr(out, "hidden_states", None),
+                                      attentions=getattr(out, "attentions", None))
+
+    model._kd_original_forward = model.forward
+    model.forward = forward
+    return model

@@ -100,3 +100,40 @@ def test_compute_loss_flow_on_lazy_models(top_k):
     else:
         ref = O.reference_loss(z, labels.cpu(), teacher_logits=y, speech_token_mask=mask)
     np.testing.assert_allclose(a[:3], [float(x) for x in ref][:3], rtol=3e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("with_num_items", [False, True])
+def test_stage1_fused_ce_model_patch(with_num_items):
+    """stage1.py:143 + :298-340 on a tiny Qwen3: freeze_model_weights + the trainer's ``model(**batch).loss``.
+    Patched (fused CE, dW rows of the old vocabulary never computed) vs stock transformers ForCausalLMLoss + the
+    reference hook: same loss, same gradients on the new-token rows, exact zeros on the old ones."""
+    import speech_distill_b200 as K
+
+    V, new, B, T = 1000, 40, 2, 48
+    model = _tiny_qwen3(V, 64, 5)
+    g = torch.Generator().manual_seed(8)
+    ids = torch.randint(0, V, (B, T), generator=g).cuda()
+    labels = ids.clone()
+    labels[:, :7] = -100
+    labels[1, 40:] = -100
+    kw = {"num_items_in_batch": torch.tensor(61)} if with_num_items else {}
+
+    K.freeze_model_weights(model, new)
+    out_ref = model(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels, **kw)
+    out_ref.loss.backward()
+    g_head = model.lm_head.weight.grad.clone()
+    g_emb = model.model.embed_tokens.weight.grad.clone()
+    model.zero_grad(set_to_none=True)
+
+    K.enable_fused_ce(model, num_new_tokens=new)
+    out = model(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels, **kw)
+    assert isinstance(out.logits, K.LazyLogits)
+    out.loss.backward()
+    assert abs(float(out.loss) - float(out_ref.loss)) <= 2e-3 * abs(float(out_ref.loss))
+    gh = model.lm_head.weight.grad
+    assert float(gh[: V - new].abs().max()) == 0.0 and float(g_head[: V - new].abs().max()) == 0.0  # stage1.py:53-57
+    ref_new, got_new = g_head[V - new:].float(), gh[V - new:].float()
+    assert float((got_new - ref_new).abs().max() / ref_new.abs().max()) < 2e-2
+    ge, ge_ref = model.model.embed_tokens.weight.grad.float(), g_emb.float()
+    assert float(ge[: V - new].abs().max()) == 0.0
+    assert float((ge[V - new:] - ge_ref[V - new:]).abs().max() / ge_ref[V - new:].abs().max().clamp_min(1e-12)) < 5e-2
