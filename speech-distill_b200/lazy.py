@@ -101,10 +101,8 @@ class LazyLogits:
         from .topk import linear_bf16
 
         H = self.hidden.shape[-1]
-        h2 = self.hidden.detach().reshape(-1, H)
-        if h2.dtype != torch.bfloat16:
-            raise KdError("LazyLogits.materialize needs bf16 hidden states")
-        out = linear_bf16(h2.contiguous(), self.head_weight().detach())
+        h2 = self.hidden.detach().reshape(-1, H).to(torch.bfloat16)
+        out = linear_bf16(h2.contiguous(), self.head_weight().detach().to(torch.bfloat16))
         out = out.reshape(*self.hidden.shape[:-1], self.vocab_size)
         return F.log_softmax(out, dim=-1) if self.log_probs else out
 

@@ -374,8 +374,16 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     (the weight gradient autograd receives is then already summed over ranks).
     """
     require_cuda(hidden, lm_head_weight)
-    if hidden.dtype != torch.bfloat16 or lm_head_weight.dtype != torch.bfloat16:
-        raise TypeError("fused_linear_kd_loss computes in bf16 with fp32 accumulation: pass bf16 hidden and weight")
+    # the tensor-core path computes in bf16 with fp32 accumulation; fp32 / fp16 operands (fp32 master weights,
+    # autocast training) are cast here, inside autograd, so their gradients come back in their own dtype
+    if hidden.dtype != torch.bfloat16:
+        if hidden.dtype not in (torch.float32, torch.float16):
+            raise TypeError(f"hidden states must be bf16, fp16 or fp32, got {hidden.dtype}")
+        hidden = hidden.to(torch.bfloat16)
+    if lm_head_weight.dtype != torch.bfloat16:
+        if lm_head_weight.dtype not in (torch.float32, torch.float16):
+            raise TypeError(f"lm_head weight must be bf16, fp16 or fp32, got {lm_head_weight.dtype}")
+        lm_head_weight = lm_head_weight.to(torch.bfloat16)
     if hidden.dim() != 3:
         raise ValueError("hidden must be [B, T, H]")
     B, T, H = hidden.shape

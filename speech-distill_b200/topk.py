@@ -80,6 +80,10 @@ def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024
     require_cuda(hidden, lm_head_weight)
     lead = hidden.shape[:-1]
     H = hidden.shape[-1]
+    if hidden.dtype != torch.bfloat16:          # fp32 / fp16 teachers: the head runs in bf16 like the student's
+        hidden = hidden.detach().to(torch.bfloat16)
+    if lm_head_weight.dtype != torch.bfloat16:
+        lm_head_weight = lm_head_weight.detach().to(torch.bfloat16)
     h2 = hidden.detach().reshape(-1, H)
     if h2.stride(-1) != 1:
         h2 = h2.contiguous()
