@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "kd_common.cuh"
+#include "kd_umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -691,6 +692,268 @@ __global__ void __launch_bounds__(kRowThreads, 1) kd_stream_row_kernel(const Str
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K2, ring form: the row-per-CTA algorithm above with the memory side handed to a producer warp.
+//   warp 0       : draws rows from the atomic queue and streams them chunk by chunk (8192 elements of z and of y,
+//                  32 KB) into a 6-stage shared-memory ring with cp.async.bulk (mbarrier complete_tx), first the
+//                  statistics pass (L2 evict_last), then - from L2 - the gradient pass (evict_first); it runs
+//                  ahead of the consumers across pass and row boundaries, so up to 192 KB per SM are in flight
+//                  whatever the consumers are doing
+//   warps 1..16  : consume the stages in order: 16 elements per thread and stage from shared memory (no global-load
+//                  latency, no prefetch registers), statistics in registers across the stages of a row, one block
+//                  reduction per row, then the gradient stages, written with evict-first 16-byte stores.
+// Dense bf16 z and y with 16-byte aligned rows; everything else takes the row form.
+// ------------------------------------------------------------------------------------------
+constexpr int kRingConsumers = 512;
+constexpr int kRingThreads = 32 + kRingConsumers;
+constexpr int kRingChunk = 8192;   // elements per stage and tensor
+constexpr int kRingStages = 6;
+constexpr uint32_t kRingStageBytes = 2u * kRingChunk * 2u;  // z + y, bf16
+
+struct RingHdr {
+  int row, pass, c0, n, target;  // pass: 1 statistics, 2 gradient, 3 zero-fill the row, 0 end of work
+};
+
+struct RingShared {
+  RingHdr hdr[kRingStages];
+  uint64_t full[kRingStages], empty[kRingStages];
+  Stats7 warp_stats[kRingConsumers / 32];
+  Stats7 row_stats;
+};
+
+__device__ __forceinline__ void bulk_load_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar,
+                                               uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_dst),
+      "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+template <bool TAU2, bool GRAD>
+__global__ void __launch_bounds__(kRingThreads, 1) kd_stream_ring_kernel(const StreamParams p, int* __restrict__ row_counter) {
+  using namespace umma;
+  using T = __nv_bfloat16;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  __shared__ RingShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = p.V, n_rows = p.B * p.T;
+  const uint32_t ring0 = smem_u32(ring_smem);
+  auto full_bar = [&](int s) { return smem_u32(&sh.full[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&sh.empty[s]); };
+
+  if (tid == 0) {
+    for (int s = 0; s < kRingStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), kRingConsumers / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ======================= producer =======================
+    if (lane == 0) {
+      const uint64_t pol_keep = GRAD ? l2_policy_evict_last() : l2_policy_evict_first();
+      const uint64_t pol_drop = l2_policy_evict_first();
+      int s = 0;
+      uint32_t phase = 0;
+      auto publish = [&](const RingHdr& h, const T* zsrc, const T* ysrc, uint64_t pol) {
+        mbar_wait(empty_bar(s), phase ^ 1u);
+        sh.hdr[s] = h;
+        if (zsrc != nullptr) {
+          const uint32_t bytes = (uint32_t)h.n * 2u;
+          mbar_expect_tx(full_bar(s), 2u * bytes);
+          const uint32_t dst = ring0 + (uint32_t)s * kRingStageBytes;
+          bulk_load_hint(dst, zsrc, bytes, full_bar(s), pol);
+          bulk_load_hint(dst + kRingChunk * 2u, ysrc, bytes, full_bar(s), pol);
+        } else {
+          mbar_arrive(full_bar(s));
+        }
+        if (++s == kRingStages) {
+          s = 0;
+          phase ^= 1u;
+        }
+      };
+      for (;;) {
+        const int row = atomicAdd(row_counter, 1);
+        if (row >= n_rows) break;
+        const int target = p.row_target[row];
+        RingHdr h = {row, 0, 0, 0, target};
+        if (target < 0) {
+          if (GRAD) {
+            h.pass = 3;
+            publish(h, nullptr, nullptr, 0);
+          }
+          continue;
+        }
+        const int b = row / p.T, t = row - b * p.T;
+        const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
+        const T* yrow = reinterpret_cast<const T*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st;
+        for (int pass = 1; pass <= (GRAD ? 2 : 1); ++pass) {
+          for (int c0 = 0; c0 < V; c0 += kRingChunk) {
+            h.pass = pass;
+            h.c0 = c0;
+            h.n = V - c0 < kRingChunk ? V - c0 : kRingChunk;
+            publish(h, zrow + c0, yrow + c0, pass == 1 ? pol_keep : pol_drop);
+          }
+        }
+      }
+      RingHdr end = {-1, 0, 0, 0, -1};
+      publish(end, nullptr, nullptr, 0);
+    }
+    return;
+  }
+
+  // ======================= consumers =======================
+  const int ctid = tid - 32, cwarp = warp - 1;
+  const float inv_tau = 1.0f / p.tau;
+  float norm = 0.f;
+  if (GRAD) {
+    const int nn = *p.n_norm;
+    norm = nn > 0 ? p.grad_scale / (float)nn : 0.f;
+  }
+  const float c1 = p.alpha * norm;
+  const float c2 = (1.f - p.alpha) * p.tau * norm;
+  const float c_tau = kLog2e * inv_tau;
+  double acc_ce = 0.0, acc_kl = 0.0, acc_t = 0.0;
+  int acc_n = 0;
+  Stats7 st;
+  float half_off1 = 0.f, off1 = 0.f, offt = 0.f, offy = 0.f, k_tau = 0.f;  // row constants of the gradient pass
+  int s = 0;
+  uint32_t phase = 0;
+  for (;;) {
+    mbar_wait(full_bar(s), phase);
+    const RingHdr h = sh.hdr[s];
+    if (h.pass == 0) break;
+    T* out_row = GRAD ? reinterpret_cast<T*>(p.dlogits) + (size_t)h.row * V : nullptr;
+    if (h.pass == 3) {  // row without a score: zero gradient, nothing was loaded
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));
+      const uint4 zero4 = make_uint4(0, 0, 0, 0);
+      for (int i = ctid; i < V / 8; i += kRingConsumers) stg_stream(out_row + (size_t)i * 8, zero4);
+    } else {
+      // this thread's two 16-byte pieces of the stage: [8 ctid, +8) and [8 (ctid + 512), +8)
+      const uint32_t zb = ring0 + (uint32_t)s * kRingStageBytes, yb = zb + kRingChunk * 2u;
+      const int e0 = ctid * 8, e1 = (ctid + kRingConsumers) * 8;
+      const int nv = (e0 < h.n ? 8 : 0) + (e1 < h.n ? 8 : 0);  // h.n is a multiple of 8
+      Vec8<T> z0, z1, y0, y1;
+      z0.a = z1.a = y0.a = y1.a = make_uint4(0, 0, 0, 0);
+      if (nv >= 8) {
+        z0.a = lds128(zb + (uint32_t)e0 * 2u);
+        y0.a = lds128(yb + (uint32_t)e0 * 2u);
+      }
+      if (nv == 16) {
+        z1.a = lds128(zb + (uint32_t)e1 * 2u);
+        y1.a = lds128(yb + (uint32_t)e1 * 2u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));  // the stage's bytes are in registers: hand it back
+      if (h.pass == 1) {
+        if (h.c0 == 0) {
+          st.m = st.mt = -CUDART_INF_F;
+          st.s1 = st.st = st.t1 = st.tt = st.a = 0.f;
+        }
+        if (nv > 0) {
+          float fz[16], fy[16], t8[8];
+          z0.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fz[j] = t8[j];
+          y0.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fy[j] = t8[j];
+          z1.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fz[8 + j] = t8[j];
+          y1.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fy[8 + j] = t8[j];
+          student_update<TAU2, 16>(fz, nv, inv_tau, st.m, st.s1, st.st);
+          teacher_update<TAU2, 16>(fy, fz, nv, inv_tau, st.mt, st.t1, st.tt, st.a);
+        }
+        if (h.c0 + h.n >= V) {  // last stage of the statistics pass: block reduction, row scalars
+          Stats7 w = warp_merge<true>(st, inv_tau);
+          if (lane == 0) sh.warp_stats[cwarp] = w;
+          named_bar_sync(1, kRingConsumers);
+          if (cwarp == 0) {
+            Stats7 x;
+            if (lane < kRingConsumers / 32) {
+              x = sh.warp_stats[lane];
+            } else {
+              x.m = x.mt = -CUDART_INF_F;
+              x.s1 = x.st = x.t1 = x.tt = x.a = 0.f;
+            }
+            x = warp_merge<true>(x, inv_tau);
+            if (lane == 0) sh.row_stats = x;
+          }
+          named_bar_sync(2, kRingConsumers);
+          const Stats7 f = sh.row_stats;
+          const float lse1 = f.m + ln_acc(f.s1);
+          const float lset = f.m * inv_tau + ln_acc(f.st);
+          const float lsett = f.mt * inv_tau + ln_acc(f.tt);
+          if (ctid == 0) {
+            const int b = h.row / p.T, t = h.row - b * p.T;
+            const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
+            const T* yrow = reinterpret_cast<const T*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st;
+            const float zl = __bfloat162float(zrow[h.target]);
+            const float yl = __bfloat162float(yrow[h.target]);
+            acc_ce += (double)(lse1 - zl);
+            acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
+            acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
+            acc_n += 1;
+          }
+          off1 = lse1 * kLog2e;
+          offt = lset * kLog2e;
+          offy = lsett * kLog2e;
+          half_off1 = 0.5f * off1;
+          k_tau = c2 * ex2(half_off1 - offt);
+        }
+      } else if (GRAD) {  // h.pass == 2
+        auto grad8 = [&](const Vec8<T>& vz, const Vec8<T>& vy, int base) {
+          float fz[8], fy[8], g[8];
+          vz.unpack(fz);
+          vy.unpack(fy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float gi;
+            if (TAU2) {
+              const float e = ex2(fmaf(fz[i], c_tau, -half_off1));
+              gi = e * fmaf(e, c1, k_tau);
+            } else {
+              gi = c1 * ex2(fmaf(fz[i], kLog2e, -off1)) + c2 * ex2(fmaf(fz[i], c_tau, -offt));
+            }
+            g[i] = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
+          }
+          const unsigned d = (unsigned)(h.target - base);
+          if (d < 8u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((int)d == i) g[i] -= c1;
+          }
+          Vec8<T> vo;
+          vo.pack(g);
+          vo.store_global(out_row + base);
+        };
+        if (nv >= 8) grad8(z0, y0, h.c0 + e0);
+        if (nv == 16) grad8(z1, y1, h.c0 + e1);
+      }
+    }
+    if (++s == kRingStages) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+  if (ctid == 0) {
+    float* out = p.partials + (size_t)blockIdx.x * kNumPartialSlots;
+    out[0] = (float)acc_ce;
+    out[1] = (float)acc_kl;
+    out[2] = (float)acc_t;
+    out[3] = (float)acc_n;
+    out[4] = out[5] = out[6] = out[7] = 0.f;
+  }
+}
+
 // deterministic fixed-order reduction of the per-cluster partial records -> sums[8]
 __global__ void kd_reduce_partials_kernel(const float* __restrict__ partials, int n, float* __restrict__ sums) {
   __shared__ double sm[kNumPartialSlots][33];
@@ -847,9 +1110,53 @@ static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream) {
   return reduce_partials(p.partials, grid, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
 }
 
+// KD_STREAM=ring selects the ring form where it applies (dense bf16, aligned rows).  It is NOT the default: on
+// B200 it measures 5 % slower than the row form at the configs[1] shape (1153 vs 1093 us; forward only 760 vs
+// 601 us) - with the loads out of the way the 16 consumer warps are bound by the XU pipe (4 ex2 per element =
+// 0.56 ms for the whole problem at 16 / clk / SM, as much as the 0.57 ms the HBM needs) and by instruction issue,
+// and the row form's second CTA-free design already overlaps its loads well enough.
+static bool stream_ring_form() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_STREAM");
+    v = (e && e[0] == 'r' && e[1] == 'i') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+template <bool TAU2, bool GRAD>
+static int launch_stream_ring(const StreamParams& p0, cudaStream_t stream) {
+  StreamParams p = p0;
+  auto kern = kd_stream_ring_kernel<TAU2, GRAD>;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_rows = p.B * p.T;
+  int grid = sms < n_rows ? sms : n_rows;
+  if (grid > kMaxClusters) grid = kMaxClusters;
+  int* counter = reinterpret_cast<int*>(p.partials + (size_t)(kMaxClusters + 1) * kNumPartialSlots);
+  if (check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), stream), "row counter")) return 1;
+  const size_t dyn = (size_t)kRingStages * kRingStageBytes + 128;
+  static bool attr_set[4] = {false, false, false, false};
+  const int which = (TAU2 ? 2 : 0) + (GRAD ? 1 : 0);
+  if (!attr_set[which]) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "ring smem attr"))
+      return 1;
+    attr_set[which] = true;
+  }
+  kern<<<grid, kRingThreads, dyn, stream>>>(p, counter);
+  if (check_cuda(cudaGetLastError(), "kd_stream_ring launch")) return 1;
+  return reduce_partials(p.partials, grid, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
+}
+
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
 static int launch_stream(const StreamParams& p0, cudaStream_t stream) {
-  if (stream_row_form()) return launch_stream_rows<TZ, TY, DENSE, TAU2, GRAD>(p0, stream);
+  if (stream_row_form()) {
+    if (DENSE && std::is_same<TZ, __nv_bfloat16>::value && std::is_same<TY, __nv_bfloat16>::value && p0.vec_ok &&
+        p0.V % 8 == 0 && stream_ring_form())
+      return launch_stream_ring<TAU2, GRAD>(p0, stream);
+    return launch_stream_rows<TZ, TY, DENSE, TAU2, GRAD>(p0, stream);
+  }
   StreamParams p = p0;
   auto kern = kd_stream_kernel<TZ, TY, DENSE, TAU2, GRAD>;
   int dev = 0, sms = 0, max_optin = 0;
