@@ -115,3 +115,43 @@ def test_freeze_model_weights_host_logic():
     loss.backward()
     np.testing.assert_allclose(toy.emb.weight.grad.numpy(), d["masked"], rtol=1e-12, atol=1e-15)
     assert [n for n, p in toy.named_parameters() if p.requires_grad] == ["emb.weight"]
+
+
+def test_header_is_plain_c():
+    """include/kd_b200.h is the drop-in boundary: it must compile as C (no C++ / CUDA / torch types) and every
+    prototype must be callable from a C translation unit that links against the library."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    import speech_distill_b200 as K
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = r'''
+#include "kd_b200.h"
+#include <stdio.h>
+int main(void) {
+  /* take the address of every entry point: unresolved or mis-declared symbols fail at link time */
+  void* fns[] = {(void*)kd_version, (void*)kd_last_error, (void*)kd_device_info, (void*)kd_prepare_rows,
+                 (void*)kd_finalize_losses, (void*)kd_stream_workspace_bytes, (void*)kd_dense_fwd_bwd,
+                 (void*)kd_sparse_fwd_bwd, (void*)kd_scale_inplace, (void*)kd_topk_logprobs, (void*)kd_mask_rows,
+                 (void*)kd_compact_rows, (void*)kd_gather_rows, (void*)kd_zero_if_empty,
+                 (void*)kd_fused_workspace_bytes, (void*)kd_fused_linear_fwd, (void*)kd_fused_linear_bwd,
+                 (void*)kd_fused_linear_bwd_range, (void*)kd_fused_linear_fwd_partial,
+                 (void*)kd_fused_merge_workspace_bytes, (void*)kd_fused_merge_ranks, (void*)kd_ce_fused_linear_fwd,
+                 (void*)kd_ce_fused_linear_bwd, (void*)kd_linear_bf16, (void*)kd_gemm_bf16};
+  printf("%d %d\n", kd_version(), (int)(sizeof(fns) / sizeof(fns[0])));
+  return kd_version() == KD_ABI_VERSION ? 0 : 1;
+}
+'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "abi.c")
+        exe = os.path.join(td, "abi")
+        open(c, "w").write(src)
+        libdir = os.path.dirname(K.LIB_PATH)
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+                        "-L", libdir, "-l:libkd_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+        assert int(out[0]) >= 2 and int(out[1]) == len(_declared())
