@@ -20,7 +20,7 @@
 
 namespace kd {
 
-constexpr int kTopkThreads = 512;
+constexpr int kTopkMaxThreads = 512;  // thread counts: 128 (k <= 64), 256 (k <= 128), 512 (k <= 512)
 constexpr int kTopkCap = 2048;
 
 __device__ __forceinline__ uint32_t order_key(float x) {
@@ -35,10 +35,10 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 
 struct TopkShared {
   uint64_t cand[kTopkCap];
-  uint64_t xch[2 * kTopkThreads];  // cross-warp exchange of block_sort_desc (u32 keys use the same storage)
+  uint64_t xch[2 * kTopkMaxThreads];  // cross-warp exchange of block_sort_desc (u32 keys use the same storage)
   uint32_t thr;
-  float red_m[kTopkThreads / 32];
-  float red_s[kTopkThreads / 32];
+  float red_m[kTopkMaxThreads / 32];
+  float red_s[kTopkMaxThreads / 32];
   int count;
   int cnt_a, cnt_b;
   float lse_m, lse_log;
@@ -84,7 +84,7 @@ __device__ void bitonic_desc_u32(uint32_t* a, int n) {
 
 constexpr int kTopkUnroll = 4;  // independent 16-byte loads in flight per thread (the loops are latency-bound)
 
-// Descending bitonic sort of one key per thread over the whole CTA (kTopkThreads keys): afterwards thread i holds
+// Descending bitonic sort of one key per thread over the whole CTA (NT keys): afterwards thread i holds
 // the i-th largest.  Exchanges inside a warp are shuffles (no barrier); the 10 stages whose partner sits in
 // another warp go through a double-buffered shared-memory array with one barrier each (the all-smem version
 // needs one barrier for each of its 45 stages).
@@ -94,12 +94,12 @@ __device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int m) {
   const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
   return ((uint64_t)hi << 32) | lo;
 }
-template <typename KeyT>
-__device__ __forceinline__ KeyT block_sort_desc(KeyT key, KeyT* xch /* [2][kTopkThreads] */) {
+template <typename KeyT, int NT>
+__device__ __forceinline__ KeyT block_sort_desc(KeyT key, KeyT* xch /* [2][NT] */) {
   const int tid = threadIdx.x;
   int buf = 0;
 #pragma unroll 1
-  for (int size = 2; size <= kTopkThreads; size <<= 1) {
+  for (int size = 2; size <= NT; size <<= 1) {
     const bool desc = (tid & size) == 0;
 #pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -107,9 +107,9 @@ __device__ __forceinline__ KeyT block_sort_desc(KeyT key, KeyT* xch /* [2][kTopk
       if (stride < 32) {
         other = shfl_xor_key(key, stride);
       } else {
-        xch[buf * kTopkThreads + tid] = key;
+        xch[buf * NT + tid] = key;
         __syncthreads();
-        other = xch[buf * kTopkThreads + (tid ^ stride)];
+        other = xch[buf * NT + (tid ^ stride)];
         buf ^= 1;  // the next cross-warp stage writes the other buffer: no second barrier needed
       }
       const bool lower = (tid & stride) == 0;            // this thread keeps the "first" element of the pair
@@ -121,12 +121,12 @@ __device__ __forceinline__ KeyT block_sort_desc(KeyT key, KeyT* xch /* [2][kTopk
   return key;
 }
 
-template <typename T, typename F>
+template <typename T, int NT, typename F>
 __device__ __forceinline__ void for_each_elem(const T* __restrict__ row, int V, bool vec_ok, F&& fn) {
   const int tid = threadIdx.x;
   const int vhi = vec_ok ? (V & ~7) : 0;
   const uint64_t pol_drop = l2_policy_evict_first();  // second (and later) reads: the lines are dead afterwards
-  constexpr int kStep = kTopkThreads * 8;
+  constexpr int kStep = NT * 8;
   int i = tid * 8;
   for (; i + (kTopkUnroll - 1) * kStep < vhi; i += kTopkUnroll * kStep) {
     Vec8<T> v[kTopkUnroll];
@@ -148,7 +148,7 @@ __device__ __forceinline__ void for_each_elem(const T* __restrict__ row, int V, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) fn(f[j], i + j);
   }
-  for (int i2 = vhi + tid; i2 < V; i2 += kTopkThreads) fn(Elem<T>::to_f(row[i2]), i2);
+  for (int i2 = vhi + tid; i2 < V; i2 += NT) fn(Elem<T>::to_f(row[i2]), i2);
 }
 
 // any element of 8 packed 16-bit values >= thr (NaN counts as >=)?  Two elements per HSETP2; fp32 rows compare
@@ -184,7 +184,7 @@ __device__ __forceinline__ bool any_ge<float>(const Vec8<float>& v, float thr) {
 }
 
 // pass 2: append every element with key >= t0 to the shared-memory candidate list
-template <typename T>
+template <typename T, int NT>
 __device__ __forceinline__ void collect_candidates(const T* __restrict__ row, int V, bool vec_ok, uint32_t t0,
                                                    TopkShared& sh) {
   const int tid = threadIdx.x;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void collect_candidates(const T* __restrict__ row, in
       for (int j = 0; j < 8; ++j) push(f[j], base + j);
     }
   };
-  constexpr int kStep = kTopkThreads * 8;
+  constexpr int kStep = NT * 8;
   int i = tid * 8;
   for (; i + (kTopkUnroll - 1) * kStep < vhi; i += kTopkUnroll * kStep) {
     Vec8<T> v[kTopkUnroll];
@@ -220,14 +220,14 @@ __device__ __forceinline__ void collect_candidates(const T* __restrict__ row, in
     v.load_global_hint(row + i, pol_drop);
     visit(v, i);
   }
-  for (int i2 = vhi + tid; i2 < V; i2 += kTopkThreads) push(Elem<T>::to_f(row[i2]), i2);
+  for (int i2 = vhi + tid; i2 < V; i2 += NT) push(Elem<T>::to_f(row[i2]), i2);
 }
 
 // block-wide count of elements satisfying pred (two alternating counters avoid a reset barrier)
-template <typename T, typename P>
+template <typename T, int NT, typename P>
 __device__ int block_count(const T* row, int V, bool vec_ok, TopkShared& sh, P&& pred) {
   int c = 0;
-  for_each_elem(row, V, vec_ok, [&](float x, int idx) { c += pred(order_key(x), idx) ? 1 : 0; });
+  for_each_elem<T, NT>(row, V, vec_ok, [&](float x, int idx) { c += pred(order_key(x), idx) ? 1 : 0; });
   c = __reduce_add_sync(0xffffffffu, c);
   __syncthreads();
   if (threadIdx.x == 0) sh.cnt_a = 0;
@@ -237,8 +237,8 @@ __device__ int block_count(const T* row, int V, bool vec_ok, TopkShared& sh, P&&
   return sh.cnt_a;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restrict__ logits, int64_t R, int V,
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) kd_topk_kernel(const T* __restrict__ logits, int64_t R, int V,
                                                                int64_t row_stride, int k, __half* __restrict__ out_v,
                                                                int32_t* __restrict__ out_i, int vec_ok_i) {
   __shared__ TopkShared sh;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
     {
       const int vhi = vec_ok ? (V & ~7) : 0;
       const uint64_t pol_keep = l2_policy_evict_last();  // the row is read again from L2 in pass 2
-      constexpr int kStep = kTopkThreads * 8;
+      constexpr int kStep = NT * 8;
       auto update8 = [&](const Vec8<T>& v) {
         float f[8];
         v.unpack(f);
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
         v.load_global_hint(row + i, pol_keep);
         update8(v);
       }
-      for (int i = vhi + tid; i < V; i += kTopkThreads) {
+      for (int i = vhi + tid; i < V; i += NT) {
         const float x = Elem<T>::to_f(row[i]);
         if (x > m) {
           s *= exp_diff(m, x, kLog2e);
@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
     if (tid == 0) sh.count = 0;
     __syncthreads();
     if (warp == 0) {
-      float a = lane < kTopkThreads / 32 ? sh.red_m[lane] : -CUDART_INF_F;
-      float b = lane < kTopkThreads / 32 ? sh.red_s[lane] : 0.f;
+      float a = lane < NT / 32 ? sh.red_m[lane] : -CUDART_INF_F;
+      float b = lane < NT / 32 ? sh.red_s[lane] : 0.f;
       const float mm = warp_max(a);
       b = warp_sum(b * exp_diff(a, mm, kLog2e));
       if (lane == 0) {
@@ -344,13 +344,13 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
     }
     // ---- threshold: k-th largest thread maximum ---------------------------------------------
     {
-      const uint32_t sorted = block_sort_desc<uint32_t>(order_key(m), reinterpret_cast<uint32_t*>(sh.xch));
+      const uint32_t sorted = block_sort_desc<uint32_t, NT>(order_key(m), reinterpret_cast<uint32_t*>(sh.xch));
       if (tid == k - 1) sh.thr = sorted;
     }
     __syncthreads();
     const uint32_t t0 = sh.thr;
     // ---- pass 2: collect candidates ----------------------------------------------------------
-    collect_candidates<T>(row, V, vec_ok, t0, sh);
+    collect_candidates<T, NT>(row, V, vec_ok, t0, sh);
     __syncthreads();
     int count = sh.count;
     if (count > kTopkCap) {
@@ -358,23 +358,23 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
       uint32_t lo = t0, hi = 0xffffffffu;  // invariant: count(key >= lo) >= k
       while (lo < hi) {
         const uint32_t mid = lo + (uint32_t)(((uint64_t)hi - lo + 1) >> 1);
-        const int c = block_count(row, V, vec_ok, sh, [&](uint32_t key, int) { return key >= mid; });
+        const int c = block_count<T, NT>(row, V, vec_ok, sh, [&](uint32_t key, int) { return key >= mid; });
         if (c >= k) lo = mid; else hi = mid - 1;
       }
       const uint32_t kth = lo;
-      const int above = block_count(row, V, vec_ok, sh, [&](uint32_t key, int) { return key > kth; });
+      const int above = block_count<T, NT>(row, V, vec_ok, sh, [&](uint32_t key, int) { return key > kth; });
       const int need = k - above;  // >= 1 ties at kth to take, smallest indices first
       int jl = 0, jh = V - 1;      // smallest J with count(key == kth && idx <= J) >= need
       while (jl < jh) {
         const int mid = jl + ((jh - jl) >> 1);
-        const int c = block_count(row, V, vec_ok, sh, [&](uint32_t key, int idx) { return key == kth && idx <= mid; });
+        const int c = block_count<T, NT>(row, V, vec_ok, sh, [&](uint32_t key, int idx) { return key == kth && idx <= mid; });
         if (c >= need) jh = mid; else jl = mid + 1;
       }
       const int jmax = jl;
       __syncthreads();
       if (tid == 0) sh.count = 0;
       __syncthreads();
-      for_each_elem(row, V, vec_ok, [&](float x, int idx) {
+      for_each_elem<T, NT>(row, V, vec_ok, [&](float x, int idx) {
         const uint32_t key = order_key(x);
         if (key > kth || (key == kth && idx <= jmax)) {
           const int slot = atomicAdd(&sh.count, 1);
@@ -394,16 +394,16 @@ __global__ void __launch_bounds__(kTopkThreads) kd_topk_kernel(const T* __restri
       out_v[r * k + j] = __float2half_rn(lp_r);
       out_i[r * k + j] = idx;
     };
-    if (count <= kTopkThreads) {  // typical: one candidate per thread, sorted in registers
+    if (count <= NT) {  // typical: one candidate per thread, sorted in registers
       const uint64_t mine = tid < count ? sh.cand[tid] : 0ull;  // pads sort last
-      const uint64_t sorted = block_sort_desc<uint64_t>(mine, sh.xch);
+      const uint64_t sorted = block_sort_desc<uint64_t, NT>(mine, sh.xch);
       if (tid < k) emit(sorted, tid);
     } else {
       int n = 32;
       while (n < count) n <<= 1;
-      for (int i = count + tid; i < n; i += kTopkThreads) sh.cand[i] = 0ull;
+      for (int i = count + tid; i < n; i += NT) sh.cand[i] = 0ull;
       bitonic_desc_u64(sh.cand, n);
-      for (int j = tid; j < k; j += kTopkThreads) emit(sh.cand[j], j);
+      for (int j = tid; j < k; j += NT) emit(sh.cand[j], j);
     }
     __syncthreads();
   }
@@ -419,8 +419,8 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
     set_error("kd_topk_logprobs: null pointer argument");
     return 1;
   }
-  if (R < 0 || V <= 0 || k <= 0 || k > V || k > kTopkThreads) {
-    set_error("kd_topk_logprobs: need 1 <= k <= min(V, %d); got k=%d V=%d R=%lld", kTopkThreads, k, V, (long long)R);
+  if (R < 0 || V <= 0 || k <= 0 || k > V || k > kTopkMaxThreads) {
+    set_error("kd_topk_logprobs: need 1 <= k <= min(V, %d); got k=%d V=%d R=%lld", kTopkMaxThreads, k, V, (long long)R);
     return 1;
   }
   if (R == 0) return 0;
@@ -428,12 +428,20 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * es) % 16 == 0) ? 1 : 0;
   // persistent: a few CTAs per SM loop over the rows, so that the rows in flight (306 KB each for bf16 at
   // V = 152,936) stay L2-resident between the two passes; KD_TOPK_CTAS_PER_SM overrides the default of 4
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    const char* e = getenv("KD_TOPK_CTAS_PER_SM");
-    per_sm = e ? atoi(e) : 4;
-    if (per_sm < 1 || per_sm > 64) per_sm = 4;
+  // Threads per row: the fewest that still give 2k thread maxima to take the threshold from.  Fewer threads per
+  // CTA = more CTAs (rows) per SM (64 registers per thread): while some rows sit in their sorts, enough others
+  // stream - with 512-thread CTAs only two rows fit an SM and the HBM idles during their sort phases (0.41 of the
+  // peak); KD_TOPK_THREADS / KD_TOPK_CTAS_PER_SM override.
+  static int nt_env = -1, per_sm_env = -1;
+  if (nt_env < 0) {
+    const char* e = getenv("KD_TOPK_THREADS");
+    nt_env = e ? atoi(e) : 0;
+    const char* c = getenv("KD_TOPK_CTAS_PER_SM");
+    per_sm_env = c ? atoi(c) : 0;
   }
+  int nt = k <= 128 ? 256 : 512;  // measured at k = 64: 256 x 4 CTAs/SM 780 us, 128 x 8 958 us, 512 x 2 943 us
+  if ((nt_env == 128 || nt_env == 256 || nt_env == 512) && nt_env >= nt) nt = nt_env;
+  int per_sm = per_sm_env > 0 ? per_sm_env : (nt == 128 ? 8 : (nt == 256 ? 5 : 2));  // what the register file holds
   int sms = 148;
   {
     int dev = 0;
@@ -442,19 +450,27 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   }
   const int grid = (int)(R < (int64_t)sms * per_sm ? R : (int64_t)sms * per_sm);
   cudaStream_t s = (cudaStream_t)stream;
+#define KD_TOPK_LAUNCH(TYPE, NT)                                                                                   \
+  kd_topk_kernel<TYPE, NT><<<grid, NT, 0, s>>>((const TYPE*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok)
+#define KD_TOPK_DISPATCH(TYPE)          \
+  do {                                  \
+    if (nt == 128) {                    \
+      KD_TOPK_LAUNCH(TYPE, 128);        \
+    } else if (nt == 256) {             \
+      KD_TOPK_LAUNCH(TYPE, 256);        \
+    } else {                            \
+      KD_TOPK_LAUNCH(TYPE, 512);        \
+    }                                   \
+  } while (0)
   switch (dtype) {
-    case KD_DTYPE_F32:
-      kd_topk_kernel<float><<<grid, kTopkThreads, 0, s>>>((const float*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok);
-      break;
-    case KD_DTYPE_BF16:
-      kd_topk_kernel<__nv_bfloat16><<<grid, kTopkThreads, 0, s>>>((const __nv_bfloat16*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok);
-      break;
-    case KD_DTYPE_F16:
-      kd_topk_kernel<__half><<<grid, kTopkThreads, 0, s>>>((const __half*)logits, R, V, row_stride, k, (__half*)out_v, out_i, vec_ok);
-      break;
+    case KD_DTYPE_F32: KD_TOPK_DISPATCH(float); break;
+    case KD_DTYPE_BF16: KD_TOPK_DISPATCH(__nv_bfloat16); break;
+    case KD_DTYPE_F16: KD_TOPK_DISPATCH(__half); break;
     default:
       set_error("kd_topk_logprobs: unsupported dtype code %d", dtype);
       return 1;
   }
+#undef KD_TOPK_DISPATCH
+#undef KD_TOPK_LAUNCH
   return check_cuda(cudaGetLastError(), "kd_topk launch");
 }
