@@ -390,7 +390,7 @@ struct RowShared {
 };
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
-__global__ void __launch_bounds__(kRowThreads, 1) kd_stream_row_kernel(const StreamParams p, int* __restrict__ row_counter) {
+__global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_stream_row_kernel(const StreamParams p, int* __restrict__ row_counter) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ RowShared sh;
   float* sp_p = reinterpret_cast<float*>(dyn_smem);  // sparse teacher only: p_k and i_k of the current row
@@ -1069,13 +1069,13 @@ static int stream_row_threads() {
   if (v == 0) {
     const char* e = getenv("KD_STREAM_THREADS");
     v = e ? atoi(e) : 512;  // measured: 512 (126 registers, no spills) > 768 > 1024 (64 registers, spills)
-    if (v != 1024 && v != 768) v = 512;
+    if (v != 1024 && v != 768 && v != 256) v = 512;
   }
   return v;
 }
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
-static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream);
+static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream, int ctas_per_sm = 1);
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
 static int launch_stream_rows(const StreamParams& p0, cudaStream_t stream) {
@@ -1084,22 +1084,33 @@ static int launch_stream_rows(const StreamParams& p0, cudaStream_t stream) {
     const int t = stream_row_threads();
     if (t == 1024) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 1024>(p0, stream);
     if (t == 768) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 768>(p0, stream);
+    if (t == 256) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 256>(p0, stream);
   }
   // dense: 512 threads x 126 registers hold two row pieces of z and y in flight per thread without spilling;
   // the top-k form has no teacher stream and is faster with 1024 x 64 (measured: 726 vs 862 us at configs[1] shape)
+  // forward only (no second sweep, nothing to keep in L2): two 256-thread CTAs per SM overlap one row's block
+  // reduction with the other's streaming (measured 551 vs 604 us at the configs[1] shape)
+  if (DENSE && !GRAD) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 256>(p0, stream, 2);
   if (DENSE) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 512>(p0, stream);
   return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 1024>(p0, stream);
 }
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
-static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream) {
+static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream, int ctas_per_sm) {
   StreamParams p = p0;
   auto kern = kd_stream_row_kernel<TZ, TY, DENSE, TAU2, GRAD, kRowThreads>;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_rows = p.B * p.T;
-  int grid = sms < n_rows ? sms : n_rows;  // one CTA per SM: ~148 rows in flight keep z + y of a row in L2
+  static int per_sm_env = -1;
+  if (per_sm_env < 0) {
+    const char* e = getenv("KD_STREAM_CTAS_PER_SM");
+    per_sm_env = e ? atoi(e) : 0;
+    if (per_sm_env < 0 || per_sm_env > 4) per_sm_env = 0;
+  }
+  const int per_sm = per_sm_env > 0 ? per_sm_env : ctas_per_sm;
+  int grid = sms * per_sm < n_rows ? sms * per_sm : n_rows;  // ~148 rows in flight keep z + y of a row in L2
   if (grid > kMaxClusters) grid = kMaxClusters;
   // the row counter sits behind the reduced record in the workspace
   int* counter = reinterpret_cast<int*>(p.partials + (size_t)(kMaxClusters + 1) * kNumPartialSlots);
