@@ -2,8 +2,6 @@
 trainer runs, transformers ``loss_utils.ForCausalLMLoss``)."""
 from __future__ import annotations
 
-import torch
-
 from . import _lib
 from ._lib import check, dtype_code, require_cuda, stream_ptr
 from .loss import fused_linear_kd_loss

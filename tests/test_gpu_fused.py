@@ -394,3 +394,52 @@ def test_fused_compacted_no_valid_row():
     out[0].backward()
     assert [float(o) for o in out] == [0.0, 0.0, 0.0, 0.0]
     assert float(hc.grad.abs().max()) == 0.0 and float(Wc.grad.abs().max()) == 0.0
+
+
+def test_fused_step_in_a_cuda_graph():
+    """The whole K1 step (forward + three-stream backward, work-unit counters, internal events) is capturable:
+    after a warm-up that creates the library's streams / counters, a CUDA graph of the step replays to the same
+    losses and gradients on new input values."""
+    import speech_distill_b200 as KD
+
+    B, T, H, V = 2, 128, 256, 5000
+    h, W, y, labels = _case(611, B, T, H, V)
+    hs = h.cuda().requires_grad_(True)
+    Ws = W.cuda().requires_grad_(True)
+    ys, ls = y.cuda(), labels.cuda()
+
+    def step():
+        hs.grad = None
+        Ws.grad = None
+        out = KD.fused_linear_kd_loss(hs, Ws, ls, teacher_logits=ys, v_chunk=1024)
+        out[0].backward()
+        return torch.stack([o.detach() for o in out])
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    ref_losses, ref_gh, ref_gw = step().clone(), hs.grad.clone(), Ws.grad.clone()
+
+    graph = torch.cuda.CUDAGraph()
+    hs.grad = None
+    Ws.grad = None
+    with torch.cuda.graph(graph):
+        out_static = step()
+    gh_static, gw_static = hs.grad, Ws.grad
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_static, ref_losses) and torch.equal(gh_static, ref_gh) and torch.equal(gw_static, ref_gw)
+
+    # new values in the static buffers, same graph
+    h2, _, y2, _ = _case(612, B, T, H, V)
+    with torch.no_grad():
+        hs.copy_(h2.cuda())
+        ys.copy_(y2.cuda())
+    graph.replay()
+    torch.cuda.synchronize()
+    got = out_static.clone()
+    want = KD.fused_linear_kd_loss(hs.detach(), Ws.detach(), ls, teacher_logits=ys, v_chunk=1024)
+    assert torch.equal(got, torch.stack(list(want)))
