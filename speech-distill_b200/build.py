@@ -15,7 +15,7 @@ SOURCES = ["kd_api.cu", "kd_stream.cu", "kd_topk.cu", "kd_rows.cu", "kd_fused.cu
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--split-compile", "0",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-Xcompiler", "-fPIC,-O3",
     "-Xptxas", "-v",
