@@ -293,6 +293,24 @@ def run_ours(args):
     e2e_ms = f0.elapsed_time(f1) / e2e_steps
     e2e_losses = out_host.tolist()
 
+    # ---- library GEMM of the same shape, for context: cuBLAS bf16 [B*T, H] x [H, V] -> bf16 logits ----
+    cublas_tf = None
+    if rank == 0:
+        try:
+            logits_buf = torch.empty(B * T, V, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                torch.matmul(h2, Wd.t(), out=logits_buf)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                torch.matmul(h2, Wd.t(), out=logits_buf)
+            c1.record()
+            torch.cuda.synchronize()
+            cublas_tf = 2.0 * B * T * H * V / (c0.elapsed_time(c1) / 10 * 1e-3) / 1e12
+            del logits_buf
+        except Exception:  # context only
+            cublas_tf = None
+
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e_ms, fwd_t, bwd_t], device=dev, dtype=torch.float64)
     if world > 1:
@@ -329,6 +347,8 @@ def run_ours(args):
                 "peak_source": f"{src} bf16_tflops_sustained: the launch is timed by CUDA events inside a loop of "
                                f"back-to-back forward+backward steps (power-capped regime), not alone",
                 "frac_of_burst_peak": achieved / burst, "burst_peak": burst,
+                "cublas_same_shape_tflops": cublas_tf,
+                "frac_of_cublas_same_shape": (achieved / cublas_tf) if cublas_tf else None,
                 "traffic": traffic, "flops_per_launch": flops_fwd, "ms_per_launch": fwd_t,
                 "note": "launch duration = CUDA events around the kd_fused_linear_fwd C call, no host sync in the loop "
                         "(tcgen05 GEMM kernel + the row-merge and reduce kernels, ~25 us)",

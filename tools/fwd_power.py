@@ -56,6 +56,9 @@ mode = os.environ.get("KD_DEBUG_SKIP_MATH", "0")
 run(f"fwd dense teacher (skip_math={mode})", lambda: KL._fused_forward(h, W, y, row_target, 2.0, 0.5, 0), fl)
 run(f"fwd no teacher    (skip_math={mode})", lambda: KL._fused_forward(h, W, None, row_target, 1.0, 1.0, 0), fl)
 run("cuBLAS bf16 8192^3", lambda: torch.matmul(A8, B8), 2.0 * 8192 ** 3, n=100)
+logits = torch.empty(B * T, V, device=dev, dtype=torch.bfloat16)
+run("cuBLAS bf16 lm_head shape (logits out)", lambda: torch.matmul(h, W.t(), out=logits), fl)
+run("kd_linear_bf16 lm_head shape", lambda: K.linear_bf16(h, W, logits), fl)
 C = torch.empty(8192, 8192, device=dev, dtype=torch.float32)
 lib = K.load_library()
 st = torch.cuda.current_stream().cuda_stream
