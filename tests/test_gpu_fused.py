@@ -443,3 +443,31 @@ def test_fused_step_in_a_cuda_graph():
     got = out_static.clone()
     want = KD.fused_linear_kd_loss(hs.detach(), Ws.detach(), ls, teacher_logits=ys, v_chunk=1024)
     assert torch.equal(got, torch.stack(list(want)))
+
+
+@pytest.mark.parametrize("B,T,H,V", [(2, 50, 136, 777), (1, 300, 72, 2049), (3, 33, 1032, 333)])
+def test_fused_ragged_hidden_rows_and_vocab(B, T, H, V):
+    """Hidden sizes that are multiples of 8 but not of the 64-wide k-block, row counts off the 256-row tile and
+    vocabularies off the 256-column tile: every ragged edge at once (TMA zero fill + masked epilogue columns)."""
+    h, W, y, labels = _case(700 + H, B, T, H, V)
+    ref, gh_ref, gw_ref = O.fused_linear_reference(h.double(), W.double(), labels, teacher_logits=y.double())
+    losses, gh, gw = _run_fused(h, W, y, labels, 2.0, 0.5)
+    for got, want in zip(losses, [float(x) for x in ref]):
+        assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
+    assert rel_err(gh.float().cpu().numpy(), gh_ref.numpy()) < 6e-3
+    assert rel_err(gw.float().cpu().numpy(), gw_ref.numpy()) < 6e-3
+
+
+@pytest.mark.parametrize("K", [1, 1024])
+def test_fused_sparse_extreme_k(K):
+    """Top-k width 1 and the maximum (1024 entries per row, more than a 256-column tile can hold distinct)."""
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(801 + K, 2, 64, 128, 3000)
+    tv, ti = _topk_cache(y, K)
+    ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
+    out = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
+    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-3, atol=1e-6)
+    with pytest.raises(KD.KdError):
+        KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=torch.zeros(2, 64, 1025).cuda(),
+                                teacher_top_k_i=torch.zeros(2, 64, 1025, dtype=torch.int32).cuda())
