@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkd_b200.so")
+# KD_B200_LIB selects another build of the same library (A/B experiments); default: the in-tree one
+LIB_PATH = os.environ.get("KD_B200_LIB") or os.path.join(_HERE, "libkd_b200.so")
 
 KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
 KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
