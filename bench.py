@@ -321,7 +321,7 @@ def run_ours(args):
         burst, sustained, hbm, src = peaks()
         tokens = B * T * world
         flops_fwd = 2.0 * B * T * H * V
-        chunks = -(-V // 9472)
+        chunks = -(-V // 18944)  # kDefaultVChunk
         launches_per_step = 2 + 3 + 3 * chunks  # prepare_rows + finalize, fwd (gemm, merge, reduce), bwd 3 GEMMs / chunk
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")

@@ -1440,11 +1440,21 @@ static inline int b_box_rows() { return BN / cta_group(); }  // rows of a K-majo
 
 // ---- workspace layout -----------------------------------------------------------------------------
 constexpr int kFwdTilesPerRange = 4;
-constexpr int kDefaultVChunk = 9472;  // 37 x 256: dW chunk GEMM = 74 x 4 tiles = 2 full waves of 148 SMs
+// 74 x 256 columns: per chunk the gradient GEMM has 16 x 74 tiles (16 per CTA pair) and dW 74 x 4 (4 per pair) -
+// whole waves of the 74 pairs - and the backward is 27 launches instead of 51.  Round-robin A/B at configs[1] size
+// (tools/vchunk_ab.py): 4.52 ms/step vs 5.10 with 9472 in the power-capped regime, 4.65 vs 4.83 in bench.py.
+constexpr int kDefaultVChunk = 18944;
 constexpr int kMergeBlocksMax = 1024;
 
 static int norm_v_chunk(int v_chunk, int V) {
-  if (v_chunk <= 0) v_chunk = kDefaultVChunk;
+  if (v_chunk <= 0) {
+    static int env_chunk = -1;  // KD_V_CHUNK overrides the library default (experiments)
+    if (env_chunk < 0) {
+      const char* e = getenv("KD_V_CHUNK");
+      env_chunk = e ? atoi(e) : 0;
+    }
+    v_chunk = env_chunk > 0 ? env_chunk : kDefaultVChunk;
+  }
   v_chunk = cdiv(v_chunk, BN) * BN;
   const int vmax = cdiv(V, BN) * BN;
   return v_chunk < vmax ? v_chunk : vmax;

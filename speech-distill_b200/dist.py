@@ -63,7 +63,7 @@ def allreduce_grad_(grad, group=None, bucket_rows=0):
     return grad
 
 
-DEFAULT_V_CHUNK = 9472  # kDefaultVChunk of csrc/kd_fused.cu
+DEFAULT_V_CHUNK = 18944  # kDefaultVChunk of csrc/kd_fused.cu
 
 
 def plan_ranges(V, row_begin, v_chunk, n_ranges):

@@ -76,7 +76,7 @@ def test_plan_ranges_properties():
     for V, row_begin, vc, n in [(152936, 0, 0, 6), (152936, 151936, 0, 6), (5000, 0, 1024, 3), (300, 0, 0, 6),
                                 (20000, 9000, 4096, 8), (152936, 0, 37888, 4)]:
         r = plan_ranges(V, row_begin, vc, n)
-        chunk = -(-(vc if vc > 0 else 9472) // 256) * 256
+        chunk = -(-(vc if vc > 0 else 18944) // 256) * 256
         assert r[0][0] == 0 and r[-1][1] == V and 1 <= len(r) <= n
         assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert all(v0 % chunk == 0 and v1 > v0 for v0, v1 in r)
