@@ -1439,7 +1439,7 @@ static inline int tile_m() { return BM * cta_group(); }     // rows of C per wor
 static inline int b_box_rows() { return BN / cta_group(); }  // rows of a K-major B box (per CTA)
 
 // ---- workspace layout -----------------------------------------------------------------------------
-constexpr int kFwdTilesPerRange = 4;
+constexpr int kFwdTilesPerRange = 8;  // A/B in bench.py: 8 is 1 % faster than 4 (fewer partial records), 2 is 2.5 % slower
 // 74 x 256 columns: per chunk the gradient GEMM has 16 x 74 tiles (16 per CTA pair) and dW 74 x 4 (4 per pair) -
 // whole waves of the 74 pairs - and the backward is 27 launches instead of 51.  Round-robin A/B at configs[1] size
 // (tools/vchunk_ab.py): 4.52 ms/step vs 5.10 with 9472 in the power-capped regime, 4.65 vs 4.83 in bench.py.
