@@ -918,9 +918,8 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == 3) {
     // ================= teacher-tile producer (y ring, local to each CTA) =================
     if (kYSlots > 0 && lane == 0) {
-      // streamed once per pass: evict-first, so the 1.25 GB of teacher logits do not push the gradient chunk
-      // (written by this kernel family, read back by dW / dH) and the lm_head tiles out of L2
-      const uint64_t y_policy = l2_policy_evict_first();
+      // (an L2 evict-first policy on these loads was tried: same time, but 0.32 GB MORE DRAM reads per forward
+      //  launch - 1.98 vs 1.66 GB in ncu - so the teacher tiles use the default policy)
       int slot = 0;
       uint32_t phase = 0;
       for (int u = uq.template next<CG>(g, n_rows_live); u >= 0; u = uq.template next<CG>(g, n_rows_live)) {
@@ -934,8 +933,8 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_expect_tx(fb, kStepBytes);
 #pragma unroll
             for (int b = 0; b < kStepBoxes; ++b)
-              tma_load_2d_hint(sY + slot * kStepBytes + b * kBoxBytes, &tma_y,
-                               g.b_n0 + n_blk * BN + c * kStepCols + 64 * b, m_row, fb, y_policy);
+              tma_load_2d(sY + slot * kStepBytes + b * kBoxBytes, &tma_y,
+                          g.b_n0 + n_blk * BN + c * kStepCols + 64 * b, m_row, fb);
             if (++slot == kYSlots) {
               slot = 0;
               phase ^= 1u;
