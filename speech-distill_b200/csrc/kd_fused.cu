@@ -4,11 +4,13 @@
 // followed by DistillationLoss.forward (distillation_loss.py:14-128) and their autograd, without
 // ever materialising the [rows, V] logits.
 //
-// One persistent, warp-specialised kernel template serves every GEMM on the path:
-//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 4-stage smem ring, SWIZZLE_128B)
-//   warp 1      : MMA issuer    (one thread, tcgen05.mma kind::f16, 128 x 256 x 16, fp32 in TMEM)
-//   warp 2      : TMEM allocator (2 accumulator buffers x 256 columns = all 512 columns)
-//   warps 4..11 : epilogue      (tcgen05.ld 32x32b: one thread per accumulator row)
+// One persistent, warp-specialised kernel template serves every GEMM on the path (CTA pairs by default:
+// tcgen05 cta_group::2, 256 x 256 tiles, see kd_umma_kernel):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 3..8-stage smem ring, SWIZZLE_128B)
+//   warp 1      : MMA issuer    (one thread, tcgen05.mma kind::f16, 256 x 256 x 16 per pair, fp32 in TMEM)
+//   warp 2      : TMEM allocator (2 accumulator buffers x 256 columns = all 512 columns) + work-unit scheduler
+//   warp 3      : TMA producer of the teacher-tile ring
+//   warps 4..19 : epilogue      (tcgen05.ld 32x32b: one thread per accumulator row, 4 column groups)
 // and the epilogue is a policy:
 //   FwdEpi  : online soft-max statistics of the student tile + streamed teacher tile (forward)
 //   GradEpi : recomputed tile -> gradient tile G (bf16) into a V-independent scratch (backward)
