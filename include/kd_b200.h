@@ -146,6 +146,8 @@ int kd_zero_if_empty(void* dst, int64_t bytes, const int32_t* n_rows, void* stre
  *                        d[(w_ce * sum CE + w_kl * tau^2 * sum KL) / N]; the usual call passes
  *                        (alpha * g, (1 - alpha) * g) with g the upstream grad of the total loss
  *                        (distillation_loss.py:126); n_norm as above.
+ * Inside the backward the gradient tile travels through the tensor cores as power-of-two-scaled fp16 against fp16
+ * copies of h and of the chunk's W rows (fp32 accumulation; KD_G_FP16=0 in the environment selects bf16 operands).
  * v_chunk: vocabulary columns per backward chunk (0 = library default); the gradient scratch is
  * 2 x R x v_chunk bf16 (double buffered), independent of V.  workspace sized by
  * kd_fused_workspace_bytes() (K = top-k width of a sparse teacher, else 0), 256-byte aligned.

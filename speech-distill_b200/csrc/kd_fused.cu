@@ -48,6 +48,9 @@ constexpr int kStepBoxes = kStepCols / 64;       // 64-column (128-byte row) TMA
 constexpr uint32_t kBoxBytes = BM * 64 * 2;      // 16 KB: [128 rows x 64 cols] of a 16-bit type, swizzled 128 B rows
 constexpr uint32_t kStepBytes = kStepBoxes * kBoxBytes;  // 32 KB
 constexpr int kSchedSlots = 2;  // work-unit queue depth per CTA (pair): the next unit is fetched while one runs
+#ifndef KD_G_FP16_DEFAULT
+#define KD_G_FP16_DEFAULT 1
+#endif
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
 // per-row record one vocabulary slice hands to the cross-rank merge (vocab-parallel mode):
 // m, s1, st, mt | t1, tt, a, z_label | y_label, sum p log p, hit value sum, hits
@@ -84,6 +87,7 @@ struct Geom {
   // rows_dim = 2: the K dimension is rows (dW = G^T h) -> only the first ceil(*n_rows / 64) k-blocks are run.
   const int32_t* n_rows;
   int rows_dim;
+  int ab_fp16;  // operands A and B are fp16 (dW / dH GEMMs with the fp16 gradient operand), else bf16
 };
 
 __host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, int& range, int& n_begin, int& n_end) {
@@ -206,6 +210,18 @@ struct SparseView {
   const uint16_t* off;  // [R][off_stride]
   int K, off_stride;
 };
+
+// fp16 gradient operand (KD_G_FP16): G is scaled by a power of two S so that its entries sit in fp16's normal
+// range (|G| <= ~coef / N: 2.4e-4 at N = 4096 would be fine, a probability of 1e-5 / N would not), rounded to fp16
+// (11 significand bits instead of bf16's 8) and multiplied with fp16 copies of h and W (exact for bf16 values inside
+// fp16's exponent range); the dW / dH epilogues multiply by 1 / S.  S = 2^(12 + ceil(log2 N) - ceil(log2 max|coef|)):
+// the largest entry is <= 2^13, the smallest normal one corresponds to a probability of ~1.5e-8.
+__device__ __forceinline__ float g_operand_scale(const int32_t* n_norm, const float* coef, float tau) {
+  const int nn = *n_norm;
+  const float cmax = fmaxf(fmaxf(fabsf(coef[0]), fabsf(coef[1]) * tau), 1e-30f);
+  const float e = 12.f + ceilf(log2f((float)(nn > 0 ? nn : 1))) - ceilf(log2f(cmax));
+  return exp2f(fminf(fmaxf(e, -100.f), 100.f));
+}
 
 // label of a row in this call's column space: row_target - label_off when it falls inside [0, V), a far-away
 // sentinel when another vocabulary slice owns it (vocab-parallel); `valid` is the row predicate itself
@@ -364,6 +380,7 @@ struct GradParams {
   const float* coef;  // device float[2]: weight of d(sum CE) and of tau^2 d(sum KL) in the returned gradient
   int v0;             // first vocabulary column of this chunk; scratch column j <-> vocabulary index v0 + j
   int label_off;      // vocab-parallel: column v of this call is vocabulary index label_off + v
+  int g_fp16;         // write G as fp16 scaled by g_operand_scale() instead of bf16
   SparseView sp;      // sparse teacher, see FwdParams
 };
 
@@ -387,7 +404,8 @@ struct GradEpi {
   __device__ GradEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {
     if (COPY) return;
     const int nn = *p.n_norm;
-    const float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
+    float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
+    if (p.g_fp16) inv_n *= g_operand_scale(p.n_norm, p.coef, p.tau);  // power of two: exact
     c1 = p.coef[0] * inv_n;
     c2 = p.use_kl ? p.coef[1] * p.tau * inv_n : 0.f;
     c_tau = kLog2e / p.tau;
@@ -454,6 +472,18 @@ struct GradEpi {
         if (j == (int)d) gq[j] -= c1;
     }
     float t8[8];
+    if (!COPY && p.g_fp16) {
+      Vec8<__half> v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t8[j] = gq[j];
+      v.pack(t8);
+      lo = v.a;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t8[j] = gq[8 + j];
+      v.pack(t8);
+      hi = v.a;
+      return;
+    }
     Vec8<__nv_bfloat16> v;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t8[j] = gq[j];
@@ -548,6 +578,10 @@ struct StoreParams {
   __nv_bfloat16* c16;      // bf16 output, row stride ld16
   int64_t ld16;
   int64_t row0_32, row0_16;  // row offsets of tile row 0 inside c32 / c16
+  // fp16 gradient operand: the accumulator holds S x the result; non-null pointers = multiply by 1 / S
+  const int32_t* scale_n_norm;
+  const float* scale_coef;
+  float scale_tau;
 };
 
 struct StoreEpi {
@@ -558,13 +592,16 @@ struct StoreEpi {
   EpiThread t;
   int row;
 
-  __device__ StoreEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
+  float out_scale;
+  __device__ StoreEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {
+    out_scale = p.scale_n_norm != nullptr ? 1.0f / g_operand_scale(p.scale_n_norm, p.scale_coef, p.scale_tau) : 1.0f;
+  }
   __device__ void begin_unit(const Geom&, int m0, int) { row = m0 + t.row_in_tile; }
 
   __device__ __forceinline__ void store16(const uint32_t (&raw)[16], int col0, int ncols) {
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * out_scale;
     if (p.mode == kAccumF32 || p.mode == kFinalBf16) {
       const float* acc = p.c32 + (p.row0_32 + row) * p.ld32 + col0;
       if (ncols >= 16 && (p.ld32 & 3) == 0) {
@@ -844,7 +881,8 @@ kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA of the pair only) =================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = instr_desc_bf16(BM * CG, BN, A_MN, B_MN);
+      // A / B format field: 1 = bf16, 0 = fp16 (bits 7..9 and 10..12 of the kind::f16 instruction descriptor)
+      const uint32_t idesc = instr_desc_bf16(BM * CG, BN, A_MN, B_MN) & (g.ab_fp16 ? ~((1u << 7) | (1u << 10)) : ~0u);
       constexpr uint64_t a_base = A_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
       constexpr uint64_t b_base = B_MN ? smem_desc_base(kBoxMnBytes, 1024) : smem_desc_base(16, 1024);
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 elements
@@ -1442,6 +1480,48 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int tile_m() { return BM * cta_group(); }     // rows of C per work tile
 static inline int b_box_rows() { return BN / cta_group(); }  // rows of a K-major B box (per CTA)
 
+// ---- fp16 gradient operand: switch and operand copies -----------------------------------------------
+// KD_G_FP16=0 keeps the bf16 gradient operand (and the bf16 h / W operands) for dW and dH
+static bool g_fp16_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_G_FP16");
+    v = e ? (e[0] != '0' ? 1 : 0) : KD_G_FP16_DEFAULT;
+  }
+  return v != 0;
+}
+
+// dst[r, :] (fp16, contiguous rows of `cols`) = src[r, :] (bf16, row stride src_stride); cols % 8 == 0.
+// bf16 -> fp16 is exact inside fp16's exponent range; smaller magnitudes round to fp16 subnormals / zero, larger
+// ones saturate to +-65504 (neither occurs for activations and weights of the models on this path).
+__global__ void __launch_bounds__(256) kd_cast_bf16_f16_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_stride,
+                                                              __half* __restrict__ dst, int rows, int cols) {
+  const int vec_per_row = cols >> 3;
+  const int64_t total = (int64_t)rows * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vec_per_row), c = (int)(i - (int64_t)r * vec_per_row) * 8;
+    Vec8<__nv_bfloat16> v;
+    v.load_global(src + (int64_t)r * src_stride + c);
+    float f[8];
+    v.unpack(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);
+    Vec8<__half> o;
+    o.pack(f);
+    *reinterpret_cast<uint4*>(dst + (int64_t)r * cols + c) = o.a;
+  }
+}
+
+static int cast_bf16_f16(const void* src, int64_t src_stride, void* dst, int rows, int cols, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  const int64_t total = (int64_t)rows * (cols >> 3);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  kd_cast_bf16_f16_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_stride,
+                                                 reinterpret_cast<__half*>(dst), rows, cols);
+  return check_cuda(cudaGetLastError(), "kd_cast_bf16_f16 launch");
+}
+
 // ---- workspace layout -----------------------------------------------------------------------------
 constexpr int kFwdTilesPerRange = 8;  // A/B in bench.py: 8 is 1 % faster than 4 (fewer partial records), 2 is 2.5 % slower
 // 74 x 256 columns: per chunk the gradient GEMM has 16 x 74 tiles (16 per CTA pair) and dW 74 x 4 (4 per pair) -
@@ -1470,6 +1550,8 @@ struct Workspace {
   size_t g_off, g_bytes;                // backward gradient chunks, 2 x bf16 [R][v_chunk] (double buffered)
   size_t g_buf_bytes;                   // one of the two
   size_t dh_off, dh_bytes;              // backward dH accumulator, fp32 [R][H]
+  size_t h16_off, h16_bytes;            // fp16 gradient operand: fp16 copy of h [R][H] ...
+  size_t w16_off, w16_buf_bytes;        // ... and of the current W chunk [v_chunk][H], double buffered
   // sparse teacher view, rebuilt by each call (after the forward region resp. the backward region)
   size_t sp_bytes, sp_idx_rel, sp_p_rel, sp_rowc_rel, sp_off_rel;  // offsets relative to the region start
   int sp_off_stride, sp_n_off;
@@ -1492,8 +1574,12 @@ static Workspace plan_workspace(int R, int H, int V, int v_chunk, int K) {
   w.g_bytes = 2 * w.g_buf_bytes;
   w.dh_off = w.g_off + w.g_bytes;
   w.dh_bytes = up((size_t)R * H * sizeof(float));
+  w.h16_off = w.dh_off + w.dh_bytes;
+  w.h16_bytes = g_fp16_enabled() ? up((size_t)R * H * 2) : 0;
+  w.w16_off = w.h16_off + w.h16_bytes;
+  w.w16_buf_bytes = g_fp16_enabled() ? up((size_t)vc * H * 2) : 0;
   w.fwd_bytes = w.bsums_off + w.bsums_bytes;
-  w.bwd_bytes = w.dh_off + w.dh_bytes;
+  w.bwd_bytes = w.w16_off + 2 * w.w16_buf_bytes;
   w.sp_bytes = 0;
   w.sp_idx_rel = w.sp_p_rel = w.sp_rowc_rel = w.sp_off_rel = 0;
   w.sp_n_off = cdiv(V, BN) + 1;
@@ -1897,6 +1983,13 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   }
   if (make_tmap(&t_h_mn, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, 64, "hidden (MN-major)")) return 1;
   if (make_tmap(&t_w_mn, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, 64, "lm_head weight (MN-major)")) return 1;
+  // fp16 gradient operand: dW and dH multiply the fp16 G with fp16 copies of h (once per call) and of the chunk's W rows
+  const bool g16 = g_fp16_enabled();
+  uint8_t* h16 = wsp + ws.h16_off;
+  if (g16) {
+    if (cast_bf16_f16(h, h_stride, h16, R, H, s)) return 1;
+    if (make_tmap(&t_h_mn, h16, (uint64_t)H, (uint64_t)R, (uint64_t)H, 64, "hidden fp16 (MN-major)")) return 1;
+  }
 
   SparseView sp_view = {};
   if (sparse && prepare_sparse(topk_v, topk_i, K, row_target, R, V, v_offset, tau, ws, wsp + ws.bwd_bytes, &sp_view, nullptr, s,
@@ -1925,6 +2018,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
         if (rec_h[b] && check_cuda(cudaStreamWaitEvent(s, pipe->eh[b], 0), "wait dH")) return 1;
         rec_w[b] = rec_h[b] = false;
       }
+      if (g16 && dH) {  // this chunk's W rows as fp16 (read by dH(c); the buffer's previous reader was dH(c - 2))
+        const uint8_t* wrow = reinterpret_cast<const uint8_t*>(W) + (size_t)v0 * (size_t)w_stride * 2;
+        if (cast_bf16_f16(wrow, w_stride, wsp + ws.w16_off + b * ws.w16_buf_bytes, cols, H, s)) return 1;
+      }
       Geom g = {};
       g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = n_blks;
@@ -1948,6 +2045,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       gp.coef = grad_coef;
       gp.v0 = v0;
       gp.label_off = v_offset;
+      gp.g_fp16 = g16 ? 1 : 0;
       gp.sp = sp_view;
       int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
@@ -1976,7 +2074,13 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       g.num_units = g.num_m_blk * g.num_n_blk;
       g.n_rows = n_rows;
       g.rows_dim = n_rows ? 2 : 0;  // K runs over rows: stop at the last live k-block
+      g.ab_fp16 = g16 ? 1 : 0;
       StoreParams sp = {};
+      if (g16) {
+        sp.scale_n_norm = n_norm;
+        sp.scale_coef = grad_coef;
+        sp.scale_tau = tau;
+      }
       sp.mode = out32 ? kStoreF32 : kStoreBf16;
       sp.m_total = cols;
       sp.n_total = H;
@@ -2008,6 +2112,18 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       g.n_rows = n_rows;
       g.rows_dim = n_rows ? 1 : 0;
       StoreParams sp = {};
+      CUtensorMap t_w16_mn;
+      if (g16) {
+        // the chunk's fp16 rows start at 0 in their own buffer; rows beyond `cols` are out of bounds = zero
+        g.b_k0 = 0;
+        g.ab_fp16 = 1;
+        if (make_tmap(&t_w16_mn, wsp + ws.w16_off + b * ws.w16_buf_bytes, (uint64_t)H, (uint64_t)cols, (uint64_t)H, 64,
+                      "lm_head weight chunk fp16 (MN-major)"))
+          return 1;
+        sp.scale_n_norm = n_norm;
+        sp.scale_coef = grad_coef;
+        sp.scale_tau = tau;
+      }
       const bool first = range_first && c == 0, last = range_last && c == n_chunks - 1;
       sp.m_total = R;
       sp.n_total = H;
@@ -2023,7 +2139,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
         sp.c16 = reinterpret_cast<__nv_bfloat16*>(dH);
         sp.ld16 = dh_stride;
       }
-      if (launch_umma<StoreEpi, false, true>(t_g_k[b], t_w_mn, g, sp, s_h)) return 1;
+      if (launch_umma<StoreEpi, false, true>(t_g_k[b], g16 ? t_w16_mn : t_w_mn, g, sp, s_h)) return 1;
       if (pipe) {
         if (check_cuda(cudaEventRecord(pipe->eh[b], s_h), "record dH")) return 1;
         rec_h[b] = any_h = true;

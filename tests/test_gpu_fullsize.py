@@ -43,7 +43,7 @@ def test_k1_dense_configs1_full_size_vs_oracle():
         assert abs(float(got) - float(want)) <= 1e-3 * max(1.0, abs(float(want)))  # north_star tolerance
         assert abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))  # what fp32 statistics deliver
     _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h, W, labels, teacher_logits=y, temperature=2.0, alpha=0.5)
-    assert rel_err(gh32, gh_ref) < 4e-3 and rel_err(gw32, gw_ref) < 4e-3    # bf16 G operand
+    assert rel_err(gh32, gh_ref) < 1e-3 and rel_err(gw32, gw_ref) < 1e-3    # north_star tolerance (fp32 accumulate)
     assert rel_err(hc.grad.float(), gh_ref) < 6e-3 and rel_err(Wc.grad.float(), gw_ref) < 6e-3
     cos = torch.nn.functional.cosine_similarity(Wc.grad.float().flatten(), gw_ref.flatten(), dim=0)
     assert float(cos) > 0.99999
@@ -55,13 +55,13 @@ def test_k1_dense_configs1_full_size_vs_oracle():
     assert torch.equal(h4.grad, hc.grad * 4) and torch.equal(W4.grad, Wc.grad * 4)
 
     # row independence: dH of the first 3 sequences computed alone (other tile schedule, other N) = same rows
-    # up to the 1/N factor; compare after rescaling by the valid-row counts.  The gradient tile is rounded to
-    # bf16 after the 1/N scaling, so the two runs round different numbers: equality holds to the bf16-G level
+    # up to the 1/N factor; compare after rescaling by the valid-row counts.  The gradient tile is rounded (to
+    # scaled fp16) after the 1/N scaling, so the two runs round different numbers: equal to that rounding level
     n_all = int((labels[:, 1:] != -100).sum())
     n_sub = int((labels[:3, 1:] != -100).sum())
     _, gh_sub, _ = K.fused_linear_kd_value_and_grad(h[:3].contiguous(), W, labels[:3].contiguous(),
                                                     teacher_logits=y[:3].contiguous(), temperature=2.0, alpha=0.5)
-    assert rel_err(gh_sub * (n_sub / n_all), gh32[:3]) < 6e-3
+    assert rel_err(gh_sub * (n_sub / n_all), gh32[:3]) < 1e-3
 
 
 def test_k1_sparse_configs2_full_size_vs_oracle():
@@ -77,7 +77,7 @@ def test_k1_sparse_configs2_full_size_vs_oracle():
                                                           teacher_top_k_v=tv, teacher_top_k_i=ti)
     for got, want in zip(losses, ref):
         assert abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))
-    assert rel_err(gh32, gh_ref) < 4e-3 and rel_err(gw32, gw_ref) < 4e-3
+    assert rel_err(gh32, gh_ref) < 1e-3 and rel_err(gw32, gw_ref) < 1e-3
 
 
 def test_stage1_configs3_full_size_masked_rows():

@@ -126,18 +126,18 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
                                                        temperature=tau, alpha=alpha)
     eh32 = rel_err(gh32.cpu().numpy(), gh_ref.numpy())
     ew32 = rel_err(gw32.cpu().numpy(), gw_ref.numpy())
-    # The gradient operand G = dlogits is bf16 (as the reference's own dlogits are; sm_100a has no mixed
-    # fp16 x bf16 MMA), so the floor against an fp64 oracle is the bf16 rounding of G (2^-9 per element,
-    # averaged down by the GEMM) plus, for bf16 outputs, 2^-9 on the largest entry.  Bars:
-    #  - fp32 accumulators strictly better than the reference's all-bf16 GPU pipeline and < 4e-3
+    # The gradient operand G = dlogits goes through the tensor cores as power-of-two-scaled fp16 (11 significand
+    # bits; the reference's own dlogits are bf16 with 8) against fp16 copies of h and W, so the fp32 accumulators
+    # meet north_star's 1e-3; bf16 outputs add their own rounding, 2^-9 on the largest entry.  Bars:
+    #  - fp32 accumulators < 1e-3 and better than the reference's all-bf16 GPU pipeline
     #  - bf16 outputs no worse than 1.25 x that pipeline (or 2.2e-3) and < 6e-3
     rh, rw = _torch_bf16_pipeline(h, W, y, labels, tau, alpha)
     eh_ref = rel_err(rh.float().cpu().numpy(), gh_ref.numpy())
     ew_ref = rel_err(rw.float().cpu().numpy(), gw_ref.numpy())
     print(f"dH err: bf16 {eh:.2e} fp32 {eh32:.2e} torch-bf16 {eh_ref:.2e} | dW err: bf16 {ew:.2e} fp32 {ew32:.2e} "
           f"torch-bf16 {ew_ref:.2e}")
-    assert eh32 < 4e-3 and ew32 < 4e-3, (eh32, ew32)
-    assert eh32 <= max(eh_ref, 1e-3) and ew32 <= max(ew_ref, 1e-3), (eh32, eh_ref, ew32, ew_ref)
+    assert eh32 < 1e-3 and ew32 < 1e-3, (eh32, ew32)  # north_star: gradients within 1e-3 (fp32 accumulate)
+    assert eh32 <= eh_ref and ew32 <= ew_ref, (eh32, eh_ref, ew32, ew_ref)
     assert eh < 6e-3 and ew < 6e-3, (eh, ew)
     assert eh <= max(1.25 * eh_ref, 2.2e-3) and ew <= max(1.25 * ew_ref, 2.2e-3), (eh, eh_ref, ew, ew_ref)
 
@@ -171,8 +171,8 @@ def test_stage1_fused_ce_masks_old_rows():
     _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), teacher_logits=None,
                                                      temperature=1.0, alpha=1.0, dw_row_begin=old, v_chunk=1024)
     assert float(gw32[:old].abs().max()) == 0.0
-    assert rel_err(gw32[old:].cpu().numpy(), gw_ref[old:].numpy()) < 4e-3
-    assert rel_err(gh32.cpu().numpy(), gh_ref.numpy()) < 4e-3
+    assert rel_err(gw32[old:].cpu().numpy(), gw_ref[old:].numpy()) < 1e-3
+    assert rel_err(gh32.cpu().numpy(), gh_ref.numpy()) < 1e-3
 
 
 def test_mask_rows_kernel():
@@ -230,7 +230,7 @@ def test_fused_sparse_matches_oracle(B, T, H, V, K, tau, alpha, dup):
     eh32, ew32 = rel_err(gh32.cpu().numpy(), gh_ref.numpy()), rel_err(gw32.cpu().numpy(), gw_ref.numpy())
     eh, ew = rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()), rel_err(Wc.grad.float().cpu().numpy(), gw_ref.numpy())
     print(f"sparse dH err: bf16 {eh:.2e} fp32 {eh32:.2e} | dW err: bf16 {ew:.2e} fp32 {ew32:.2e}")
-    assert eh32 < 4e-3 and ew32 < 4e-3, (eh32, ew32)  # same bars as the dense form (bf16 G operand)
+    assert eh32 < 1e-3 and ew32 < 1e-3, (eh32, ew32)  # same bars as the dense form
     assert eh < 6e-3 and ew < 6e-3, (eh, ew)
 
 

@@ -80,11 +80,11 @@ def test_vocab_parallel_slices_equal_unsharded(G, V, sparse):
     dW = torch.cat(dw_parts, 0)
     assert dW.shape == (V, H) and dW.dtype == torch.bfloat16
     eh, ew = rel_err(dH.cpu().numpy(), gh_ref.numpy()), rel_err(dW.float().cpu().numpy(), gw_ref.numpy())
-    assert eh < 4e-3 and ew < 6e-3, (eh, ew)
+    assert eh < 1e-3 and ew < 6e-3, (eh, ew)  # dH: fp32 partial sums; dW slices: bf16 outputs
 
     # against the unsharded kernels: same losses to fp32 merge-order noise, same gradients to bf16-G noise
     out1 = KD.fused_linear_kd_loss(hc, Wc, lc, teacher_logits=None if sparse else yc, temperature=tau, alpha=alpha, **kw)
     np.testing.assert_allclose(losses, [float(o) for o in out1], rtol=2e-6, atol=1e-7)
     _, gh1, gw1 = KD.fused_linear_kd_value_and_grad(hc, Wc, lc, teacher_logits=None if sparse else yc,
                                                     temperature=tau, alpha=alpha, **kw)
-    assert rel_err(dH.cpu().numpy(), gh1.cpu().numpy()) < 2e-3
+    assert rel_err(dH.cpu().numpy(), gh1.cpu().numpy()) < 1e-3
