@@ -322,7 +322,9 @@ def run_ours(args):
         tokens = B * T * world
         flops_fwd = 2.0 * B * T * H * V
         chunks = -(-V // 18944)  # kDefaultVChunk
-        launches_per_step = 2 + 3 + 3 * chunks  # prepare_rows + finalize, fwd (gemm, merge, reduce), bwd 3 GEMMs / chunk
+        # prepare_rows + finalize, fwd (gemm, merge, reduce), bwd 3 GEMMs / chunk, fp16 operand copies (h once, W per chunk)
+        g16 = os.environ.get("KD_G_FP16", "1") != "0"
+        launches_per_step = 2 + 3 + 3 * chunks + ((1 + chunks) if g16 else 0)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
