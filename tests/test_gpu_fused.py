@@ -471,3 +471,24 @@ def test_fused_sparse_extreme_k(K):
     with pytest.raises(KD.KdError):
         KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=torch.zeros(2, 64, 1025).cuda(),
                                 teacher_top_k_i=torch.zeros(2, 64, 1025, dtype=torch.int32).cuda())
+
+
+@pytest.mark.parametrize("log2_scale", [-14, 15])
+def test_fused_gradient_operand_scale_tracks_upstream_grad(log2_scale):
+    """The power-of-two scale of the fp16 gradient operand follows the upstream gradient (loss scaling in AMP,
+    1 / accumulation steps): scaling the loss by 2^k scales both gradients by exactly 2^k, no overflow, no flush."""
+    import speech_distill_b200 as KD
+
+    h, W, y, labels = _case(911, 2, 96, 128, 3001)
+
+    def grads(scale):
+        hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+        out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), teacher_logits=y.cuda(), grad_dtype=torch.float32)
+        (out[0] * scale).backward()
+        return hc.grad.float(), Wc.grad.float()
+
+    gh1, gw1 = grads(1.0)
+    ghs, gws = grads(2.0 ** log2_scale)
+    assert torch.isfinite(ghs).all() and torch.isfinite(gws).all()
+    # bf16 leaves round their gradients: compare against the rounded reference scaled exactly
+    assert torch.equal(ghs, gh1 * 2.0 ** log2_scale) and torch.equal(gws, gw1 * 2.0 ** log2_scale)
