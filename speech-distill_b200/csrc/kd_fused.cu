@@ -1649,6 +1649,11 @@ struct BwdPipe {
   std::mutex enqueue;  // the streams and events are per device: one backward is enqueued at a time
   cudaStream_t sw = nullptr, sh = nullptr;
   cudaEvent_t eg[2] = {nullptr, nullptr}, ew[2] = {nullptr, nullptr}, eh[2] = {nullptr, nullptr};
+  // state that survives from one vocabulary-range call of a backward to the next (reset at KD_RANGE_FIRST): which
+  // G buffers still have readers in flight, and the last dW / dH events (the dH chain is joined only at the end)
+  bool rec_w[2] = {false, false}, rec_h[2] = {false, false};
+  bool any_w = false, any_h = false;
+  int last_w = 0, last_h = 0;
   bool ready = false;
 };
 
@@ -1987,7 +1992,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   const bool g16 = g_fp16_enabled();
   uint8_t* h16 = wsp + ws.h16_off;
   if (g16) {
-    if (cast_bf16_f16(h, h_stride, h16, R, H, s)) return 1;
+    // (once per backward: later ranges reuse the copy in the same workspace while dW kernels may still read it)
+    if (range_first && cast_bf16_f16(h, h_stride, h16, R, H, s)) return 1;
     if (make_tmap(&t_h_mn, h16, (uint64_t)H, (uint64_t)R, (uint64_t)H, 64, "hidden fp16 (MN-major)")) return 1;
   }
 
@@ -1997,13 +2003,24 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     return 1;
 
   // three chains (grad on the caller's stream, dW, dH) when the pipeline is on; one serial chain otherwise
-  BwdPipe* pipe = (bwd_pipe_enabled() && n_chunks > 1) ? get_bwd_pipe() : nullptr;
+  // a backward split into vocabulary ranges uses the pipeline in every range (its dH chain runs across them)
+  const bool multi_range = !(range_first && range_last);
+  BwdPipe* pipe = (bwd_pipe_enabled() && (n_chunks > 1 || multi_range)) ? get_bwd_pipe() : nullptr;
   std::unique_lock<std::mutex> pipe_lock;
   if (pipe) pipe_lock = std::unique_lock<std::mutex>(pipe->enqueue);  // host threads sharing a device take turns
   cudaStream_t s_w = pipe ? pipe->sw : s, s_h = pipe ? pipe->sh : s;
-  bool rec_w[2] = {false, false}, rec_h[2] = {false, false};  // chunk c - 2 recorded an event on this buffer
-  bool any_w = false, any_h = false;
-  int last_w = 0, last_h = 0;
+  BwdPipe local_state;  // serial mode: the flags are unused
+  BwdPipe& st = pipe ? *pipe : local_state;
+  if (range_first) {
+    st.rec_w[0] = st.rec_w[1] = st.rec_h[0] = st.rec_h[1] = false;
+    st.any_w = st.any_h = false;
+  }
+  bool (&rec_w)[2] = st.rec_w;
+  bool (&rec_h)[2] = st.rec_h;
+  bool& any_w = st.any_w;
+  bool& any_h = st.any_h;
+  int& last_w = st.last_w;
+  int& last_h = st.last_h;
 
   for (int c = 0; c < n_chunks; ++c) {
     const int b = c & 1;
@@ -2147,9 +2164,12 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       }
     }
   }
-  if (pipe) {  // join: both side chains are serial, so their last events cover everything
+  if (pipe) {
+    // join: both side chains are serial, so their last events cover everything.  dW is joined after every range
+    // (its rows are handed to the all-reduce), dH only after the last one: between ranges the dH chain keeps
+    // running and the next range's gradient kernels wait per buffer, as inside a range.
     if (any_w && check_cuda(cudaStreamWaitEvent(s, pipe->ew[last_w], 0), "join dW")) return 1;
-    if (any_h && check_cuda(cudaStreamWaitEvent(s, pipe->eh[last_h], 0), "join dH")) return 1;
+    if (range_last && any_h && check_cuda(cudaStreamWaitEvent(s, pipe->eh[last_h], 0), "join dH")) return 1;
   }
   return 0;
 }
