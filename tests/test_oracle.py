@@ -119,3 +119,45 @@ def test_stage1_ce_reference_masks_rows():
     assert torch.all(gw[:15] == 0) and gw[15:].abs().max() > 0 and gh.abs().max() > 0
     r = O.closed_form((h @ w.t()).numpy(), lab.numpy(), teacher_logits=(h @ w.t()).numpy(), temperature=1.0, alpha=1.0)
     assert abs(r["losses"][1] - float(loss)) < 1e-6  # HF upcasts logits to fp32
+
+
+# ---- the oracle against the reference's CALLER (unmodified compute_loss, oracle/make_golden_flow.py) ---------------
+import ast  # noqa: E402
+
+
+def _load_flow_model(d, tag):
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+
+    cfg = ast.literal_eval(str(d[f"{tag}_cfg"]))
+    model = Qwen3ForCausalLM(Qwen3Config(**cfg)).float()
+    sd = {k[len(tag) + 1:]: torch.from_numpy(d[k]).view(torch.bfloat16).float() for k in d.files if k.startswith(tag + "/")}
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+@pytest.mark.parametrize("name", ["onthefly_topk16", "dense_teacher"])
+def test_oracle_reproduces_reference_compute_loss(name):
+    """tests/golden/flow_*.npz hold what reference train.py:43-116 returned and logged for a tiny fp32 Qwen3 pair.
+    The oracle, fed with the same models' logits (and the top-k cache built as train.py:82-91 does), gives the same
+    four numbers and the same gradient of the student's LM head: the oracle is pinned on the caller as well."""
+    d = np.load(os.path.join(GOLDEN, f"flow_{name}.npz"))
+    student, teacher = _load_flow_model(d, "student"), _load_flow_model(d, "teacher")
+    ids = torch.from_numpy(d["input_ids"])
+    labels = torch.from_numpy(d["labels"])
+    mask = torch.from_numpy(d["speech_token_mask"])
+    top_k = int(d["top_k"])
+    with torch.no_grad():
+        y = teacher(input_ids=ids).logits
+    kw = {}
+    z = student(input_ids=ids).logits
+    if top_k > 0:
+        lp = torch.log_softmax(y[..., : z.size(-1)], dim=-1)
+        v, i = torch.topk(lp, top_k, dim=-1)
+        kw = dict(teacher_top_k_v=v.to(torch.float16), teacher_top_k_i=i.to(torch.int32))
+    else:
+        kw = dict(teacher_logits=y)
+    out = O.reference_loss(z, labels, speech_token_mask=mask, temperature=2.0, alpha=0.5, **kw)
+    out[0].backward()
+    want = [float(d["loss"]), float(d["student_loss"]), float(d["distill_loss"]), float(d["teacher_loss"])]
+    np.testing.assert_allclose([float(o) for o in out], want, rtol=2e-6)
+    np.testing.assert_allclose(student.lm_head.weight.grad.numpy(), d["grad_lm_head"], rtol=1e-4, atol=1e-8)
