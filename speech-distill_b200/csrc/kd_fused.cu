@@ -1654,6 +1654,7 @@ struct BwdPipe {
   bool rec_w[2] = {false, false}, rec_h[2] = {false, false};
   bool any_w = false, any_h = false;
   int last_w = 0, last_h = 0;
+  const void* owner = nullptr;  // workspace of the backward whose ranges the state above describes
   bool ready = false;
 };
 
@@ -2011,10 +2012,21 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   cudaStream_t s_w = pipe ? pipe->sw : s, s_h = pipe ? pipe->sh : s;
   BwdPipe local_state;  // serial mode: the flags are unused
   BwdPipe& st = pipe ? *pipe : local_state;
+  if (pipe && !range_first && pipe->owner != workspace) {
+    // another backward used the pipeline between two ranges of this one (a second host thread): its state is not
+    // ours.  Drain both side chains into the caller's stream and start from a clean slate - rare, and always safe.
+    if (check_cuda(cudaEventRecord(pipe->ew[0], s_w), "drain dW")) return 1;
+    if (check_cuda(cudaEventRecord(pipe->eh[0], s_h), "drain dH")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(s, pipe->ew[0], 0), "drain dW")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(s, pipe->eh[0], 0), "drain dH")) return 1;
+    st.rec_w[0] = st.rec_w[1] = st.rec_h[0] = st.rec_h[1] = false;
+    st.any_w = st.any_h = false;
+  }
   if (range_first) {
     st.rec_w[0] = st.rec_w[1] = st.rec_h[0] = st.rec_h[1] = false;
     st.any_w = st.any_h = false;
   }
+  if (pipe) pipe->owner = workspace;
   bool (&rec_w)[2] = st.rec_w;
   bool (&rec_h)[2] = st.rec_h;
   bool& any_w = st.any_w;
