@@ -42,7 +42,7 @@ extern "C" {
 #define KD_DTYPE_BF16 1
 #define KD_DTYPE_F16 2
 
-#define KD_ABI_VERSION 2
+#define KD_ABI_VERSION 3
 
 /* OR-ed into grad_dtype of the fused backward: dH is written as fp32 (a vocab-parallel caller sums the
  * per-slice partial dH across ranks before rounding) while dW keeps the base dtype. */
@@ -151,23 +151,35 @@ int kd_zero_if_empty(void* dst, int64_t bytes, const int32_t* n_rows, void* stre
  * v_chunk: vocabulary columns per backward chunk (0 = library default); the gradient scratch is
  * 2 x R x v_chunk bf16 (double buffered), independent of V.  workspace sized by
  * kd_fused_workspace_bytes() (K = top-k width of a sparse teacher, else 0), 256-byte aligned.
- * The backward runs its three GEMM chains (gradient tile, dW, dH) on the caller's stream plus two
+ * The backward runs its three chains (gradient chunk, dW, dH) on the caller's stream plus two
  * internal streams that fork from and join back into it, so the call is still ordered like one
- * stream operation; KD_BWD_STREAMS=0 in the environment keeps everything on the caller's stream. */
+ * stream operation; KD_BWD_STREAMS=0 in the environment keeps everything on the caller's stream.
+ *
+ * Logit cache (optional, NULL / 0 = off).  The forward can keep the first columns of the logits, encoded in 16 bits
+ * (fp16 of z minus a per-row, per-32-column integer reference, so the rounding error of an entry shrinks with its
+ * probability), in a caller-provided buffer; the backward then forms those vocabulary chunks of the gradient with an
+ * HBM-bound elementwise kernel that runs beside the dW / dH GEMMs instead of recomputing the logits with a fourth
+ * GEMM (executed FLOPs 8 R H V -> 6 R H V when everything fits).  The buffer size is the caller's choice, NOT a
+ * function of V: kd_fused_logit_cache_bytes(R, V, v_chunk, budget) returns how much of `budget` is usable (whole
+ * backward chunks: about 514 bytes per row and 256 columns); columns that do not fit are recomputed as before, so
+ * peak memory stays bounded by workspace + budget for any vocabulary.  Pass the same buffer, size and v_chunk to the
+ * backward of the same forward.  256-byte aligned. */
 size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int K);
+size_t kd_fused_logit_cache_bytes(int R, int V, int v_chunk, size_t budget_bytes);
 int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                         const float* topk_v, const int32_t* topk_i, int K,
                         const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, float tau,
-                        float alpha, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        float alpha, float* sums, float* row_stats, void* logit_cache, size_t logit_cache_bytes,
+                        void* workspace, size_t workspace_bytes, void* stream);
 int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                         int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                         const float* topk_v, const int32_t* topk_i, int K,
                         const int32_t* row_target, const int32_t* n_rows, const float* row_stats, int R, int H,
                         int V, float tau, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
                         void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
-                        int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
+                        int v_chunk, const void* logit_cache, size_t logit_cache_bytes, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* The same backward restricted to vocabulary rows/columns [v_begin, v_end) (v_begin a multiple of 256), so a
  * data-parallel caller can all-reduce finished dW row blocks while later ones are computed:
@@ -184,8 +196,19 @@ int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, in
                               const int32_t* n_norm,
                               const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                               int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
-                              int range_flags, int sm_limit, int v_offset, void* workspace,
-                              size_t workspace_bytes, void* stream);
+                              int range_flags, int sm_limit, int v_offset, const void* logit_cache,
+                              size_t logit_cache_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hooks (no arithmetic).  kd_launch_count: kernels this library has launched in this process so far.
+ * kd_fused_bwd_trace_begin arms a trace of the following kd_fused_linear_bwd* calls: every kernel they launch is
+ * bracketed by two timed CUDA events on the stream it is launched on (the backward runs on three streams);
+ * kd_fused_bwd_trace_read synchronises the device, disarms the trace and writes up to max_records HOST records
+ * float[4] = (class, vocabulary chunk, start ms, end ms) relative to the first event; classes: 0 fp16 operand copy,
+ * 1 gradient chunk from the logit cache, 2 dW GEMM, 3 dH GEMM, 4 gradient chunk by recompute GEMM.  Returns the
+ * number of records, -1 on error. */
+unsigned long long kd_launch_count(void);
+int kd_fused_bwd_trace_begin(void);
+int kd_fused_bwd_trace_read(float* host_out, int max_records);
 
 /* ---- vocab-parallel mode: every rank holds W[v_offset : v_offset + V, :] (V = its slice) and the
  * matching teacher columns, all ranks see the same rows.  kd_fused_linear_fwd_partial runs the forward over the
@@ -198,7 +221,8 @@ int kd_fused_linear_fwd_partial(const void* h, int64_t h_stride, const void* W, 
                                 int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                                 const float* topk_v, const int32_t* topk_i, int K,
                                 const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, int v_offset,
-                                float tau, float* rank_rec, void* workspace, size_t workspace_bytes, void* stream);
+                                float tau, float* rank_rec, void* logit_cache, size_t logit_cache_bytes,
+                                void* workspace, size_t workspace_bytes, void* stream);
 size_t kd_fused_merge_workspace_bytes(void);
 int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_target, int R, int teacher_kind,
                          float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
@@ -212,13 +236,14 @@ int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_targe
  * upstream gradient of the mean CE. */
 int kd_ce_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                            const int32_t* row_target, const int32_t* n_rows, int R, int H, int V,
-                           float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
-                           void* stream);
+                           float* sums, float* row_stats, void* logit_cache, size_t logit_cache_bytes,
+                           void* workspace, size_t workspace_bytes, void* stream);
 int kd_ce_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                            const int32_t* row_target, const int32_t* n_rows, const float* row_stats, int R,
                            int H, int V, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
                            void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
-                           int v_chunk, void* workspace, size_t workspace_bytes, void* stream);
+                           int v_chunk, const void* logit_cache, size_t logit_cache_bytes, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ---- teacher LM head in front of the top-k compaction ---------------------------------------
  * out[R,V] bf16 (row stride out_stride, a multiple of 8 elements, 16-byte aligned base; the padding columns

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("KD_B200_LIB") or os.path.join(_HERE, "libkd_b200.so")
 
 KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
 KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
-ABI_VERSION = 2  # KD_ABI_VERSION in include/kd_b200.h
+ABI_VERSION = 3  # KD_ABI_VERSION in include/kd_b200.h
 KD_RANGE_FIRST, KD_RANGE_LAST = 1, 2
 KD_GRAD_DH_F32 = 0x100
 
@@ -23,6 +23,9 @@ _vp, _i32, _i64, _f32, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c
 SIGNATURES = {
     "kd_version": (_i32, []),
     "kd_last_error": (_c.c_char_p, []),
+    "kd_launch_count": (_c.c_ulonglong, []),
+    "kd_fused_bwd_trace_begin": (_i32, []),
+    "kd_fused_bwd_trace_read": (_i32, [_vp, _i32]),
     "kd_device_info": (_i32, [_c.POINTER(_i32)] * 3),
     "kd_prepare_rows": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "kd_finalize_losses": (_i32, [_vp, _f32, _f32, _i32, _vp, _vp]),
@@ -35,24 +38,26 @@ SIGNATURES = {
     "kd_topk_logprobs": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "kd_mask_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
     "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "kd_fused_logit_cache_bytes": (_sz, [_i32, _i32, _i32, _sz]),
     "kd_compact_rows": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "kd_gather_rows": (_i32, [_vp, _i64, _vp, _i32, _vp, _i64, _i64, _i32, _vp]),
     "kd_zero_if_empty": (_i32, [_vp, _i64, _vp, _vp]),
     "kd_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32,
-                                   _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
+                                   _i32, _f32, _f32, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "kd_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
                                    _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _sz,
-                                   _vp]),
+                                   _vp, _sz, _vp]),
     "kd_fused_linear_bwd_range": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp,
                                          _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32,
-                                         _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+                                         _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp]),
     "kd_fused_linear_fwd_partial": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp,
-                                           _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
+                                           _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp, _sz, _vp]),
     "kd_fused_merge_workspace_bytes": (_sz, []),
     "kd_fused_merge_ranks": (_i32, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
-    "kd_ce_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "kd_ce_fused_linear_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _sz,
+                                      _vp]),
     "kd_ce_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64,
-                                      _vp, _i64, _i64, _i32, _vp, _sz, _vp]),
+                                      _vp, _i64, _i64, _i32, _vp, _sz, _vp, _sz, _vp]),
     "kd_linear_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
     "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
 }

@@ -1,4 +1,5 @@
 // C-ABI plumbing shared by all kernels: error text, version, device info.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -21,7 +22,16 @@ int check_cuda(cudaError_t e, const char* what) {
   return 2;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
+}
+
 }  // namespace kd
+
+extern "C" unsigned long long kd_launch_count(void) { return kd::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int kd_version(void) { return KD_ABI_VERSION; }
 

@@ -17,6 +17,40 @@ constexpr int kNumPartialSlots = 8;  // floats per partial-sum record
 // error plumbing (kd_api.cu)
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+// cudaGetLastError() after a kernel launch; also counts the launch (kd_launch_count(), bench.py's gpu_launches)
+int check_launch(const char* what);
+
+constexpr int kMaxDevices = 64;
+// index of the current device for per-device caches (function attributes, SM counts, stream pools)
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
+// Every entry point launches on the device that OWNS its tensors, whatever the calling thread's current device is
+// (single-process multi-GPU callers: a teacher on another GPU, one thread per device): the guard looks the device
+// of a primary pointer up, switches to it for the duration of the call and restores the caller's device after.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* p) {
+    if (p == nullptr) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();  // not a CUDA pointer: the entry point's own checks report it
+      return;
+    }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (a.device != prev && cudaSetDevice(a.device) == cudaSuccess) switched = true;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 __device__ __forceinline__ float ex2(float x) {
   float y;

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "kd_common.cuh"
 #include "kd_umma.cuh"
@@ -39,7 +40,6 @@ constexpr int kThreads = 128 + kEpiThreads;      // 640 (<= 96 registers per thr
 constexpr int kColGroups = kEpiWarps / 4;        // column groups working on one step side by side
 constexpr uint32_t kABytes = BM * BK * 2;        // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 2;        // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kBoxMnBytes = 64 * BK * 2;    // one 64(mn) x 64(k) MN-major box = 8 KB
 constexpr uint32_t kTmemCols = 512;
 constexpr int kStepCols = 32 * kColGroups;       // columns per epilogue step: 32 for each column group (128)
@@ -57,14 +57,14 @@ constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt,
 constexpr int kRankRecFloats = 12;
 
 // shared-memory plan of one kernel instantiation: as many operand stages as fit beside the epilogue rings
-template <int CG, int YSLOTS, int GSLOTS>
+template <int CG, int YSLOTS, int GSLOTS, int MAXSTAGES = 8>
 struct SmemPlan {
   static constexpr uint32_t kBBytesL = kBBytes / CG;
   static constexpr uint32_t kStageL = kABytes + kBBytesL;
   static constexpr uint32_t kRing = (YSLOTS + GSLOTS) * kStepBytes;
   static constexpr uint32_t kBudget = 232448 - 1024 /*alignment slack*/ - 512 /*barriers*/;
   static constexpr int kStagesRaw = (int)((kBudget - kRing) / kStageL);
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > MAXSTAGES ? MAXSTAGES : kStagesRaw;
   static constexpr uint32_t kYOff = kStages * kStageL;
   static constexpr uint32_t kGOff = kYOff + YSLOTS * kStepBytes;
   static constexpr uint32_t kBarOff = kGOff + GSLOTS * kStepBytes;
@@ -88,11 +88,23 @@ struct Geom {
   const int32_t* n_rows;
   int rows_dim;
   int ab_fp16;  // operands A and B are fp16 (dW / dH GEMMs with the fp16 gradient operand), else bf16
+  // unit order.  0: the m block is the fast index (units that run side by side share the B tile: forward, dH);
+  // 1: the n range is the fast index (they share the A tile: dW = G^T h, whose A tile is a 2 MB column block of
+  // the gradient chunk - with m fast all 74 CTA pairs swept the whole 155 MB chunk once per h tile, 0.62 GB of
+  // DRAM reads per chunk for 0.16 GB algorithmic, ncu profiles/r01g)
+  int n_fast;
 };
 
+__host__ __device__ inline int num_ranges_of(const Geom& g) { return (g.num_n_blk + g.n_per_unit - 1) / g.n_per_unit; }
 __host__ __device__ inline void decode_unit(const Geom& g, int u, int& m_blk, int& range, int& n_begin, int& n_end) {
-  range = u / g.num_m_blk;
-  m_blk = u - range * g.num_m_blk;
+  if (g.n_fast) {
+    const int nr = num_ranges_of(g);
+    m_blk = u / nr;
+    range = u - m_blk * nr;
+  } else {
+    range = u / g.num_m_blk;
+    m_blk = u - range * g.num_m_blk;
+  }
   n_begin = range * g.n_per_unit;
   n_end = n_begin + g.n_per_unit < g.num_n_blk ? n_begin + g.n_per_unit : g.num_n_blk;
 }
@@ -244,6 +256,10 @@ struct FwdParams {
   int label_off;    // vocab-parallel: this call's columns are vocabulary [label_off, label_off + V)
   SparseView sp;    // sparse teacher (index-sorted entries + per-tile offsets), unused otherwise
   int debug_skip_math;  // KD_DEBUG_SKIP_MATH=1: bring-up knob that measures the pipeline without the epilogue math
+  // logit cache (see LogitCache): the first zc_tiles 256-column tiles of every row are kept, encoded, for the
+  // backward; zc_tiles = 0 switches the store path off
+  int zc_tiles;
+  int16_t* zc_ref;  // [zc_tiles * 8][R] piece references
 };
 
 template <typename TY, bool DENSE, bool TAU2, bool Y_TMA, bool SPARSE = false>
@@ -251,20 +267,23 @@ struct FwdEpi {
   static_assert(!(DENSE && SPARSE), "one teacher kind per instantiation");
   using Params = FwdParams;
   static constexpr bool kUseYRing = DENSE && Y_TMA;
-  // three teacher-tile slots (96 KB) + four operand stages: measured 4 % faster than 2 + 5 (1056 vs 1097 us);
-  // 4 + 3 and a third slot in the gradient kernel (which also stages G) are slower
-  static constexpr int kYSlots = kUseYRing ? 3 : 0;
-  static constexpr int kGSlots = 0;
+  // two teacher-tile slots + one staging buffer for the logit-cache store (32 KB each) + four operand stages.
+  // (Round 1, without the cache store: three teacher slots + four stages measured 4 % faster than 2 + 5.)
+  static constexpr int kYSlots = kUseYRing ? 2 : 0;
+  static constexpr int kGSlots = 1;
+  static constexpr int kMaxStages = 8;
+  static constexpr int kBoundThreads = kThreads;
   const Params& p;
   EpiThread t;
-  int row, target, range;
+  int row, target, range, m0;
   bool valid;
   float m, s1, st, mt, t1, tt, a, zl;
   YRing ring;
 
   __device__ FwdEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
 
-  __device__ void begin_unit(const Geom&, int m0, int range_) {
+  __device__ void begin_unit(const Geom&, int m0_, int range_) {
+    m0 = m0_;
     row = m0 + t.row_in_tile;
     range = range_;
     target = local_target(row < p.R ? p.row_target[row] : -1, p.label_off, p.V, valid);
@@ -298,9 +317,24 @@ struct FwdEpi {
     }
   }
 
+  // logit cache: 16 logits -> fp16 of (z - ref), two 16-byte pieces
+  __device__ __forceinline__ void encode16(const uint32_t (&raw)[16], float ref, uint4& lo, uint4& hi) {
+    float t8[8];
+    Vec8<__half> v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t8[j] = __uint_as_float(raw[j]) - ref;
+    v.pack(t8);
+    lo = v.a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t8[j] = __uint_as_float(raw[8 + j]) - ref;
+    v.pack(t8);
+    hi = v.a;
+  }
+
   template <int CG>
   __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
     const int col_base = g.b_n0 + n_blk * BN + t.cgrp * 32;
+    const bool zc_on = n_blk < p.zc_tiles;  // uniform over the CTA pair
     int e_beg = 0, e_end = 0;
     if (SPARSE && valid) {  // this row's teacher entries inside the tile
       const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + (g.b_n0 / BN + n_blk);
@@ -324,34 +358,96 @@ struct FwdEpi {
       }
       const int col0 = col_base + c * kStepCols;
       const int nrem = p.V - col0;
-      if (!valid || nrem <= 0 || p.debug_skip_math) continue;
-      if (SPARSE) {  // cross term sum_k p_k z[i_k] (distillation_loss.py:101-106): rare, predicated pick-up
-        for (int e = e_beg; e < e_end; ++e) {
-          const unsigned d = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col0);
-          if (d < 32u) {
-            float z = 0.f;
+      const bool live = valid && nrem > 0 && !p.debug_skip_math;
+      float ref = 0.f;
+      if (zc_on) {
+        // logit-cache staging buffer (one, as in GradEpi): the previous step's TMA stores must have finished reading
+        // it - they were issued a whole TMEM load + teacher-tile wait ago - before this step's pieces are written
+        if (t.epi_tid == 0) bulk_wait_read_all();
+        named_bar_sync(1, kEpiThreads);
+        if (live) {
+          // piece reference: the smallest integer >= every logit this thread has seen in its columns of this row
+          // so far, the 32 of this step included.  It is <= row max + 1, so |z - ref| <= (row max - z) + 1: the
+          // fp16 rounding error of an entry shrinks with its probability (see LogitCache).
+          float vm = m;
+          if (nrem >= 32) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j == (int)(d & 15u)) z = __uint_as_float(d < 16u ? raw0[j] : raw1[j]);
-            a = fmaf(p.sp.p[(size_t)row * p.sp.K + e], z, a);
+            for (int j = 0; j < 16; ++j) vm = fmaxf(vm, fmaxf(__uint_as_float(raw0[j]), __uint_as_float(raw1[j])));
+          } else {  // ragged vocabulary edge
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < nrem) vm = fmaxf(vm, __uint_as_float(raw0[j]));
+              if (16 + j < nrem) vm = fmaxf(vm, __uint_as_float(raw1[j]));
+            }
+          }
+          ref = fminf(fmaxf(ceilf(vm), -32000.f), 32000.f);
+          p.zc_ref[(size_t)(n_blk * 8 + c * kColGroups + t.cgrp) * p.R + row] = (int16_t)ref;
+        } else {  // rows that are not scored (and columns past V) store zeros
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sts128(step_piece_addr(t.g_base, t, q), make_uint4(0, 0, 0, 0));
+        }
+      }
+      if (live) {
+        if (SPARSE) {  // cross term sum_k p_k z[i_k] (distillation_loss.py:101-106): rare, predicated pick-up
+          for (int e = e_beg; e < e_end; ++e) {
+            const unsigned d = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col0);
+            if (d < 32u) {
+              float z = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j == (int)(d & 15u)) z = __uint_as_float(d < 16u ? raw0[j] : raw1[j]);
+              a = fmaf(p.sp.p[(size_t)row * p.sp.K + e], z, a);
+            }
+          }
+        }
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
+          if (nc <= 0) {  // (ragged edge) nothing to score, but the cache piece must still be defined
+            if (zc_on) {
+              sts128(step_piece_addr(t.g_base, t, 2), make_uint4(0, 0, 0, 0));
+              sts128(step_piece_addr(t.g_base, t, 3), make_uint4(0, 0, 0, 0));
+            }
+            break;
+          }
+          float fy[16];
+          if (DENSE) {
+            if (kUseYRing) {
+              unpack_sub<__nv_bfloat16>(pk, sub, nc, fy);
+            } else {
+              const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0 + 16 * sub;
+              load_row16<TY>(yp, p.y_vec_ok != 0, nc, fy);
+            }
+          }
+          if (sub == 0) {
+            if (zc_on) {
+              uint4 lo, hi;
+              encode16(raw0, ref, lo, hi);
+              sts128(step_piece_addr(t.g_base, t, 0), lo);
+              sts128(step_piece_addr(t.g_base, t, 1), hi);
+            }
+            sub_chunk(raw0, fy, col0, nc);
+          } else {
+            if (zc_on) {
+              uint4 lo, hi;
+              encode16(raw1, ref, lo, hi);
+              sts128(step_piece_addr(t.g_base, t, 2), lo);
+              sts128(step_piece_addr(t.g_base, t, 3), hi);
+            }
+            sub_chunk(raw1, fy, col0 + 16, nc);
           }
         }
       }
+      if (zc_on) {
+        // swizzled [128 x kStepCols] fp16 step -> TMA stores (the store path of the gradient tile, GradEpi)
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (t.epi_tid == 0) {
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
-        if (nc <= 0) break;
-        float fy[16];
-        if (DENSE) {
-          if (kUseYRing) {
-            unpack_sub<__nv_bfloat16>(pk, sub, nc, fy);
-          } else {
-            const TY* yp = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col0 + 16 * sub;
-            load_row16<TY>(yp, p.y_vec_ok != 0, nc, fy);
-          }
+          for (int b = 0; b < kStepBoxes; ++b)
+            tma_store_2d(t.tma_g, t.g_base + b * kBoxBytes, n_blk * BN + c * kStepCols + 64 * b, m0);
+          bulk_commit();
         }
-        if (sub == 0) sub_chunk(raw0, fy, col0, nc);
-        else sub_chunk(raw1, fy, col0 + 16, nc);
       }
     }
   }
@@ -363,7 +459,9 @@ struct FwdEpi {
       *reinterpret_cast<float4*>(rec + 4) = make_float4(t1, tt, a, zl);
     }
   }
-  __device__ void finish() {}
+  __device__ void finish() {
+    if (t.epi_tid == 0) bulk_wait_all();
+  }
 };
 
 // ---- backward: gradient tile ------------------------------------------------------------------
@@ -394,6 +492,8 @@ struct GradEpi {
   static constexpr bool kUseYRing = DENSE && Y_TMA;
   static constexpr int kYSlots = kUseYRing ? 2 : 0;
   static constexpr int kGSlots = 1;
+  static constexpr int kMaxStages = 8;
+  static constexpr int kBoundThreads = kThreads;
   const Params& p;
   EpiThread t;
   int row, target, m0;
@@ -567,6 +667,175 @@ struct GradEpi {
   }
 };
 
+// ---- backward from the logit cache: gradient chunk without the recompute GEMM ---------------------
+// Logit cache (written by FwdEpi, read here).  The forward keeps the first `tiles` 256-column tiles of the logits
+// of every row in a buffer whose size is a caller-given constant (so the path's peak memory stays independent
+// of V: a larger vocabulary simply has a smaller cached fraction, the rest is recomputed by GradEpi):
+//   z16 [R][tiles * 256]  fp16 of (z - ref),   ref [tiles * 8][R] int16: one integer reference per row and
+//   32-column piece, chosen by the forward as ceil(running row max of the thread that owns the piece).
+// Because ref <= row max + 1, |z - ref| <= (row max - z) + 1 and the fp16 rounding error of the decoded logit is
+// <= 2^-11 (d + 1) for an entry d below the row max, i.e. an absolute error of e^-d (d + 1) 2^-11 <= 5e-4 of the
+// LARGEST probability of the row for the entry's probability - an order below the fp16 rounding of G itself
+// (plain fp16 logits would carry 2^-12 |z| regardless of the entry's weight: 2e-3 at |z| = 8).
+// With the cache the backward's gradient chunk is an HBM-bound elementwise kernel (read z16 2 B + teacher 2 B,
+// write G 2 B per element) that runs beside the dW / dH GEMMs of the previous chunk instead of a fourth GEMM:
+// executed FLOPs drop from 8 R H V to the algorithmic 6 R H V.
+struct LogitCache {
+  int tiles;            // cached 256-column tiles (0 = no cache)
+  __half* z16;          // [R][tiles * 256]
+  int16_t* ref;         // [tiles * 8][R]
+  int64_t z_stride;     // tiles * 256
+};
+
+struct GradCachedParams {
+  LogitCache zc;
+  const void* y;
+  int64_t y_stride;
+  int y_vec_ok;
+  const int32_t* row_target;
+  const float* row_stats;
+  const int32_t* n_norm;
+  const float* coef;
+  const int32_t* n_rows;  // live rows after compaction, or null
+  float tau;
+  int use_kl, g_fp16;
+  int R, V, v0, cols_pad, label_off;  // chunk = vocabulary columns [v0, v0 + cols_pad), cols_pad % 256 == 0
+  void* G;                            // [R][g_stride] 16-bit
+  int64_t g_stride;
+  SparseView sp;
+};
+
+constexpr int kGcThreads = 256;  // 8 warps, one row strip each
+constexpr int kGcUnroll = 2;     // 256-column pieces in flight per warp
+
+template <typename TY, bool DENSE, bool TAU2, bool SPARSE>
+__global__ void __launch_bounds__(kGcThreads) kd_grad_cached_kernel(const GradCachedParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nn = *p.n_norm;
+  float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
+  if (p.g_fp16) inv_n *= g_operand_scale(p.n_norm, p.coef, p.tau);
+  const float c1 = p.coef[0] * inv_n;
+  const float c2 = p.use_kl ? p.coef[1] * p.tau * inv_n : 0.f;
+  const float c_tau = kLog2e / p.tau;
+  int r_end = p.R;
+  if (p.n_rows != nullptr) {  // compacted rows: everything behind the last live 256-row tile is never read
+    const int live = (*p.n_rows + 2 * BM - 1) / (2 * BM) * (2 * BM);
+    r_end = live < r_end ? live : r_end;
+  }
+  for (int row = blockIdx.x * (kGcThreads / 32) + warp; row < r_end; row += gridDim.x * (kGcThreads / 32)) {
+    bool valid;
+    const int target = local_target(p.row_target[row], p.label_off, p.V, valid);
+    uint16_t* grow = reinterpret_cast<uint16_t*>(p.G) + (size_t)row * p.g_stride;
+    if (!valid) {  // rows that are not scored contribute nothing: zeros, no reads
+      for (int j = lane * 8; j < p.cols_pad; j += 256) *reinterpret_cast<uint4*>(grow + j) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
+    const float off1 = rs.x * kLog2e, offt = rs.y * kLog2e, offy = rs.z * kLog2e;
+    const float half_off1 = 0.5f * off1;
+    const float k_tau = c2 * ex2(half_off1 - offt);
+    const __half* zrow = p.zc.z16 + (size_t)row * p.zc.z_stride + p.v0;
+    const int16_t* refrow = p.zc.ref + row;
+    const TY* yrow = DENSE ? reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + p.v0 : nullptr;
+    for (int j0 = 0; j0 < p.cols_pad; j0 += 256 * kGcUnroll) {
+      uint4 zv[kGcUnroll];
+      Vec8<TY> yv[kGcUnroll];
+      float ref[kGcUnroll];
+      // ---- loads of all pieces first (memory-level parallelism), then the arithmetic ----
+#pragma unroll
+      for (int u = 0; u < kGcUnroll; ++u) {
+        const int j = j0 + u * 256 + lane * 8;
+        const int nrem = p.V - (p.v0 + j);
+        if (j < p.cols_pad && nrem > 0) {
+          zv[u] = ldg_stream(zrow + j);
+          ref[u] = (float)refrow[(size_t)((p.v0 + j) >> 5) * p.R];
+          if (DENSE && nrem >= 8 && p.y_vec_ok) yv[u].load_global(yrow + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGcUnroll; ++u) {
+        const int j = j0 + u * 256 + lane * 8;
+        if (j >= p.cols_pad) break;
+        const int col = p.v0 + j;
+        const int nrem = p.V - col;
+        float gq[8];
+        if (nrem <= 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gq[i] = 0.f;
+        } else {
+          float fz[8], fy[8];
+          {
+            Vec8<__half> v;
+            v.a = zv[u];
+            v.unpack(fz);
+          }
+          if (DENSE) {
+            if (nrem >= 8 && p.y_vec_ok) {
+              if (std::is_same<TY, __nv_bfloat16>::value) {
+                yv[u].a.x = clamp_neg_inf_bf16x2(yv[u].a.x);
+                yv[u].a.y = clamp_neg_inf_bf16x2(yv[u].a.y);
+                yv[u].a.z = clamp_neg_inf_bf16x2(yv[u].a.z);
+                yv[u].a.w = clamp_neg_inf_bf16x2(yv[u].a.w);
+                yv[u].unpack(fy);
+              } else {
+                yv[u].unpack(fy);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fy[i] = fmaxf(fy[i], -1e30f);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) fy[i] = i < nrem ? fmaxf(Elem<TY>::to_f(yrow[j + i]), -1e30f) : -CUDART_INF_F;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float z = fz[i] + ref[u];
+            float gi;
+            if (TAU2) {
+              const float e = ex2(fmaf(z, c_tau, -half_off1));
+              gi = e * fmaf(e, c1, k_tau);
+            } else {
+              gi = c1 * ex2(fmaf(z, kLog2e, -off1)) + c2 * ex2(fmaf(z, c_tau, -offt));
+            }
+            if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
+            gq[i] = i < nrem ? gi : 0.f;
+          }
+          if (SPARSE) {  // - c2 P with P = scatter(i_k, p_k); duplicate indices accumulate
+            const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + col / BN;  // uniform over the warp's piece
+            const int e_beg = o[0], e_end = o[1];
+            for (int e = e_beg; e < e_end; ++e) {
+              const unsigned ds = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col);
+              if (ds < 8u) {
+                const float pk = c2 * p.sp.p[(size_t)row * p.sp.K + e];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (i == (int)ds) gq[i] -= pk;
+              }
+            }
+          }
+          const unsigned d = (unsigned)(target - col);
+          if (d < 8u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i == (int)d) gq[i] -= c1;
+          }
+        }
+        uint4 outv;
+        if (p.g_fp16) {
+          Vec8<__half> v;
+          v.pack(gq);
+          outv = v.a;
+        } else {
+          Vec8<__nv_bfloat16> v;
+          v.pack(gq);
+          outv = v.a;
+        }
+        *reinterpret_cast<uint4*>(grow + j) = outv;
+      }
+    }
+  }
+}
+
 // ---- plain stores: dW rows (bf16), dH accumulation (fp32 -> bf16), test hook (fp32) ------------
 enum StoreMode { kStoreF32 = 0, kAccumF32 = 1, kFinalBf16 = 2, kStoreBf16 = 3 };
 struct StoreParams {
@@ -588,6 +857,11 @@ struct StoreEpi {
   using Params = StoreParams;
   static constexpr int kYSlots = 0;
   static constexpr int kGSlots = 0;
+  // The dW / dH GEMMs share their SMs with the gradient kernel of the next vocabulary chunk (kd_grad_cached_kernel,
+  // HBM-bound): six operand stages (192 KB) and <= 64 registers per thread (launch bound of 1024 threads) leave it
+  // 24 K registers and ~30 KB of shared memory per SM.
+  static constexpr int kMaxStages = 6;
+  static constexpr int kBoundThreads = 1024;
   const Params& p;
   EpiThread t;
   int row;
@@ -689,7 +963,7 @@ struct StoreEpi {
 // a unit is dead when row compaction left no live row in its M tile (rows_dim 1) or no live k-block (rows_dim 2)
 template <int CG>
 __device__ __forceinline__ bool unit_live(const Geom& g, int u, int n_rows_live) {
-  if (g.rows_dim == 1) return (u % g.num_m_blk) * (CG * BM) < n_rows_live;
+  if (g.rows_dim == 1) return (g.n_fast ? u / num_ranges_of(g) : u % g.num_m_blk) * (CG * BM) < n_rows_live;
   if (g.rows_dim == 2) return n_rows_live > 0;
   return true;
 }
@@ -734,11 +1008,11 @@ struct UnitQueue {
 //   tma_g : gradient scratch [rows][v_chunk] bf16, 64 x 128 boxes stored from the g ring (epilogue)
 // ---------------------------------------------------------------------------------------------
 template <class Epi, bool A_MN, bool B_MN, int CG>
-__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(Epi::kBoundThreads, 1)
 kd_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_g, const Geom g,
                const typename Epi::Params ep, int* __restrict__ sched_counter) {
-  using Plan = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots>;
+  using Plan = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots, Epi::kMaxStages>;
   constexpr int kStages = Plan::kStages;
   constexpr int kYSlots = Epi::kYSlots;
   constexpr uint32_t kBBytesL = Plan::kBBytesL;      // this CTA's share of the B tile
@@ -1110,6 +1384,7 @@ __global__ void __launch_bounds__(256) kd_fused_merge_kernel(const MergeParams p
       *reinterpret_cast<float4*>(rec + 4) = make_float4(t1, tt, a, zl);
       *reinterpret_cast<float4*>(rec + 8) = make_float4(yl, rc.x, rc.y, rc.z);
     } else if (lane == 0) {
+      if (target - p.label_off >= p.V) zl = CUDART_NAN_F;  // label outside the vocabulary: loud, not silently wrong
       const float lse1 = m + ln_acc(s1);
       const float lset = m * p.inv_tau + ln_acc(st);
       float lsett = 0.f;
@@ -1382,14 +1657,11 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
 // dW all-reduce leaves NCCL's CTAs their own SMs, otherwise the last CTAs of every launch queue behind them
 static thread_local int tl_sm_limit = 0;
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+static int sm_count() {  // of the current device (the entry points switch to the tensors' device first)
+  static int n[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 // CTA-pair mode (tcgen05 cta_group::2) is the default; KD_UMMA_CTA_GROUP=1 selects the single-CTA kernels
@@ -1434,13 +1706,14 @@ template <class Epi, bool A_MN, bool B_MN, int CG>
 static int launch_umma_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
                           const Geom& g, const typename Epi::Params& ep, cudaStream_t stream) {
   auto kern = kd_umma_kernel<Epi, A_MN, B_MN, CG>;
-  constexpr uint32_t smem = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots>::kBytes;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  constexpr uint32_t smem = SmemPlan<CG, Epi::kYSlots, Epi::kGSlots, Epi::kMaxStages>::kBytes;
+  static bool attr_set[kMaxDevices] = {};  // per instantiation and device (function attributes are per device)
+  const int dev_slot = current_device_slot();
+  if (!attr_set[dev_slot]) {
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "kd_umma smem attribute"))
       return 1;
-    attr_set = true;
+    attr_set[dev_slot] = true;
   }
   if (g.num_units <= 0 || g.num_k_blk <= 0) {
     set_error("kd_umma: empty problem (units=%d, k blocks=%d)", g.num_units, g.num_k_blk);
@@ -1462,7 +1735,7 @@ static int launch_umma_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     gg.dynamic = 1;
   }
   kern<<<grid, kThreads, smem, stream>>>(ta, tb, ty, tg, gg, ep, counter);
-  return check_cuda(cudaGetLastError(), "kd_umma launch");
+  return check_launch("kd_umma launch");
 }
 template <class Epi, bool A_MN, bool B_MN>
 static int launch_umma(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const CUtensorMap& tg,
@@ -1492,8 +1765,10 @@ static bool g_fp16_enabled() {
 }
 
 // dst[r, :] (fp16, contiguous rows of `cols`) = src[r, :] (bf16, row stride src_stride); cols % 8 == 0.
-// bf16 -> fp16 is exact inside fp16's exponent range; smaller magnitudes round to fp16 subnormals / zero, larger
-// ones saturate to +-65504 (neither occurs for activations and weights of the models on this path).
+// bf16 -> fp16 is exact inside fp16's normal range.  Magnitudes below 6e-8 flush to zero (harmless: far below the
+// rounding of the products they enter); magnitudes above 65504 - not seen in LM-head activations or weights, but
+// nothing guarantees it - become +-inf on purpose: the gradients then come out non-finite, which a training loop
+// notices, instead of being silently wrong as a saturating cast would leave them (KD_G_FP16=0 is the way out).
 __global__ void __launch_bounds__(256) kd_cast_bf16_f16_kernel(const __nv_bfloat16* __restrict__ src, int64_t src_stride,
                                                               __half* __restrict__ dst, int rows, int cols) {
   const int vec_per_row = cols >> 3;
@@ -1504,8 +1779,6 @@ __global__ void __launch_bounds__(256) kd_cast_bf16_f16_kernel(const __nv_bfloat
     v.load_global(src + (int64_t)r * src_stride + c);
     float f[8];
     v.unpack(f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);
     Vec8<__half> o;
     o.pack(f);
     *reinterpret_cast<uint4*>(dst + (int64_t)r * cols + c) = o.a;
@@ -1519,7 +1792,7 @@ static int cast_bf16_f16(const void* src, int64_t src_stride, void* dst, int row
   if (blocks > 148 * 8) blocks = 148 * 8;
   kd_cast_bf16_f16_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_stride,
                                                  reinterpret_cast<__half*>(dst), rows, cols);
-  return check_cuda(cudaGetLastError(), "kd_cast_bf16_f16 launch");
+  return check_launch("kd_cast_bf16_f16 launch");
 }
 
 // ---- workspace layout -----------------------------------------------------------------------------
@@ -1614,16 +1887,17 @@ static int check_common(const void* h, int64_t h_stride, const void* W, int64_t 
 }
 
 template <bool DENSE, typename TY>
-static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* ty, const Geom& g,
-                      const FwdParams& fp, bool tau2, cudaStream_t s) {
+static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* ty, const CUtensorMap& tz,
+                      const Geom& g, const FwdParams& fp, bool tau2, cudaStream_t s) {
+  // tz: the logit cache as a TMA store target (any valid map when the cache is off)
   if constexpr (DENSE && sizeof(TY) == 2) {
     if (ty != nullptr) {  // teacher tile staged by TMA
-      if (tau2) return launch_umma<FwdEpi<TY, true, true, true>, false, false>(ta, tb, *ty, ta, g, fp, s);
-      return launch_umma<FwdEpi<TY, true, false, true>, false, false>(ta, tb, *ty, ta, g, fp, s);
+      if (tau2) return launch_umma<FwdEpi<TY, true, true, true>, false, false>(ta, tb, *ty, tz, g, fp, s);
+      return launch_umma<FwdEpi<TY, true, false, true>, false, false>(ta, tb, *ty, tz, g, fp, s);
     }
   }
-  if (tau2) return launch_umma<FwdEpi<TY, DENSE, true, false>, false, false>(ta, tb, g, fp, s);
-  return launch_umma<FwdEpi<TY, DENSE, false, false>, false, false>(ta, tb, g, fp, s);
+  if (tau2) return launch_umma<FwdEpi<TY, DENSE, true, false>, false, false>(ta, tb, ta, tz, g, fp, s);
+  return launch_umma<FwdEpi<TY, DENSE, false, false>, false, false>(ta, tb, ta, tz, g, fp, s);
 }
 template <bool DENSE, typename TY>
 static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* ty, const CUtensorMap& tg,
@@ -1637,6 +1911,50 @@ static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   if (tau2) return launch_umma<GradEpi<TY, DENSE, true, false>, false, false>(ta, tb, ta, tg, g, gp, s);
   return launch_umma<GradEpi<TY, DENSE, false, false>, false, false>(ta, tb, ta, tg, g, gp, s);
 }
+
+// ---- backward trace (measurement hook): per-kernel start / end times on the three backward streams ----------
+// kd_fused_bwd_trace_begin() arms it; every launch of the following backward calls is bracketed by two timed events
+// on the stream it is launched on; kd_fused_bwd_trace_read() synchronises and returns (class, chunk, start ms,
+// end ms) records relative to the first event.  bench.py uses it for the per-kernel rooflines of the step - the
+// live, concurrent timeline, which a serialising profiler cannot show.  Off (the default) it costs one branch.
+enum TraceClass { kTraceCast = 0, kTraceGrad = 1, kTraceDw = 2, kTraceDh = 3, kTraceGradRecompute = 4 };
+struct TraceRec {
+  int cls, chunk;
+  cudaEvent_t e0, e1;
+};
+struct BwdTrace {
+  std::mutex mu;
+  bool on = false;
+  std::vector<TraceRec> recs;
+  std::vector<cudaEvent_t> pool;  // recycled timed events
+  cudaEvent_t take() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+static BwdTrace g_trace;
+
+struct TraceScope {  // records e0 now and e1 at scope exit on `s`; inert when the trace is off
+  cudaStream_t s;
+  cudaEvent_t e1 = nullptr;
+  TraceScope(int cls, int chunk, cudaStream_t s_) : s(s_) {
+    if (!g_trace.on) return;
+    std::lock_guard<std::mutex> lock(g_trace.mu);
+    TraceRec r = {cls, chunk, g_trace.take(), g_trace.take()};
+    cudaEventRecord(r.e0, s);
+    e1 = r.e1;
+    g_trace.recs.push_back(r);
+  }
+  ~TraceScope() {
+    if (e1) cudaEventRecord(e1, s);
+  }
+};
 
 // ---- backward pipeline: three serial chains on three streams -----------------------------------------
 //   caller's stream : grad(0) grad(1) grad(2) ...          (G chunk c -> buffer c & 1)
@@ -1721,7 +2039,7 @@ static int prepare_sparse(const float* topk_v, const int32_t* topk_i, int K, con
   pp.off_stride = ws.sp_off_stride;
   const int blocks = R < 8 * sm_count() ? R : 8 * sm_count();
   kd_sparse_prepare_kernel<<<blocks, kPrepThreads, (size_t)Kp2 * 8, s>>>(pp);
-  if (check_cuda(cudaGetLastError(), "kd_sparse_prepare launch")) return 1;
+  if (check_launch("kd_sparse_prepare launch")) return 1;
   view->idx = pp.s_idx;
   view->p = pp.s_p;
   view->off = pp.off;
@@ -1738,6 +2056,62 @@ static bool make_teacher_tmap(CUtensorMap* m, const void* y, int y_dtype, int64_
   return make_tmap(m, y, (uint64_t)V, (uint64_t)R, (uint64_t)y_stride, BM, "teacher logits") == 0;
 }
 
+
+// ---- logit cache: layout and the cached gradient launch -------------------------------------------------
+static inline size_t zc_tile_bytes(int R) { return (size_t)R * BN * 2 + (size_t)(BN / 32) * R * 2; }  // z16 + ref
+
+// the cache a caller-provided buffer of `bytes` holds for R rows of a V-column head (tiles = 0: none)
+static LogitCache plan_logit_cache(void* buf, size_t bytes, int R, int V) {
+  LogitCache zc = {};
+  if (!buf || bytes == 0 || (reinterpret_cast<uintptr_t>(buf) & 255) != 0) return zc;
+  size_t tiles = bytes / zc_tile_bytes(R);
+  const size_t all = (size_t)cdiv(V, BN);
+  if (tiles > all) tiles = all;
+  zc.tiles = (int)tiles;
+  zc.z16 = reinterpret_cast<__half*>(buf);
+  zc.z_stride = (int64_t)tiles * BN;
+  zc.ref = reinterpret_cast<int16_t*>(reinterpret_cast<uint8_t*>(buf) + (size_t)R * tiles * BN * 2);
+  return zc;
+}
+
+static bool dw_n_fast() {  // KD_DW_ORDER=m restores round 1's unit order of the dW GEMM (A/B experiments)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_DW_ORDER");
+    v = (e && e[0] == 'm') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static bool grad_cached_overlap() {  // KD_GRAD_OVERLAP=0: the cached gradient kernel stays on the caller's stream order
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KD_GRAD_OVERLAP");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <typename TY, bool DENSE, bool SPARSE>
+static int launch_grad_cached_t(const GradCachedParams& gp, bool tau2, int blocks, cudaStream_t s) {
+  if (tau2) kd_grad_cached_kernel<TY, DENSE, true, SPARSE><<<blocks, kGcThreads, 0, s>>>(gp);
+  else kd_grad_cached_kernel<TY, DENSE, false, SPARSE><<<blocks, kGcThreads, 0, s>>>(gp);
+  return check_launch("kd_grad_cached launch");
+}
+
+static int launch_grad_cached(const GradCachedParams& gp, int teacher_kind, int y_dtype, bool tau2, cudaStream_t s) {
+  // one warp per row strip; four CTAs per SM when the kernel has the SMs to itself, one beside a GEMM CTA
+  int blocks = cdiv(gp.R, kGcThreads / 32);
+  const int cap = 4 * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (teacher_kind == KD_TEACHER_DENSE) {
+    if (y_dtype == KD_DTYPE_BF16) return launch_grad_cached_t<__nv_bfloat16, true, false>(gp, tau2, blocks, s);
+    return launch_grad_cached_t<float, true, false>(gp, tau2, blocks, s);
+  }
+  if (teacher_kind == KD_TEACHER_SPARSE) return launch_grad_cached_t<__nv_bfloat16, false, true>(gp, tau2, blocks, s);
+  return launch_grad_cached_t<__nv_bfloat16, false, false>(gp, tau2, blocks, s);
+}
+
 }  // namespace fused
 }  // namespace kd
 
@@ -1749,38 +2123,53 @@ extern "C" size_t kd_fused_workspace_bytes(int R, int H, int V, int v_chunk, int
   return plan_workspace(R, H, V, v_chunk, K).total;
 }
 
+extern "C" size_t kd_fused_logit_cache_bytes(int R, int V, int v_chunk, size_t budget_bytes) {
+  if (R <= 0 || V <= 0) return 0;
+  // whole backward chunks only (a chunk is either read from the cache or recomputed), the last one may be ragged
+  const size_t per_tile = zc_tile_bytes(R);
+  const size_t all = (size_t)cdiv(V, BN), chunk_tiles = (size_t)norm_v_chunk(v_chunk, V) / BN;
+  size_t tiles = budget_bytes / per_tile;
+  if (tiles >= all) tiles = all;
+  else tiles = tiles / chunk_tiles * chunk_tiles;
+  return tiles * per_tile;
+}
+
 static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                           const void* y, int y_dtype, int64_t y_stride, const float* topk_v, const int32_t* topk_i,
                           int K, const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, int v_offset,
-                          float tau, float* sums, float* row_stats, float* rank_rec, void* workspace,
-                          size_t workspace_bytes, void* stream);
+                          float tau, float* sums, float* row_stats, float* rank_rec, void* logit_cache,
+                          size_t logit_cache_bytes, void* workspace, size_t workspace_bytes, void* stream);
 
 extern "C" int kd_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                                    const void* y, int y_dtype, int64_t y_stride, const float* topk_v,
                                    const int32_t* topk_i, int K, const int32_t* row_target, const int32_t* n_rows,
                                    int R, int H, int V, float tau, float alpha, float* sums, float* row_stats,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   void* logit_cache, size_t logit_cache_bytes, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   (void)alpha;
   if (!sums || !row_stats) {
     set_error("kd_fused_linear_fwd: null pointer argument");
     return 1;
   }
   return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target,
-                        n_rows, R, H, V, 0, tau, sums, row_stats, nullptr, workspace, workspace_bytes, stream);
+                        n_rows, R, H, V, 0, tau, sums, row_stats, nullptr, logit_cache, logit_cache_bytes, workspace,
+                        workspace_bytes, stream);
 }
 
 extern "C" int kd_fused_linear_fwd_partial(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                                            int teacher_kind, const void* y, int y_dtype, int64_t y_stride,
                                            const float* topk_v, const int32_t* topk_i, int K,
                                            const int32_t* row_target, const int32_t* n_rows, int R, int H, int V,
-                                           int v_offset, float tau, float* rank_rec, void* workspace,
-                                           size_t workspace_bytes, void* stream) {
+                                           int v_offset, float tau, float* rank_rec, void* logit_cache,
+                                           size_t logit_cache_bytes, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
   if (!rank_rec || v_offset < 0) {
     set_error("kd_fused_linear_fwd_partial: null record buffer or negative vocabulary offset");
     return 1;
   }
   return fused_fwd_impl(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K, row_target,
-                        n_rows, R, H, V, v_offset, tau, nullptr, nullptr, rank_rec, workspace, workspace_bytes, stream);
+                        n_rows, R, H, V, v_offset, tau, nullptr, nullptr, rank_rec, logit_cache, logit_cache_bytes,
+                        workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t kd_fused_merge_workspace_bytes(void) {
@@ -1790,6 +2179,7 @@ extern "C" size_t kd_fused_merge_workspace_bytes(void) {
 extern "C" int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t* row_target, int R, int teacher_kind,
                                     float tau, float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
                                     void* stream) {
+  DeviceGuard device_guard(rank_recs);
   if (!rank_recs || !row_target || !sums || !row_stats || !workspace || G <= 0 || R <= 0 || !(tau > 0.f)) {
     set_error("kd_fused_merge_ranks: bad arguments");
     return 1;
@@ -1813,15 +2203,16 @@ extern "C" int kd_fused_merge_ranks(const float* rank_recs, int G, const int32_t
   if (blocks > kMergeBlocksMax) blocks = kMergeBlocksMax;
   cudaStream_t s = (cudaStream_t)stream;
   kd_fused_rank_merge_kernel<<<blocks, 256, 0, s>>>(mp);
-  if (check_cuda(cudaGetLastError(), "kd_fused_rank_merge launch")) return 1;
+  if (check_launch("kd_fused_rank_merge launch")) return 1;
   return reduce_partials(mp.block_sums, blocks, sums, s);
 }
 
 static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_t w_stride, int teacher_kind,
                           const void* y, int y_dtype, int64_t y_stride, const float* topk_v, const int32_t* topk_i,
                           int K, const int32_t* row_target, const int32_t* n_rows, int R, int H, int V, int v_offset,
-                          float tau, float* sums, float* row_stats, float* rank_rec, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          float tau, float* sums, float* row_stats, float* rank_rec, void* logit_cache,
+                          size_t logit_cache_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  DeviceGuard device_guard(h);
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_fwd")) return 1;
   if (!row_target || !workspace) {
     set_error("kd_fused_linear_fwd: null pointer argument");
@@ -1872,20 +2263,31 @@ static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_
   }
   const bool tau2 = tau == 2.0f;
   int rc;
-  CUtensorMap ty;
+  CUtensorMap ty, tz = ta;
+  const LogitCache zc = plan_logit_cache(logit_cache, logit_cache_bytes, R, V);
+  if (logit_cache != nullptr && logit_cache_bytes > 0 && zc.tiles == 0) {
+    set_error("kd_fused_linear_fwd: logit cache must be 256-byte aligned and hold at least one 256-column tile "
+              "(%zu bytes for R=%d)", zc_tile_bytes(R), R);
+    return 1;
+  }
+  if (zc.tiles > 0) {
+    fp.zc_tiles = zc.tiles;
+    fp.zc_ref = zc.ref;
+    if (make_tmap(&tz, zc.z16, (uint64_t)zc.z_stride, (uint64_t)R, (uint64_t)zc.z_stride, BM, "logit cache")) return 1;
+  }
   const float4* sp_rowc = nullptr;
   const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&ty, y, y_dtype, y_stride, R, V);
   if (teacher_kind == KD_TEACHER_DENSE) {
-    rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, y_tma ? &ty : nullptr, g, fp, tau2, s)
-                                  : launch_fwd<true, float>(ta, tb, nullptr, g, fp, tau2, s);
+    rc = y_dtype == KD_DTYPE_BF16 ? launch_fwd<true, __nv_bfloat16>(ta, tb, y_tma ? &ty : nullptr, tz, g, fp, tau2, s)
+                                  : launch_fwd<true, float>(ta, tb, nullptr, tz, g, fp, tau2, s);
   } else if (sparse) {
     if (prepare_sparse(topk_v, topk_i, K, row_target, R, V, v_offset, tau, ws, wsp + ws.fwd_bytes, &fp.sp, &sp_rowc, s,
                        "kd_fused_linear_fwd"))
       return 1;
-    rc = tau2 ? launch_umma<FwdEpi<__nv_bfloat16, false, true, false, true>, false, false>(ta, tb, g, fp, s)
-              : launch_umma<FwdEpi<__nv_bfloat16, false, false, false, true>, false, false>(ta, tb, g, fp, s);
+    rc = tau2 ? launch_umma<FwdEpi<__nv_bfloat16, false, true, false, true>, false, false>(ta, tb, ta, tz, g, fp, s)
+              : launch_umma<FwdEpi<__nv_bfloat16, false, false, false, true>, false, false>(ta, tb, ta, tz, g, fp, s);
   } else {
-    rc = launch_fwd<false, __nv_bfloat16>(ta, tb, nullptr, g, fp, tau2, s);
+    rc = launch_fwd<false, __nv_bfloat16>(ta, tb, nullptr, tz, g, fp, tau2, s);
   }
   if (rc) return rc;
 
@@ -1909,7 +2311,7 @@ static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_
   int blocks = cdiv(R, 8);
   if (blocks > kMergeBlocksMax) blocks = kMergeBlocksMax;
   kd_fused_merge_kernel<<<blocks, 256, 0, s>>>(mp);
-  if (check_cuda(cudaGetLastError(), "kd_fused_merge launch")) return 1;
+  if (check_launch("kd_fused_merge launch")) return 1;
   if (rank_rec != nullptr) return 0;  // vocab-parallel: the cross-rank merge finalises
   return reduce_partials(bsums, blocks, sums, s);
 }
@@ -1919,12 +2321,47 @@ extern "C" int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* 
                                    const int32_t* topk_i, int K, const int32_t* row_target, const int32_t* n_rows,
                                    const float* row_stats, int R, int H, int V, float tau, const int32_t* n_norm,
                                    const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
-                                   int64_t dw_stride, int64_t dw_row_begin, int v_chunk, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   int64_t dw_stride, int64_t dw_row_begin, int v_chunk, const void* logit_cache,
+                                   size_t logit_cache_bytes, void* workspace, size_t workspace_bytes, void* stream) {
   return kd_fused_linear_bwd_range(h, h_stride, W, w_stride, teacher_kind, y, y_dtype, y_stride, topk_v, topk_i, K,
                                    row_target, n_rows, row_stats, R, H, V, tau, n_norm, grad_coef, grad_dtype, dH, dh_stride,
                                    dW, dw_stride, dw_row_begin, v_chunk, 0, V, KD_RANGE_FIRST | KD_RANGE_LAST, 0, 0,
-                                   workspace, workspace_bytes, stream);
+                                   logit_cache, logit_cache_bytes, workspace, workspace_bytes, stream);
+}
+
+extern "C" int kd_fused_bwd_trace_begin(void) {
+  std::lock_guard<std::mutex> lock(g_trace.mu);
+  for (const TraceRec& r : g_trace.recs) {
+    g_trace.pool.push_back(r.e0);
+    g_trace.pool.push_back(r.e1);
+  }
+  g_trace.recs.clear();
+  g_trace.on = true;
+  return 0;
+}
+
+extern "C" int kd_fused_bwd_trace_read(float* host_out, int max_records) {
+  // host_out: HOST float[max_records][4] = (class, chunk, start ms, end ms); returns the number of records (or -1)
+  std::lock_guard<std::mutex> lock(g_trace.mu);
+  g_trace.on = false;
+  if (g_trace.recs.empty()) return 0;
+  if (check_cuda(cudaDeviceSynchronize(), "trace sync")) return -1;
+  const cudaEvent_t t0 = g_trace.recs[0].e0;
+  int n = 0;
+  for (const TraceRec& r : g_trace.recs) {
+    if (n >= max_records) break;
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, t0, r.e0) != cudaSuccess || cudaEventElapsedTime(&b, t0, r.e1) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    host_out[4 * n] = (float)r.cls;
+    host_out[4 * n + 1] = (float)r.chunk;
+    host_out[4 * n + 2] = a;
+    host_out[4 * n + 3] = b;
+    ++n;
+  }
+  return n;
 }
 
 struct SmLimitScope {
@@ -1939,8 +2376,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
                                          const int32_t* n_norm,
                                          const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                                          int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
-                                         int range_flags, int sm_limit, int v_offset, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
+                                         int range_flags, int sm_limit, int v_offset, const void* logit_cache,
+                                         size_t logit_cache_bytes, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  DeviceGuard device_guard(h);
   if (check_common(h, h_stride, W, w_stride, R, H, V, tau, "kd_fused_linear_bwd")) return 1;
   if (v_begin < 0 || v_end > V || v_begin >= v_end || v_begin % BN != 0) {
     set_error("kd_fused_linear_bwd_range: bad vocabulary range [%d, %d) (V=%d; begin must be a multiple of %d)",
@@ -1968,6 +2407,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     set_error("kd_fused_linear_bwd: grad_dtype must be KD_DTYPE_BF16 or KD_DTYPE_F32 (optionally | KD_GRAD_DH_F32)");
     return 1;
   }
+  const LogitCache zc = plan_logit_cache(const_cast<void*>(logit_cache), logit_cache_bytes, R, V);
   const bool out32 = dw_dtype == KD_DTYPE_F32;                            // dW
   const bool dh_out32 = out32 || (grad_dtype & KD_GRAD_DH_F32) != 0;      // dH
   cudaStream_t s = (cudaStream_t)stream;
@@ -1994,7 +2434,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   uint8_t* h16 = wsp + ws.h16_off;
   if (g16) {
     // (once per backward: later ranges reuse the copy in the same workspace while dW kernels may still read it)
-    if (range_first && cast_bf16_f16(h, h_stride, h16, R, H, s)) return 1;
+    if (range_first) {
+      TraceScope ts(kTraceCast, -1, s);
+      if (cast_bf16_f16(h, h_stride, h16, R, H, s)) return 1;
+    }
     if (make_tmap(&t_h_mn, h16, (uint64_t)H, (uint64_t)R, (uint64_t)H, 64, "hidden fp16 (MN-major)")) return 1;
   }
 
@@ -2046,11 +2489,44 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
         if (rec_w[b] && check_cuda(cudaStreamWaitEvent(s, pipe->ew[b], 0), "wait dW")) return 1;
         if (rec_h[b] && check_cuda(cudaStreamWaitEvent(s, pipe->eh[b], 0), "wait dH")) return 1;
         rec_w[b] = rec_h[b] = false;
+        if (!grad_cached_overlap()) {  // experiment: no gradient kernel beside the previous chunk's GEMMs
+          if (rec_w[b ^ 1] && check_cuda(cudaStreamWaitEvent(s, pipe->ew[b ^ 1], 0), "wait dW")) return 1;
+          if (rec_h[b ^ 1] && check_cuda(cudaStreamWaitEvent(s, pipe->eh[b ^ 1], 0), "wait dH")) return 1;
+        }
       }
       if (g16 && dH) {  // this chunk's W rows as fp16 (read by dH(c); the buffer's previous reader was dH(c - 2))
         const uint8_t* wrow = reinterpret_cast<const uint8_t*>(W) + (size_t)v0 * (size_t)w_stride * 2;
+        TraceScope ts(kTraceCast, c, s);
         if (cast_bf16_f16(wrow, w_stride, wsp + ws.w16_off + b * ws.w16_buf_bytes, cols, H, s)) return 1;
       }
+      int rc;
+      if (v0 / BN + n_blks <= zc.tiles) {
+        // the forward kept this chunk's logits: elementwise gradient kernel (HBM-bound) instead of the recompute GEMM
+        GradCachedParams cp = {};
+        cp.zc = zc;
+        cp.y = y;
+        cp.y_stride = y_stride;
+        cp.y_vec_ok = (y && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (y_stride * ys) % 16 == 0) ? 1 : 0;
+        cp.row_target = row_target;
+        cp.row_stats = row_stats;
+        cp.n_norm = n_norm;
+        cp.coef = grad_coef;
+        cp.n_rows = n_rows;
+        cp.tau = tau;
+        cp.use_kl = teacher_kind == KD_TEACHER_NONE ? 0 : 1;
+        cp.g_fp16 = g16 ? 1 : 0;
+        cp.R = R;
+        cp.V = V;
+        cp.v0 = v0;
+        cp.cols_pad = n_blks * BN;
+        cp.label_off = v_offset;
+        cp.G = wsp + ws.g_off + b * ws.g_buf_bytes;
+        cp.g_stride = vc;
+        cp.sp = sp_view;
+        TraceScope ts(kTraceGrad, c, s);
+        rc = launch_grad_cached(cp, teacher_kind, y_dtype, tau2, s);
+      } else {
+      TraceScope ts(kTraceGradRecompute, c, s);
       Geom g = {};
       g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = n_blks;
@@ -2076,7 +2552,6 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       gp.label_off = v_offset;
       gp.g_fp16 = g16 ? 1 : 0;
       gp.sp = sp_view;
-      int rc;
       if (teacher_kind == KD_TEACHER_DENSE) {
         rc = y_dtype == KD_DTYPE_BF16
                  ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k[b], g, gp, tau2, s)
@@ -2088,6 +2563,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
                                                                                                    t_g_k[b], g, gp, s);
       } else {
         rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
+      }
       }
       if (rc) return rc;
       if (pipe && check_cuda(cudaEventRecord(pipe->eg[b], s), "record grad")) return 1;
@@ -2104,6 +2580,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       g.n_rows = n_rows;
       g.rows_dim = n_rows ? 2 : 0;  // K runs over rows: stop at the last live k-block
       g.ab_fp16 = g16 ? 1 : 0;
+      g.n_fast = dw_n_fast() ? 1 : 0;  // the h tiles of one vocabulary tile run side by side and share G^T through L2
       StoreParams sp = {};
       if (g16) {
         sp.scale_n_norm = n_norm;
@@ -2121,7 +2598,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       sp.c32 = reinterpret_cast<float*>(dW);
       sp.ld32 = dw_stride;
       sp.row0_32 = v0;
-      if (launch_umma<StoreEpi, true, true>(t_g_mn[b], t_h_mn, g, sp, s_w)) return 1;
+      {
+        TraceScope ts(kTraceDw, c, s_w);
+        if (launch_umma<StoreEpi, true, true>(t_g_mn[b], t_h_mn, g, sp, s_w)) return 1;
+      }
       if (pipe) {
         if (check_cuda(cudaEventRecord(pipe->ew[b], s_w), "record dW")) return 1;
         rec_w[b] = any_w = true;
@@ -2168,7 +2648,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
         sp.c16 = reinterpret_cast<__nv_bfloat16*>(dH);
         sp.ld16 = dh_stride;
       }
-      if (launch_umma<StoreEpi, false, true>(t_g_k[b], g16 ? t_w16_mn : t_w_mn, g, sp, s_h)) return 1;
+      {
+        TraceScope ts(kTraceDh, c, s_h);
+        if (launch_umma<StoreEpi, false, true>(t_g_k[b], g16 ? t_w16_mn : t_w_mn, g, sp, s_h)) return 1;
+      }
       if (pipe) {
         if (check_cuda(cudaEventRecord(pipe->eh[b], s_h), "record dH")) return 1;
         rec_h[b] = any_h = true;
@@ -2190,19 +2673,22 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
 // frozen-vocabulary mask folded into the dW GEMM (dw_row_begin = V_old).  Thin forwards of the general calls.
 extern "C" int kd_ce_fused_linear_fwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                                       const int32_t* row_target, const int32_t* n_rows, int R, int H, int V,
-                                      float* sums, float* row_stats, void* workspace, size_t workspace_bytes,
-                                      void* stream) {
+                                      float* sums, float* row_stats, void* logit_cache, size_t logit_cache_bytes,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
   return kd_fused_linear_fwd(h, h_stride, W, w_stride, KD_TEACHER_NONE, nullptr, 0, 0, nullptr, nullptr, 0, row_target,
-                             n_rows, R, H, V, 1.0f, 1.0f, sums, row_stats, workspace, workspace_bytes, stream);
+                             n_rows, R, H, V, 1.0f, 1.0f, sums, row_stats, logit_cache, logit_cache_bytes, workspace,
+                             workspace_bytes, stream);
 }
 extern "C" int kd_ce_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t w_stride,
                                       const int32_t* row_target, const int32_t* n_rows, const float* row_stats, int R,
                                       int H, int V, const int32_t* n_norm, const float* grad_coef, int grad_dtype,
                                       void* dH, int64_t dh_stride, void* dW, int64_t dw_stride, int64_t dw_row_begin,
-                                      int v_chunk, void* workspace, size_t workspace_bytes, void* stream) {
+                                      int v_chunk, const void* logit_cache, size_t logit_cache_bytes, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   return kd_fused_linear_bwd(h, h_stride, W, w_stride, KD_TEACHER_NONE, nullptr, 0, 0, nullptr, nullptr, 0, row_target,
                              n_rows, row_stats, R, H, V, 1.0f, n_norm, grad_coef, grad_dtype, dH, dh_stride, dW,
-                             dw_stride, dw_row_begin, v_chunk, workspace, workspace_bytes, stream);
+                             dw_stride, dw_row_begin, v_chunk, logit_cache, logit_cache_bytes, workspace,
+                             workspace_bytes, stream);
 }
 
 // out[R, V] (bf16, row stride out_stride) = h[R, H] * W[V, H]^T : the LM head alone, on the K1 pipeline
@@ -2210,6 +2696,7 @@ extern "C" int kd_ce_fused_linear_bwd(const void* h, int64_t h_stride, const voi
 // of the top-k compaction (train.py:60-94, extract_teacher_logits.py:109-129), block of rows by block of rows.
 extern "C" int kd_linear_bf16(const void* h, int64_t h_stride, const void* W, int64_t w_stride, void* out,
                               int64_t out_stride, int R, int H, int V, void* stream) {
+  DeviceGuard device_guard(h);
   if (check_common(h, h_stride, W, w_stride, R, H, V, 1.0f, "kd_linear_bf16")) return 1;
   if (!out) {
     set_error("kd_linear_bf16: null output");
@@ -2235,6 +2722,7 @@ extern "C" int kd_linear_bf16(const void* h, int64_t h_stride, const void* W, in
 
 extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             float* C, int64_t ldc, int M, int N, int K, void* stream) {
+  DeviceGuard device_guard(A);
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) {
     set_error("kd_gemm_bf16: bad arguments");
     return 1;

@@ -95,27 +95,30 @@ __global__ void __launch_bounds__(256) kd_zero_if_empty_kernel(uint4* __restrict
 using namespace kd;
 
 extern "C" int kd_zero_if_empty(void* dst, int64_t bytes, const int32_t* n_rows, void* stream) {
+  kd::DeviceGuard device_guard(dst);
   if (!dst || !n_rows || bytes < 0 || (bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) {
     set_error("kd_zero_if_empty: bad arguments (16-byte aligned buffer and size required)");
     return 1;
   }
   if (bytes == 0) return 0;
   kd_zero_if_empty_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), bytes >> 4, n_rows);
-  return check_cuda(cudaGetLastError(), "kd_zero_if_empty launch");
+  return check_launch("kd_zero_if_empty launch");
 }
 
 extern "C" int kd_compact_rows(const int32_t* row_target, int R, int32_t* perm, int32_t* inv, int32_t* target_c,
                                int32_t* n_valid, void* stream) {
+  kd::DeviceGuard device_guard(row_target);
   if (!row_target || !perm || !inv || !target_c || R <= 0) {
     set_error("kd_compact_rows: bad arguments");
     return 1;
   }
   kd_compact_rows_kernel<<<1, kCompactThreads, 0, (cudaStream_t)stream>>>(row_target, R, perm, inv, target_c, n_valid);
-  return check_cuda(cudaGetLastError(), "kd_compact_rows launch");
+  return check_launch("kd_compact_rows launch");
 }
 
 extern "C" int kd_gather_rows(const void* src, int64_t src_stride_bytes, const int32_t* map, int R, void* dst,
                               int64_t dst_stride_bytes, int64_t row_bytes, int zero_fill, void* stream) {
+  kd::DeviceGuard device_guard(src);
   if (!src || !map || !dst || R <= 0 || row_bytes <= 0) {
     set_error("kd_gather_rows: bad arguments");
     return 1;
@@ -129,5 +132,5 @@ extern "C" int kd_gather_rows(const void* src, int64_t src_stride_bytes, const i
   kd_gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint8_t*>(src), src_stride_bytes, map, R, reinterpret_cast<uint8_t*>(dst),
       dst_stride_bytes, row_bytes, zero_fill, vec_ok ? 1 : 0);
-  return check_cuda(cudaGetLastError(), "kd_gather_rows launch");
+  return check_launch("kd_gather_rows launch");
 }

@@ -1,30 +1,25 @@
 // K2: streaming KD loss + gradient on materialised logits (HBM-bound).
 //
-// Replaces distillation_loss.py:31-128 and its autograd.  One thread-block CLUSTER owns one
-// row (b,t) at a time; each CTA of the cluster streams its slice of the vocabulary from HBM
-// exactly once (16 B loads, L1 bypass), keeps the raw bytes in shared memory, accumulates
-// online soft-max statistics, exchanges the 7 per-row statistics over DSMEM, and then forms
-// the gradient from the shared-memory copy and streams it out.  HBM traffic = read z + read y
-// + write dz (6 B / element for bf16), the algorithmic minimum of SURVEY.md 8(d).
+// Replaces distillation_loss.py:31-128 and its autograd.  One CTA owns one row (b,t) at a time (rows drawn from an
+// atomic counter, ~148 in flight): sweep 1 streams z and y from HBM into the online soft-max statistics, one block
+// reduction gives the row's log-sum-exps, sweep 2 re-reads the row from L2 and streams the gradient out.  HBM traffic
+// = read z + read y + write dz (6 B / element for bf16), the algorithmic minimum of SURVEY.md 8(d).
+// (Round 1 also carried a cluster / shared-memory-stash form and a TMA-ring form; both measured slower - 2210 and
+// 1153 us against 1095 us at the configs[1] shape, profiles/r01e_hbm_bench.log - and were removed.)
 //
 // Per valid row (appendix C of SURVEY.md), all fp32:
 //   student: m, S1 = sum e^{z-m}, St = sum e^{(z-m)/tau}
 //   teacher: mt, T1 = sum e^{y-mt}, Tt = sum e^{(y-mt)/tau}, A = sum e^{(y-mt)/tau} (y - z)
 //   CE = LSE1 - z_l ; KL = A/(tau Tt) - LSEt_tau + LSE_tau ; teacherCE = LSEt1 - y_l
 //   G  = c1 (e^{z-LSE1} - [v=l]) + c2 (e^{z/tau-LSE_tau} - P),  c1 = alpha g/N, c2 = (1-alpha) tau g/N
-#include <cooperative_groups.h>
-
 #include <cstdlib>
 #include <type_traits>
 
 #include "kd_common.cuh"
 #include "kd_umma.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace kd {
 
-constexpr int kStreamThreads = 512;
 constexpr int kMaxTopK = 1024;
 
 struct StreamParams {
@@ -39,9 +34,7 @@ struct StreamParams {
   float tau, alpha, grad_scale;
   const int32_t* n_norm;
   void* dlogits;
-  float* partials;  // [n_clusters][kNumPartialSlots]
-  int stash_elems;  // per CTA, multiple of 8
-  int slice_elems;  // per CTA, multiple of 8
+  float* partials;  // [CTAs][kNumPartialSlots]
   int vec_ok;       // 16-byte vector path legal for every row pointer
 };
 
@@ -69,315 +62,13 @@ __device__ __forceinline__ Stats7 warp_merge(Stats7 s, float inv_tau) {
   return s;
 }
 
-// Shared-memory control block (static part)
-struct StreamShared {
-  Stats7 warp_stats[kStreamThreads / 32];
-  Stats7 cta_stats[2];  // double-buffered by row parity, read by peers over DSMEM
-  float row_consts[8];
-};
-
-template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
-__global__ void __launch_bounds__(kStreamThreads) kd_stream_kernel(const StreamParams p) {
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
-  __shared__ StreamShared sh;
-
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-  const int cluster_id = blockIdx.x / csize;
-  const int n_clusters = gridDim.x / csize;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  TZ* stash_z = reinterpret_cast<TZ*>(dyn_smem);
-  TY* stash_y = reinterpret_cast<TY*>(dyn_smem + (size_t)p.stash_elems * sizeof(TZ));
-  // sparse scratch lives after the stash(es)
-  float* sp_p = reinterpret_cast<float*>(dyn_smem + (size_t)p.stash_elems * (sizeof(TZ) + (DENSE ? sizeof(TY) : 0)));
-  int32_t* sp_i = reinterpret_cast<int32_t*>(sp_p + (DENSE ? 0 : p.K));
-
-  const float inv_tau = 1.0f / p.tau;
-  const int V = p.V;
-  const int lo = min(V, crank * p.slice_elems);
-  const int hi = min(V, lo + p.slice_elems);
-  const int stash_hi = min(hi, lo + p.stash_elems);
-  const bool vec_ok = p.vec_ok != 0;
-  // vector body [lo, vhi), scalar tail [vhi, hi); without alignment everything is tail
-  const int vhi = vec_ok ? lo + ((hi - lo) & ~7) : lo;
-
-  const int n_rows = p.B * p.T;
-  float norm = 0.f;
-  if (GRAD) {
-    const int nn = *p.n_norm;
-    norm = nn > 0 ? p.grad_scale / (float)nn : 0.f;
-  }
-  const float c1 = p.alpha * norm;
-  const float c2 = (1.f - p.alpha) * p.tau * norm;
-
-  double acc_ce = 0.0, acc_kl = 0.0, acc_t = 0.0;
-  int acc_n = 0, acc_hits = 0;
-  int parity = 0;
-
-  for (int row = cluster_id; row < n_rows; row += n_clusters) {
-    const int b = row / p.T, t = row - b * p.T;
-    const int target = p.row_target[row];
-    TZ* out_row = GRAD ? reinterpret_cast<TZ*>(p.dlogits) + (size_t)row * V : nullptr;
-
-    if (target < 0) {  // invalid row: zero gradient, nothing to read (uniform across the cluster)
-      if (GRAD) {
-        if (vec_ok) {
-          const uint4 zero4 = make_uint4(0, 0, 0, 0);
-          constexpr int kPer16 = 16 / sizeof(TZ);
-          for (int i = lo + tid * kPer16; i + kPer16 <= hi; i += kStreamThreads * kPer16) stg_stream(out_row + i, zero4);
-          const int done = lo + ((hi - lo) / kPer16) * kPer16;
-          for (int i = done + tid; i < hi; i += kStreamThreads) out_row[i] = Elem<TZ>::from_f(0.f);
-        } else {
-          for (int i = lo + tid; i < hi; i += kStreamThreads) out_row[i] = Elem<TZ>::from_f(0.f);
-        }
-      }
-      continue;
-    }
-
-    const TZ* zrow = reinterpret_cast<const TZ*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
-    const TY* yrow = DENSE ? reinterpret_cast<const TY*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st : nullptr;
-
-    // ---------------- sweep 1: HBM -> registers -> smem stash, online statistics -------------
-    Stats7 s;
-    s.m = s.mt = -CUDART_INF_F;
-    s.s1 = s.st = s.t1 = s.tt = s.a = 0.f;
-    for (int i = lo + tid * 8; i < vhi; i += kStreamThreads * 8) {
-      Vec8<TZ> vz;
-      vz.load_global(zrow + i);
-      Vec8<TY> vy;
-      if (DENSE) vy.load_global(yrow + i);
-      if (i + 8 <= stash_hi) {
-        vz.store_shared(stash_z + (i - lo));
-        if (DENSE) vy.store_shared(stash_y + (i - lo));
-      }
-      float fz[8], fy[8];
-      vz.unpack(fz);
-      student_update<TAU2, 8>(fz, 8, inv_tau, s.m, s.s1, s.st);
-      if (DENSE) {
-        vy.unpack(fy);
-        teacher_update<TAU2, 8>(fy, fz, 8, inv_tau, s.mt, s.t1, s.tt, s.a);
-      }
-    }
-    for (int i = vhi + tid; i < hi; i += kStreamThreads) {  // scalar tail / unaligned path
-      float fz[8], fy[8];
-      const TZ zr = zrow[i];
-      fz[0] = Elem<TZ>::to_f(zr);
-      if (i < stash_hi) stash_z[i - lo] = zr;
-      student_update<TAU2, 8>(fz, 1, inv_tau, s.m, s.s1, s.st);
-      if (DENSE) {
-        const TY yr = yrow[i];
-        fy[0] = Elem<TY>::to_f(yr);
-        if (i < stash_hi) stash_y[i - lo] = yr;
-        teacher_update<TAU2, 8>(fy, fz, 1, inv_tau, s.mt, s.t1, s.tt, s.a);
-      }
-    }
-
-    // ---------------- block + cluster reduction of the statistics ----------------------------
-    s = warp_merge<DENSE>(s, inv_tau);
-    if (lane == 0) sh.warp_stats[warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      Stats7 w;
-      if (lane < kStreamThreads / 32) {
-        w = sh.warp_stats[lane];
-      } else {
-        w.m = w.mt = -CUDART_INF_F;
-        w.s1 = w.st = w.t1 = w.tt = w.a = 0.f;
-      }
-      w = warp_merge<DENSE>(w, inv_tau);
-      if (lane == 0) sh.cta_stats[parity] = w;
-    }
-
-    // sparse teacher: every CTA needs p_k for its own fix-ups
-    float sp_lk = 0.f;
-    if (!DENSE) {
-      const float* vrow = p.topk_v + (size_t)row * p.K;
-      const int32_t* irow = p.topk_i + (size_t)row * p.K;
-      if (warp == 1) {
-        float vm = -CUDART_INF_F;
-        for (int k = lane; k < p.K; k += 32) vm = fmaxf(vm, vrow[k]);
-        vm = warp_max(vm);
-        float sum = 0.f;
-        for (int k = lane; k < p.K; k += 32) sum += ex2((vrow[k] - vm) * kLog2e * inv_tau);
-        sum = warp_sum(sum);
-        sp_lk = vm * inv_tau + ln_acc(sum);
-        for (int k = lane; k < p.K; k += 32) {
-          sp_p[k] = __expf(vrow[k] * inv_tau - sp_lk);
-          sp_i[k] = irow[k];
-        }
-        if (lane == 0) sh.row_consts[7] = sp_lk;
-      }
-    }
-    cluster.sync();  // cta_stats[parity] of every CTA is visible cluster-wide (also a CTA barrier)
-
-    Stats7 f = sh.cta_stats[parity];
-    if (csize > 1) {
-      f.m = f.mt = -CUDART_INF_F;
-      f.s1 = f.st = f.t1 = f.tt = f.a = 0.f;
-      for (int r = 0; r < csize; ++r) {
-        const Stats7* peer = cluster.map_shared_rank(&sh.cta_stats[parity], r);
-        const Stats7 o = *peer;
-        merge_student(f.m, f.s1, f.st, o.m, o.s1, o.st, inv_tau);
-        if (DENSE) merge_teacher(f.mt, f.t1, f.tt, f.a, o.mt, o.t1, o.tt, o.a, inv_tau);
-      }
-    }
-    parity ^= 1;
-
-    const float lse1 = f.m + ln_acc(f.s1);
-    const float lset = f.m * inv_tau + ln_acc(f.st);
-    float lsett = 0.f;
-    if (DENSE) lsett = f.mt * inv_tau + ln_acc(f.tt);
-    if (!DENSE) sp_lk = sh.row_consts[7];
-
-    // ---------------- per-row scalars (rank 0 only) -------------------------------------------
-    if (crank == 0) {
-      if (DENSE) {
-        if (tid == 0) {
-          const float zl = Elem<TZ>::to_f(zrow[target]);
-          const float yl = Elem<TY>::to_f(yrow[target]);
-          acc_ce += (double)(lse1 - zl);
-          acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
-          acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
-          acc_n += 1;
-        }
-      } else if (warp == 0) {
-        // KL_r = sum_k p_k (log p_k - z_{i_k}/tau) + LSE_tau ; monitor hits (distillation_loss.py:104-116)
-        const float* vrow = p.topk_v + (size_t)row * p.K;
-        float part = 0.f, hsum = 0.f;
-        int hits = 0;
-        for (int k = lane; k < p.K; k += 32) {
-          const int idx = sp_i[k];
-          const float pk = sp_p[k];
-          const float vk = vrow[k];
-          if (idx >= 0 && idx < V) {
-            const float zk = Elem<TZ>::to_f(zrow[idx]);
-            part += pk * ((vk * inv_tau - sp_lk) - zk * inv_tau);
-          }
-          if (idx == target) {
-            hits += 1;
-            hsum += vk;
-          }
-        }
-        part = warp_sum(part);
-        hsum = warp_sum(hsum);
-        hits = __reduce_add_sync(0xffffffffu, hits);
-        if (lane == 0) {
-          const float zl = Elem<TZ>::to_f(zrow[target]);
-          acc_ce += (double)(lse1 - zl);
-          acc_kl += (double)(part + lset);
-          acc_t += (double)hsum;
-          acc_hits += hits;
-          acc_n += 1;
-        }
-      }
-    }
-
-    // ---------------- sweep 2: gradient from the stash, streamed out ---------------------------
-    if (GRAD) {
-      // e^{z-LSE1} = E^2 (tau=2) with E = e^{(z-LSE1)/2};  e^{z/2-LSE_tau} = E * e^{LSE1/2-LSE_tau}
-      const float c_tau = kLog2e * inv_tau;
-      const float off1 = lse1 * kLog2e;            // e^{z-LSE1}
-      const float offt = lset * kLog2e;            // e^{z/tau-LSE_tau}
-      const float offy = lsett * kLog2e;           // e^{y/tau-LSEt_tau}
-      const float half_off1 = off1 * 0.5f;
-      const float k_tau = c2 * ex2(half_off1 - offt);  // tau=2 only
-      auto grad8 = [&](const float(&fz)[8], const float(&fy)[8], int base, int nvalid, float(&g)[8]) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < nvalid) {
-            float gi;
-            if (TAU2) {
-              const float e = ex2(fmaf(fz[i], c_tau, -half_off1));
-              gi = e * fmaf(e, c1, k_tau);
-            } else {
-              gi = c1 * ex2(fmaf(fz[i], kLog2e, -off1)) + c2 * ex2(fmaf(fz[i], c_tau, -offt));
-            }
-            if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
-            g[i] = gi;
-          }
-        }
-        const unsigned d = (unsigned)(target - base);
-        if (d < (unsigned)nvalid) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if ((int)d == i) g[i] -= c1;
-        }
-      };
-      for (int i = lo + tid * 8; i < vhi; i += kStreamThreads * 8) {
-        Vec8<TZ> vz;
-        Vec8<TY> vy;
-        if (i + 8 <= stash_hi) {
-          vz.load_shared(stash_z + (i - lo));
-          if (DENSE) vy.load_shared(stash_y + (i - lo));
-        } else {  // beyond the stash: second read comes from L2
-          vz.load_global(zrow + i);
-          if (DENSE) vy.load_global(yrow + i);
-        }
-        float fz[8], fy[8], g[8];
-        vz.unpack(fz);
-        if (DENSE) vy.unpack(fy);
-        grad8(fz, fy, i, 8, g);
-        Vec8<TZ> vo;
-        vo.pack(g);
-        vo.store_global(out_row + i);
-      }
-      for (int i = vhi + tid; i < hi; i += kStreamThreads) {
-        float fz[8], fy[8], g[8];
-        fz[0] = Elem<TZ>::to_f(i < stash_hi ? stash_z[i - lo] : zrow[i]);
-        if (DENSE) fy[0] = Elem<TY>::to_f(i < stash_hi ? stash_y[i - lo] : yrow[i]);
-        grad8(fz, fy, i, 1, g);
-        out_row[i] = Elem<TZ>::from_f(g[0]);
-      }
-      if (!DENSE) {
-        // scatter part of the sparse gradient: G[i_k] -= c2 * (sum of p_j with i_j == i_k), exact in
-        // fp32 and written once by the CTA that owns the column (after its own sweep-2 stores)
-        __syncthreads();
-        for (int k = tid; k < p.K; k += kStreamThreads) {
-          const int idx = sp_i[k];
-          if (idx < lo || idx >= hi) continue;
-          float ptot = 0.f;
-          bool first = true;
-          for (int j = 0; j < p.K; ++j) {
-            if (sp_i[j] == idx) {
-              ptot += sp_p[j];
-              if (j < k) first = false;
-            }
-          }
-          if (!first) continue;
-          const float zk = Elem<TZ>::to_f(idx < stash_hi ? stash_z[idx - lo] : zrow[idx]);
-          float gi = c1 * ex2(fmaf(zk, kLog2e, -off1)) + c2 * (ex2(fmaf(zk, c_tau, -offt)) - ptot);
-          if (idx == target) gi -= c1;
-          out_row[idx] = Elem<TZ>::from_f(gi);
-        }
-      }
-    }
-    // the stash and sp_* are rewritten by the next row's sweep 1 only after this barrier
-    __syncthreads();
-  }
-
-  // peers may still be reading cta_stats over DSMEM: do not exit before everyone is done
-  cluster.sync();
-  if (crank == 0 && tid == 0) {
-    float* out = p.partials + (size_t)cluster_id * kNumPartialSlots;
-    out[0] = (float)acc_ce;
-    out[1] = (float)acc_kl;
-    out[2] = (float)acc_t;
-    out[3] = (float)acc_n;
-    out[4] = (float)acc_hits;
-    out[5] = out[6] = out[7] = 0.f;
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------
 // K2, row-per-CTA form (default).  One CTA owns a whole row: sweep 1 streams z and y from HBM (16-byte loads,
 // the next 16 elements' loads in flight while 16 are being reduced) into the online statistics, one block
 // reduction gives the row's log-sum-exps, sweep 2 re-reads the row - 612 KB for bf16 z + y, still resident in
 // the 126 MB L2 because only ~148 rows are in flight - and streams the gradient out with evict-first stores.
-// HBM traffic stays at the algorithmic 6 B / element; compared with the cluster form above there is no shared-
-// memory stash, no DSMEM exchange and 8x fewer reductions per row (the cluster form spends ~2/3 of its issued
+// HBM traffic stays at the algorithmic 6 B / element; compared with round 1's cluster form there is no shared-
+// memory stash, no DSMEM exchange and 8x fewer reductions per row (the cluster form spent ~2/3 of its issued
 // instructions on them and is latency-bound at 18 us per row).
 // ------------------------------------------------------------------------------------------
 constexpr int kRowThreadsMax = 1024;
@@ -548,8 +239,10 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
     // ---------------- per-row scalars ----------------
     if (DENSE) {
       if (tid == 0) {
-        const float zl = Elem<TZ>::to_f(zrow[target]);
-        const float yl = Elem<TY>::to_f(yrow[target]);
+        // a label outside [0, V) (the reference's F.cross_entropy asserts on it) poisons the loss instead of reading
+        // out of bounds: NaN is loud and needs no host sync
+        const float zl = target < p.V ? Elem<TZ>::to_f(zrow[target]) : CUDART_NAN_F;
+        const float yl = target < p.V ? Elem<TY>::to_f(yrow[target]) : CUDART_NAN_F;
         acc_ce += (double)(lse1 - zl);
         acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
         acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
@@ -577,7 +270,7 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
       hsum = warp_sum(hsum);
       hits = __reduce_add_sync(0xffffffffu, hits);
       if (lane == 0) {
-        const float zl = Elem<TZ>::to_f(zrow[target]);
+        const float zl = target < p.V ? Elem<TZ>::to_f(zrow[target]) : CUDART_NAN_F;
         acc_ce += (double)(lse1 - zl);
         acc_kl += (double)(part + lset);
         acc_t += (double)hsum;
@@ -693,267 +386,6 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
 }
 
 
-// ------------------------------------------------------------------------------------------
-// K2, ring form: the row-per-CTA algorithm above with the memory side handed to a producer warp.
-//   warp 0       : draws rows from the atomic queue and streams them chunk by chunk (8192 elements of z and of y,
-//                  32 KB) into a 6-stage shared-memory ring with cp.async.bulk (mbarrier complete_tx), first the
-//                  statistics pass (L2 evict_last), then - from L2 - the gradient pass (evict_first); it runs
-//                  ahead of the consumers across pass and row boundaries, so up to 192 KB per SM are in flight
-//                  whatever the consumers are doing
-//   warps 1..16  : consume the stages in order: 16 elements per thread and stage from shared memory (no global-load
-//                  latency, no prefetch registers), statistics in registers across the stages of a row, one block
-//                  reduction per row, then the gradient stages, written with evict-first 16-byte stores.
-// Dense bf16 z and y with 16-byte aligned rows; everything else takes the row form.
-// ------------------------------------------------------------------------------------------
-constexpr int kRingConsumers = 512;
-constexpr int kRingThreads = 32 + kRingConsumers;
-constexpr int kRingChunk = 8192;   // elements per stage and tensor
-constexpr int kRingStages = 6;
-constexpr uint32_t kRingStageBytes = 2u * kRingChunk * 2u;  // z + y, bf16
-
-struct RingHdr {
-  int row, pass, c0, n, target;  // pass: 1 statistics, 2 gradient, 3 zero-fill the row, 0 end of work
-};
-
-struct RingShared {
-  RingHdr hdr[kRingStages];
-  uint64_t full[kRingStages], empty[kRingStages];
-  Stats7 warp_stats[kRingConsumers / 32];
-  Stats7 row_stats;
-};
-
-__device__ __forceinline__ void bulk_load_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar,
-                                               uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_dst),
-      "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy)
-      : "memory");
-}
-
-template <bool TAU2, bool GRAD>
-__global__ void __launch_bounds__(kRingThreads, 1) kd_stream_ring_kernel(const StreamParams p, int* __restrict__ row_counter) {
-  using namespace umma;
-  using T = __nv_bfloat16;
-  extern __shared__ __align__(128) uint8_t ring_smem[];
-  __shared__ RingShared sh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int V = p.V, n_rows = p.B * p.T;
-  const uint32_t ring0 = smem_u32(ring_smem);
-  auto full_bar = [&](int s) { return smem_u32(&sh.full[s]); };
-  auto empty_bar = [&](int s) { return smem_u32(&sh.empty[s]); };
-
-  if (tid == 0) {
-    for (int s = 0; s < kRingStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), kRingConsumers / 32);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == 0) {
-    // ======================= producer =======================
-    if (lane == 0) {
-      const uint64_t pol_keep = GRAD ? l2_policy_evict_last() : l2_policy_evict_first();
-      const uint64_t pol_drop = l2_policy_evict_first();
-      int s = 0;
-      uint32_t phase = 0;
-      auto publish = [&](const RingHdr& h, const T* zsrc, const T* ysrc, uint64_t pol) {
-        mbar_wait(empty_bar(s), phase ^ 1u);
-        sh.hdr[s] = h;
-        if (zsrc != nullptr) {
-          const uint32_t bytes = (uint32_t)h.n * 2u;
-          mbar_expect_tx(full_bar(s), 2u * bytes);
-          const uint32_t dst = ring0 + (uint32_t)s * kRingStageBytes;
-          bulk_load_hint(dst, zsrc, bytes, full_bar(s), pol);
-          bulk_load_hint(dst + kRingChunk * 2u, ysrc, bytes, full_bar(s), pol);
-        } else {
-          mbar_arrive(full_bar(s));
-        }
-        if (++s == kRingStages) {
-          s = 0;
-          phase ^= 1u;
-        }
-      };
-      for (;;) {
-        const int row = atomicAdd(row_counter, 1);
-        if (row >= n_rows) break;
-        const int target = p.row_target[row];
-        RingHdr h = {row, 0, 0, 0, target};
-        if (target < 0) {
-          if (GRAD) {
-            h.pass = 3;
-            publish(h, nullptr, nullptr, 0);
-          }
-          continue;
-        }
-        const int b = row / p.T, t = row - b * p.T;
-        const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
-        const T* yrow = reinterpret_cast<const T*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st;
-        for (int pass = 1; pass <= (GRAD ? 2 : 1); ++pass) {
-          for (int c0 = 0; c0 < V; c0 += kRingChunk) {
-            h.pass = pass;
-            h.c0 = c0;
-            h.n = V - c0 < kRingChunk ? V - c0 : kRingChunk;
-            publish(h, zrow + c0, yrow + c0, pass == 1 ? pol_keep : pol_drop);
-          }
-        }
-      }
-      RingHdr end = {-1, 0, 0, 0, -1};
-      publish(end, nullptr, nullptr, 0);
-    }
-    return;
-  }
-
-  // ======================= consumers =======================
-  const int ctid = tid - 32, cwarp = warp - 1;
-  const float inv_tau = 1.0f / p.tau;
-  float norm = 0.f;
-  if (GRAD) {
-    const int nn = *p.n_norm;
-    norm = nn > 0 ? p.grad_scale / (float)nn : 0.f;
-  }
-  const float c1 = p.alpha * norm;
-  const float c2 = (1.f - p.alpha) * p.tau * norm;
-  const float c_tau = kLog2e * inv_tau;
-  double acc_ce = 0.0, acc_kl = 0.0, acc_t = 0.0;
-  int acc_n = 0;
-  Stats7 st;
-  float half_off1 = 0.f, off1 = 0.f, offt = 0.f, offy = 0.f, k_tau = 0.f;  // row constants of the gradient pass
-  int s = 0;
-  uint32_t phase = 0;
-  for (;;) {
-    mbar_wait(full_bar(s), phase);
-    const RingHdr h = sh.hdr[s];
-    if (h.pass == 0) break;
-    T* out_row = GRAD ? reinterpret_cast<T*>(p.dlogits) + (size_t)h.row * V : nullptr;
-    if (h.pass == 3) {  // row without a score: zero gradient, nothing was loaded
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(s));
-      const uint4 zero4 = make_uint4(0, 0, 0, 0);
-      for (int i = ctid; i < V / 8; i += kRingConsumers) stg_stream(out_row + (size_t)i * 8, zero4);
-    } else {
-      // this thread's two 16-byte pieces of the stage: [8 ctid, +8) and [8 (ctid + 512), +8)
-      const uint32_t zb = ring0 + (uint32_t)s * kRingStageBytes, yb = zb + kRingChunk * 2u;
-      const int e0 = ctid * 8, e1 = (ctid + kRingConsumers) * 8;
-      const int nv = (e0 < h.n ? 8 : 0) + (e1 < h.n ? 8 : 0);  // h.n is a multiple of 8
-      Vec8<T> z0, z1, y0, y1;
-      z0.a = z1.a = y0.a = y1.a = make_uint4(0, 0, 0, 0);
-      if (nv >= 8) {
-        z0.a = lds128(zb + (uint32_t)e0 * 2u);
-        y0.a = lds128(yb + (uint32_t)e0 * 2u);
-      }
-      if (nv == 16) {
-        z1.a = lds128(zb + (uint32_t)e1 * 2u);
-        y1.a = lds128(yb + (uint32_t)e1 * 2u);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(s));  // the stage's bytes are in registers: hand it back
-      if (h.pass == 1) {
-        if (h.c0 == 0) {
-          st.m = st.mt = -CUDART_INF_F;
-          st.s1 = st.st = st.t1 = st.tt = st.a = 0.f;
-        }
-        if (nv > 0) {
-          float fz[16], fy[16], t8[8];
-          z0.unpack(t8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) fz[j] = t8[j];
-          y0.unpack(t8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) fy[j] = t8[j];
-          z1.unpack(t8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) fz[8 + j] = t8[j];
-          y1.unpack(t8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) fy[8 + j] = t8[j];
-          student_update<TAU2, 16>(fz, nv, inv_tau, st.m, st.s1, st.st);
-          teacher_update<TAU2, 16>(fy, fz, nv, inv_tau, st.mt, st.t1, st.tt, st.a);
-        }
-        if (h.c0 + h.n >= V) {  // last stage of the statistics pass: block reduction, row scalars
-          Stats7 w = warp_merge<true>(st, inv_tau);
-          if (lane == 0) sh.warp_stats[cwarp] = w;
-          named_bar_sync(1, kRingConsumers);
-          if (cwarp == 0) {
-            Stats7 x;
-            if (lane < kRingConsumers / 32) {
-              x = sh.warp_stats[lane];
-            } else {
-              x.m = x.mt = -CUDART_INF_F;
-              x.s1 = x.st = x.t1 = x.tt = x.a = 0.f;
-            }
-            x = warp_merge<true>(x, inv_tau);
-            if (lane == 0) sh.row_stats = x;
-          }
-          named_bar_sync(2, kRingConsumers);
-          const Stats7 f = sh.row_stats;
-          const float lse1 = f.m + ln_acc(f.s1);
-          const float lset = f.m * inv_tau + ln_acc(f.st);
-          const float lsett = f.mt * inv_tau + ln_acc(f.tt);
-          if (ctid == 0) {
-            const int b = h.row / p.T, t = h.row - b * p.T;
-            const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_sb + (int64_t)t * p.z_st;
-            const T* yrow = reinterpret_cast<const T*>(p.y) + (int64_t)b * p.y_sb + (int64_t)t * p.y_st;
-            const float zl = __bfloat162float(zrow[h.target]);
-            const float yl = __bfloat162float(yrow[h.target]);
-            acc_ce += (double)(lse1 - zl);
-            acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
-            acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
-            acc_n += 1;
-          }
-          off1 = lse1 * kLog2e;
-          offt = lset * kLog2e;
-          offy = lsett * kLog2e;
-          half_off1 = 0.5f * off1;
-          k_tau = c2 * ex2(half_off1 - offt);
-        }
-      } else if (GRAD) {  // h.pass == 2
-        auto grad8 = [&](const Vec8<T>& vz, const Vec8<T>& vy, int base) {
-          float fz[8], fy[8], g[8];
-          vz.unpack(fz);
-          vy.unpack(fy);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float gi;
-            if (TAU2) {
-              const float e = ex2(fmaf(fz[i], c_tau, -half_off1));
-              gi = e * fmaf(e, c1, k_tau);
-            } else {
-              gi = c1 * ex2(fmaf(fz[i], kLog2e, -off1)) + c2 * ex2(fmaf(fz[i], c_tau, -offt));
-            }
-            g[i] = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
-          }
-          const unsigned d = (unsigned)(h.target - base);
-          if (d < 8u) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((int)d == i) g[i] -= c1;
-          }
-          Vec8<T> vo;
-          vo.pack(g);
-          vo.store_global(out_row + base);
-        };
-        if (nv >= 8) grad8(z0, y0, h.c0 + e0);
-        if (nv == 16) grad8(z1, y1, h.c0 + e1);
-      }
-    }
-    if (++s == kRingStages) {
-      s = 0;
-      phase ^= 1u;
-    }
-  }
-  if (ctid == 0) {
-    float* out = p.partials + (size_t)blockIdx.x * kNumPartialSlots;
-    out[0] = (float)acc_ce;
-    out[1] = (float)acc_kl;
-    out[2] = (float)acc_t;
-    out[3] = (float)acc_n;
-    out[4] = out[5] = out[6] = out[7] = 0.f;
-  }
-}
-
 // deterministic fixed-order reduction of the per-cluster partial records -> sums[8]
 __global__ void kd_reduce_partials_kernel(const float* __restrict__ partials, int n, float* __restrict__ sums) {
   __shared__ double sm[kNumPartialSlots][33];
@@ -971,7 +403,7 @@ __global__ void kd_reduce_partials_kernel(const float* __restrict__ partials, in
 
 int reduce_partials(const float* partials, int n, float* sums, cudaStream_t stream) {
   kd_reduce_partials_kernel<<<1, 32 * kNumPartialSlots, 0, stream>>>(partials, n, sums);
-  return check_cuda(cudaGetLastError(), "kd_reduce_partials launch");
+  return check_launch("kd_reduce_partials launch");
 }
 
 __global__ void kd_prepare_rows_kernel(const int64_t* __restrict__ labels, const uint8_t* __restrict__ mask, int B,
@@ -984,7 +416,11 @@ __global__ void kd_prepare_rows_kernel(const int64_t* __restrict__ labels, const
     const int b = r / T, t = r - b * T;
     int64_t l = 0;
     const bool ok = row_is_valid(labels, mask, T, b, t, ignore_index, &l);
-    if (row_target) row_target[r] = ok ? (int32_t)l : -1;
+    // a scored row whose label is not a vocabulary index (negative but not ignore_index, or beyond int32) keeps
+    // counting as valid - as in the reference, whose cross_entropy then fails - and gets a target no vocabulary
+    // holds: every kernel turns that into a NaN loss instead of a silently wrong one
+    const int32_t tgt = (l < 0 || l > 0x7ffffffe) ? 0x7fffffff : (int32_t)l;
+    if (row_target) row_target[r] = ok ? tgt : -1;
     cnt += ok ? 1 : 0;
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -1054,16 +490,6 @@ __global__ void kd_zero_rows_kernel(T* __restrict__ x, int64_t n) {
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxClusters = 1024;
 
-// KD_STREAM=cluster selects the cluster / shared-memory-stash form; the row-per-CTA form is the default
-static bool stream_row_form() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("KD_STREAM");
-    v = (e && e[0] == 'c') ? 0 : 1;
-  }
-  return v != 0;
-}
-
 static int stream_row_threads() {
   static int v = 0;
   if (v == 0) {
@@ -1099,9 +525,8 @@ template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowTh
 static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream, int ctas_per_sm) {
   StreamParams p = p0;
   auto kern = kd_stream_row_kernel<TZ, TY, DENSE, TAU2, GRAD, kRowThreads>;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device_slot());
   const int n_rows = p.B * p.T;
   static int per_sm_env = -1;
   if (per_sm_env < 0) {
@@ -1117,116 +542,13 @@ static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream, int
   if (check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), stream), "row counter")) return 1;
   const size_t dyn = DENSE ? 0 : (size_t)p.K * 8;
   kern<<<grid, kRowThreads, dyn, stream>>>(p, counter);
-  if (check_cuda(cudaGetLastError(), "kd_stream_row launch")) return 1;
-  return reduce_partials(p.partials, grid, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
-}
-
-// KD_STREAM=ring selects the ring form where it applies (dense bf16, aligned rows).  It is NOT the default: on
-// B200 it measures 5 % slower than the row form at the configs[1] shape (1153 vs 1093 us; forward only 760 vs
-// 601 us) - with the loads out of the way the 16 consumer warps are bound by the XU pipe (4 ex2 per element =
-// 0.56 ms for the whole problem at 16 / clk / SM, as much as the 0.57 ms the HBM needs) and by instruction issue,
-// and the row form's second CTA-free design already overlaps its loads well enough.
-static bool stream_ring_form() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("KD_STREAM");
-    v = (e && e[0] == 'r' && e[1] == 'i') ? 1 : 0;
-  }
-  return v != 0;
-}
-
-template <bool TAU2, bool GRAD>
-static int launch_stream_ring(const StreamParams& p0, cudaStream_t stream) {
-  StreamParams p = p0;
-  auto kern = kd_stream_ring_kernel<TAU2, GRAD>;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_rows = p.B * p.T;
-  int grid = sms < n_rows ? sms : n_rows;
-  if (grid > kMaxClusters) grid = kMaxClusters;
-  int* counter = reinterpret_cast<int*>(p.partials + (size_t)(kMaxClusters + 1) * kNumPartialSlots);
-  if (check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), stream), "row counter")) return 1;
-  const size_t dyn = (size_t)kRingStages * kRingStageBytes + 128;
-  static bool attr_set[4] = {false, false, false, false};
-  const int which = (TAU2 ? 2 : 0) + (GRAD ? 1 : 0);
-  if (!attr_set[which]) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "ring smem attr"))
-      return 1;
-    attr_set[which] = true;
-  }
-  kern<<<grid, kRingThreads, dyn, stream>>>(p, counter);
-  if (check_cuda(cudaGetLastError(), "kd_stream_ring launch")) return 1;
+  if (check_launch("kd_stream_row launch")) return 1;
   return reduce_partials(p.partials, grid, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
 }
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
 static int launch_stream(const StreamParams& p0, cudaStream_t stream) {
-  if (stream_row_form()) {
-    if (DENSE && std::is_same<TZ, __nv_bfloat16>::value && std::is_same<TY, __nv_bfloat16>::value && p0.vec_ok &&
-        p0.V % 8 == 0 && stream_ring_form())
-      return launch_stream_ring<TAU2, GRAD>(p0, stream);
-    return launch_stream_rows<TZ, TY, DENSE, TAU2, GRAD>(p0, stream);
-  }
-  StreamParams p = p0;
-  auto kern = kd_stream_kernel<TZ, TY, DENSE, TAU2, GRAD>;
-  int dev = 0, sms = 0, max_optin = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-
-  const size_t bytes_per_elem = sizeof(TZ) + (DENSE ? sizeof(TY) : 0);
-  const size_t sparse_bytes = DENSE ? 0 : (size_t)p.K * 8 + 16;
-  const size_t static_bytes = sizeof(StreamShared) + 64;
-  // Cluster size: smallest power of two <= 8 whose per-CTA slice fits in half an SM's shared
-  // memory (two CTAs per SM overlap one CTA's reduction bubbles with the other's streaming);
-  // else 8 with as much stash as fits, the rest of the slice is re-read through L2.
-  const size_t half_sm = (size_t)(max_optin - 2048) / 2 - static_bytes - sparse_bytes;
-  const size_t full_sm = (size_t)max_optin - static_bytes - sparse_bytes - 1024;
-  int csize = 8;
-  const int v8 = (p.V + 7) / 8;
-  for (int c = 1; c <= 8; c *= 2) {
-    const size_t slice = (size_t)((v8 + c - 1) / c) * 8;
-    if (slice * bytes_per_elem <= half_sm) {
-      csize = c;
-      break;
-    }
-  }
-  p.slice_elems = ((v8 + csize - 1) / csize) * 8;
-  size_t stash = (size_t)p.slice_elems;
-  if (stash * bytes_per_elem > half_sm) {
-    // does it fit with one CTA per SM?
-    if (stash * bytes_per_elem > full_sm) stash = (full_sm / bytes_per_elem) & ~(size_t)7;
-  }
-  p.stash_elems = (int)stash;
-  const size_t dyn = stash * bytes_per_elem + sparse_bytes;
-  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "smem attr"))
-    return 1;
-
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kStreamThreads);
-  cfg.dynamicSmemBytes = dyn;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = csize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cfg.gridDim = dim3(csize);
-  int max_clusters = 0;
-  if (check_cuda(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg), "cluster occupancy")) return 1;
-  if (max_clusters < 1) {
-    set_error("kd_stream: no cluster of %d CTAs with %zu B shared memory fits on this device", csize, dyn);
-    return 1;
-  }
-  const int n_rows = p.B * p.T;
-  int n_clusters = max_clusters < n_rows ? max_clusters : n_rows;
-  if (n_clusters > kMaxClusters) n_clusters = kMaxClusters;
-  cfg.gridDim = dim3(n_clusters * csize);
-  if (check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "kd_stream launch")) return 1;
-  return reduce_partials(p.partials, n_clusters, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);
+  return launch_stream_rows<TZ, TY, DENSE, TAU2, GRAD>(p0, stream);
 }
 
 template <typename TZ, typename TY, bool DENSE>
@@ -1304,27 +626,30 @@ extern "C" size_t kd_stream_workspace_bytes(void) {
 
 extern "C" int kd_prepare_rows(const int64_t* labels, const uint8_t* mask, int B, int T, int64_t ignore_index,
                                int32_t* row_target, int32_t* n_valid, void* stream) {
+  DeviceGuard device_guard(labels);
   if (labels == nullptr || n_valid == nullptr || B <= 0 || T <= 0) {
     set_error("kd_prepare_rows: bad arguments");
     return 1;
   }
   kd_prepare_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(labels, mask, B, T, ignore_index, row_target, n_valid);
-  return check_cuda(cudaGetLastError(), "kd_prepare_rows launch");
+  return check_launch("kd_prepare_rows launch");
 }
 
 extern "C" int kd_finalize_losses(const float* sums, float tau, float alpha, int sparse, float* losses, void* stream) {
+  DeviceGuard device_guard(sums);
   if (!sums || !losses) {
     set_error("kd_finalize_losses: null pointer");
     return 1;
   }
   kd_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, tau, alpha, sparse, losses);
-  return check_cuda(cudaGetLastError(), "kd_finalize launch");
+  return check_launch("kd_finalize launch");
 }
 
 extern "C" int kd_dense_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b, int64_t z_stride_t, const void* y,
                                 int y_dtype, int64_t y_stride_b, int64_t y_stride_t, const int32_t* row_target, int B,
                                 int T, int V, float tau, float alpha, const int32_t* n_norm, float grad_scale,
                                 float* sums, void* dlogits, void* workspace, size_t workspace_bytes, void* stream) {
+  DeviceGuard device_guard(z);
   if (!z || !y || !row_target || !sums || (dlogits && !n_norm)) {
     set_error("kd_dense_fwd_bwd: null pointer argument");
     return 1;
@@ -1343,6 +668,7 @@ extern "C" int kd_sparse_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b,
                                  const float* topk_v, const int32_t* topk_i, int K, const int32_t* row_target, int B,
                                  int T, int V, float tau, float alpha, const int32_t* n_norm, float grad_scale,
                                  float* sums, void* dlogits, void* workspace, size_t workspace_bytes, void* stream) {
+  DeviceGuard device_guard(z);
   if (!z || !topk_v || !topk_i || !row_target || !sums || (dlogits && !n_norm)) {
     set_error("kd_sparse_fwd_bwd: null pointer argument");
     return 1;
@@ -1363,6 +689,7 @@ extern "C" int kd_sparse_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b,
 }
 
 extern "C" int kd_scale_inplace(void* x, int dtype, int64_t n, const float* scale, void* stream) {
+  DeviceGuard device_guard(x);
   if (!x || !scale || n < 0) {
     set_error("kd_scale_inplace: bad arguments");
     return 1;
@@ -1378,10 +705,11 @@ extern "C" int kd_scale_inplace(void* x, int dtype, int64_t n, const float* scal
     case KD_DTYPE_F16: kd_scale_kernel<__half><<<blocks, threads, 0, s>>>((__half*)x, n, scale); break;
     default: set_error("kd_scale_inplace: unsupported dtype code %d", dtype); return 1;
   }
-  return check_cuda(cudaGetLastError(), "kd_scale launch");
+  return check_launch("kd_scale launch");
 }
 
 extern "C" int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stream) {
+  DeviceGuard device_guard(grad);
   if (!grad || old_vocab < 0 || H <= 0) {
     set_error("kd_mask_rows: bad arguments");
     return 1;

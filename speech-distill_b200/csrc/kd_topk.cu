@@ -415,6 +415,7 @@ using namespace kd;
 
 extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k, void* out_v,
                                 int32_t* out_i, void* stream) {
+  kd::DeviceGuard device_guard(logits);
   if (!logits || !out_v || !out_i) {
     set_error("kd_topk_logprobs: null pointer argument");
     return 1;
@@ -472,5 +473,5 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   }
 #undef KD_TOPK_DISPATCH
 #undef KD_TOPK_LAUNCH
-  return check_cuda(cudaGetLastError(), "kd_topk launch");
+  return check_launch("kd_topk launch");
 }

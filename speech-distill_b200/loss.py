@@ -182,6 +182,23 @@ def _fused_workspace(R, H, V, v_chunk, device, K=0):
     return _workspace(lib.kd_fused_workspace_bytes(R, H, V, int(v_chunk), int(K)), device)
 
 
+def logit_cache_budget(mb=None):
+    """Bytes the forward may spend on the logit cache (include/kd_b200.h, "Logit cache"): a constant chosen by the
+    caller - ``mb`` megabytes, else KD_LOGIT_CACHE_MB, else 1536 - never a function of V."""
+    import os
+
+    if mb is None:
+        mb = float(os.environ.get("KD_LOGIT_CACHE_MB", "1536"))
+    return max(int(mb * (1 << 20)), 0)
+
+
+def alloc_logit_cache(R, V, v_chunk, device, mb=None):
+    """uint8 buffer for the encoded logits of the first vocabulary chunks (None when the budget holds none)."""
+    lib = _lib.load()
+    nbytes = lib.kd_fused_logit_cache_bytes(int(R), int(V), int(v_chunk), logit_cache_budget(mb))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
 def _teacher_kind(y, topk):
     if y is not None:
         return _lib.KD_TEACHER_DENSE
@@ -217,9 +234,9 @@ def gather_rows(src, row_map, zero_fill=True):
     return out
 
 
-def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None, n_rows=None):
+def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None, n_rows=None, cache=None):
     """topk = (v fp32 [R,K], i int32 [R,K]) for the sparse teacher, else None; n_rows = device count of live
-    (compacted) rows or None."""
+    (compacted) rows or None; cache = logit-cache buffer (alloc_logit_cache) the backward will read, or None."""
     lib = _lib.load()
     R, H = h.shape
     V = W.shape[0]
@@ -233,7 +250,8 @@ def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None, n_rows=N
         h.data_ptr(), h.stride(0), W.data_ptr(), W.stride(0), teacher_kind,
         _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
         _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), _ptr(n_rows), R, H, V,
-        float(tau), float(alpha), sums.data_ptr(), row_stats.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        float(tau), float(alpha), sums.data_ptr(), row_stats.data_ptr(), _ptr(cache),
+        cache.numel() if cache is not None else 0, ws.data_ptr(), ws.numel(), stream_ptr(dev))
     check(rc, "kd_fused_linear_fwd")
     return sums, row_stats, ws
 
@@ -241,7 +259,7 @@ def _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk=None, n_rows=N
 class _KDFusedLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype,
-                topk_v=None, topk_i=None, grad_sync=None, compact=False):
+                topk_v=None, topk_i=None, grad_sync=None, compact=False, cache_mb=None):
         inv = n_rows = None
         if compact:  # valid rows to the front; every GEMM tile behind them is skipped (kd_rows.cu)
             perm, inv, row_target, n_rows = compact_rows(row_target)
@@ -252,7 +270,10 @@ class _KDFusedLinear(torch.autograd.Function):
                 topk_v, topk_i = gather_rows(topk_v, perm), gather_rows(topk_i, perm)
         topk = (topk_v, topk_i) if topk_v is not None else None
         teacher_kind = _teacher_kind(y, topk)
-        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk, n_rows)
+        cache = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:  # a backward will follow: keep the logits it needs
+            cache = alloc_logit_cache(h.shape[0], W.shape[0], v_chunk, h.device, cache_mb)
+        sums, row_stats, ws = _fused_forward(h, W, y, row_target, tau, alpha, v_chunk, topk, n_rows, cache)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
         eff_alpha = alpha if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
@@ -261,6 +282,7 @@ class _KDFusedLinear(torch.autograd.Function):
         ctx.cfg = (tau, eff_alpha, teacher_kind, int(dw_row_begin), int(v_chunk), grad_dtype)
         ctx.save_for_backward(h, W, y, row_target, row_stats, n_norm, topk_v, topk_i, inv, n_rows)
         ctx.ws = ws
+        ctx.cache = cache
         ctx.grad_sync = grad_sync
         total, task, distill, teacher = losses.unbind(0)
         ctx.mark_non_differentiable(teacher)
@@ -279,15 +301,15 @@ class _KDFusedLinear(torch.autograd.Function):
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
         dH, dW = _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin,
                                  v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk,
-                                 ctx.grad_sync, n_rows=n_rows)
+                                 ctx.grad_sync, n_rows=n_rows, cache=ctx.cache)
         if inv is not None and dH is not None:
             dH = gather_rows(dH, inv)  # back to the original row order; rows that are not scored get zeros
-        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None, None, None
+        return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin, v_chunk,
                     grad_dtype, need_h, need_w, ws=None, topk=None, grad_sync=None, v_offset=0, dh_fp32=False,
-                    n_rows=None):
+                    n_rows=None, cache=None):
     """kd_fused_linear_bwd, or - with ``grad_sync`` (dist.GradSync) - kd_fused_linear_bwd_range over a few
     vocabulary ranges, handing each finished dW row block to the all-reduce while the next range runs."""
     lib = _lib.load()
@@ -319,8 +341,8 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
             _ptr(y), dtype_code(y.dtype) if y is not None else 0, y.stride(0) if y is not None else 0,
             _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), _ptr(n_rows),
             row_stats.data_ptr(), R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), gcode, _ptr(dH), H, _ptr(dW), H,
-            int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), int(v_offset), ws.data_ptr(),
-            ws.numel(), stream_ptr(dev))
+            int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), int(v_offset), _ptr(cache),
+            cache.numel() if cache is not None else 0, ws.data_ptr(), ws.numel(), stream_ptr(dev))
         check(rc, "kd_fused_linear_bwd_range")
         if grad_sync is not None and need_w:
             grad_sync.reduce_rows(dW, max(v0, int(dw_row_begin)), v1)
@@ -332,7 +354,7 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
 def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                                    temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
                                    grad_dtype=torch.float32, teacher_top_k_v=None, teacher_top_k_i=None,
-                                   compact_rows=None):
+                                   compact_rows=None, logit_cache_mb=None):
     """Forward + backward in one call, outside autograd: returns (losses[4] fp32, dHidden, dWeight) with the
     gradients of ``total`` in ``grad_dtype``.  fp32 exposes the kernels' accumulators before the final
     rounding to bf16 that autograd imposes on bf16 leaves (used by the parity tests and by callers that keep
@@ -340,12 +362,14 @@ def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logit
     with torch.no_grad():
         out = fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits, speech_token_mask, temperature,
                                    alpha, ignore_index, dw_row_begin, v_chunk, teacher_top_k_v=teacher_top_k_v,
-                                   teacher_top_k_i=teacher_top_k_i, compact_rows=compact_rows, _return_ctx=True)
+                                   teacher_top_k_i=teacher_top_k_i, compact_rows=compact_rows,
+                                   logit_cache_mb=logit_cache_mb, _return_ctx=True)
     losses, saved = out
-    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk, inv, n_rows = saved
+    h2, W, y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk, inv, n_rows, cache = saved
     coef = torch.tensor([eff_alpha, 1.0 - eff_alpha], dtype=torch.float32, device=h2.device)
     dH, dW = _fused_backward(h2, W, y, row_target, row_stats, n_norm, coef, float(temperature), teacher_kind,
-                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True, None, topk, n_rows=n_rows)
+                             int(dw_row_begin), int(v_chunk), grad_dtype, True, True, None, topk, n_rows=n_rows,
+                             cache=cache)
     if inv is not None:
         dH = gather_rows(dH, inv)
     return losses, dH.view(hidden.shape), dW
@@ -354,7 +378,8 @@ def fused_linear_kd_value_and_grad(hidden, lm_head_weight, labels, teacher_logit
 def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, speech_token_mask=None,
                          temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX, dw_row_begin=0, v_chunk=0,
                          reduce_fn=None, count_reduce_fn=None, grad_dtype=torch.bfloat16, teacher_top_k_v=None,
-                         teacher_top_k_i=None, grad_sync=None, compact_rows=None, _return_ctx=False):
+                         teacher_top_k_i=None, grad_sync=None, compact_rows=None, logit_cache_mb=None,
+                         _return_ctx=False):
     """``DistillationLoss(student_logits = hidden @ lm_head_weight.T, ...)`` without the logits.
 
     hidden [B,T,H] (or [R,H] with labels [.., T]) bf16, lm_head_weight [V,H] bf16, labels [B,T].
@@ -369,6 +394,9 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     (the reference's boolean row gather, distillation_loss.py:37-45, without its host sync).  Default (None):
     on for the top-k cache and for plain CE, where only [R,H] / [R,K] rows move; off for a dense teacher, whose
     [R,V] rows would have to be copied (worth it from roughly 15 % ignored rows on: pass True).
+    ``logit_cache_mb``: budget of the forward's logit cache (None = KD_LOGIT_CACHE_MB or 1536 MB, 0 = off).  The
+    cache is a constant-size buffer, independent of V: vocabulary chunks that fit are differentiated from the cached
+    logits by an HBM-bound kernel beside the dW / dH GEMMs, the rest is recomputed on the tensor cores.
     ``reduce_fn`` / ``count_reduce_fn`` / ``grad_sync``: token-shard data-parallel hooks (dist.py): all-reduce of
     the sums record and of the valid-row count, and the dW all-reduce overlapped with the backward
     (the weight gradient autograd receives is then already summed over ranks).
@@ -426,16 +454,18 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
                 y = gather_rows(y, perm, zero_fill=False)
             if topk is not None:
                 topk = (gather_rows(topk[0], perm), gather_rows(topk[1], perm))
+        cache = alloc_logit_cache(hd.shape[0], V, v_chunk, dev, logit_cache_mb)
         sums, row_stats, _ = _fused_forward(hd, W.detach(), y, row_target, float(temperature), float(alpha), v_chunk,
-                                            topk, n_rows)
+                                            topk, n_rows, cache)
         if reduce_fn is not None:
             sums = reduce_fn(sums)
         eff_alpha = float(alpha) if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
         losses = finalize_losses(sums, temperature, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
-        return losses, (hd, W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk, inv, n_rows)
+        return losses, (hd, W.detach(), y, row_target, row_stats, n_norm, teacher_kind, eff_alpha, topk, inv, n_rows,
+                        cache)
     out = _KDFusedLinear.apply(h2, W, y, row_target, n_valid, n_norm, float(temperature), float(alpha),
                                int(dw_row_begin), int(v_chunk), reduce_fn, grad_dtype, topk_v, topk_i, grad_sync,
-                               compact)
+                               compact, logit_cache_mb)
     return out
 
 

@@ -18,7 +18,8 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, dtype_code, require_cuda, stream_ptr
-from .loss import (IGNORE_INDEX, _fused_backward, _fused_workspace, _ptr, _teacher_kind, _workspace, finalize_losses,
+from .loss import (IGNORE_INDEX, _fused_backward, _fused_workspace, _ptr, _teacher_kind, _workspace, alloc_logit_cache,
+                   finalize_losses,
                    prepare_rows)
 
 RANK_REC_FLOATS = 12  # kRankRecFloats of csrc/kd_fused.cu
@@ -41,7 +42,7 @@ def vocab_slices(V, world, align=256):
     return out
 
 
-def forward_partial(h2, W_slice, y_slice, topk, row_target, v_offset, tau, v_chunk=0):
+def forward_partial(h2, W_slice, y_slice, topk, row_target, v_offset, tau, v_chunk=0, cache=None):
     """kd_fused_linear_fwd_partial: the slice's per-row record [R, 12] (fp32)."""
     lib = _lib.load()
     R, H = h2.shape
@@ -56,7 +57,8 @@ def forward_partial(h2, W_slice, y_slice, topk, row_target, v_offset, tau, v_chu
         _ptr(y_slice), dtype_code(y_slice.dtype) if y_slice is not None else 0,
         y_slice.stride(0) if y_slice is not None else 0,
         _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), 0, R, H, V, int(v_offset),
-        float(tau), rec.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev))
+        float(tau), rec.data_ptr(), _ptr(cache), cache.numel() if cache is not None else 0, ws.data_ptr(), ws.numel(),
+        stream_ptr(dev))
     check(rc, "kd_fused_linear_fwd_partial")
     return rec, ws
 
@@ -100,7 +102,10 @@ class _KDVocabParallel(torch.autograd.Function):
                 gather_fn, reduce_fn):
         topk = (topk_v, topk_i) if topk_v is not None else None
         teacher_kind = _teacher_kind(y_slice, topk)
-        rec, ws = forward_partial(h, W_slice, y_slice, topk, row_target, v_offset, tau, v_chunk)
+        cache = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            cache = alloc_logit_cache(h.shape[0], W_slice.shape[0], v_chunk, h.device)
+        rec, ws = forward_partial(h, W_slice, y_slice, topk, row_target, v_offset, tau, v_chunk, cache)
         sums, row_stats = merge_ranks(gather_fn(rec), row_target, teacher_kind, tau)
         eff_alpha = alpha if teacher_kind != _lib.KD_TEACHER_NONE else 1.0
         losses = finalize_losses(sums, tau, eff_alpha, teacher_kind == _lib.KD_TEACHER_SPARSE)
@@ -108,6 +113,7 @@ class _KDVocabParallel(torch.autograd.Function):
         ctx.cfg = (tau, eff_alpha, teacher_kind, int(v_offset), int(v_chunk), reduce_fn)
         ctx.save_for_backward(h, W_slice, y_slice, row_target, row_stats, n_valid, topk_v, topk_i)
         ctx.ws = ws
+        ctx.cache = cache
         total, task, distill, teacher = losses.unbind(0)
         ctx.mark_non_differentiable(teacher)
         return total, task, distill, teacher
@@ -124,7 +130,8 @@ class _KDVocabParallel(torch.autograd.Function):
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dH32, dW = _fused_backward(h, W_slice, y_slice, row_target, row_stats, n_valid, coef, tau, teacher_kind, 0,
-                                   v_chunk, torch.bfloat16, need_h, need_w, ctx.ws, topk, None, v_offset, dh_fp32=True)
+                                   v_chunk, torch.bfloat16, need_h, need_w, ctx.ws, topk, None, v_offset, dh_fp32=True,
+                                   cache=ctx.cache)
         dH = None
         if need_h:
             dH = reduce_fn(dH32).to(h.dtype)  # partial sums over vocabulary slices -> one rounding

@@ -134,11 +134,13 @@ def test_header_is_plain_c():
 #include <stdio.h>
 int main(void) {
   /* take the address of every entry point: unresolved or mis-declared symbols fail at link time */
-  void* fns[] = {(void*)kd_version, (void*)kd_last_error, (void*)kd_device_info, (void*)kd_prepare_rows,
+  void* fns[] = {(void*)kd_version, (void*)kd_last_error, (void*)kd_launch_count, (void*)kd_fused_bwd_trace_begin,
+                 (void*)kd_fused_bwd_trace_read, (void*)kd_device_info, (void*)kd_prepare_rows,
                  (void*)kd_finalize_losses, (void*)kd_stream_workspace_bytes, (void*)kd_dense_fwd_bwd,
                  (void*)kd_sparse_fwd_bwd, (void*)kd_scale_inplace, (void*)kd_topk_logprobs, (void*)kd_mask_rows,
                  (void*)kd_compact_rows, (void*)kd_gather_rows, (void*)kd_zero_if_empty,
-                 (void*)kd_fused_workspace_bytes, (void*)kd_fused_linear_fwd, (void*)kd_fused_linear_bwd,
+                 (void*)kd_fused_workspace_bytes, (void*)kd_fused_logit_cache_bytes, (void*)kd_fused_linear_fwd,
+                 (void*)kd_fused_linear_bwd,
                  (void*)kd_fused_linear_bwd_range, (void*)kd_fused_linear_fwd_partial,
                  (void*)kd_fused_merge_workspace_bytes, (void*)kd_fused_merge_ranks, (void*)kd_ce_fused_linear_fwd,
                  (void*)kd_ce_fused_linear_bwd, (void*)kd_linear_bf16, (void*)kd_gemm_bf16};
@@ -155,3 +157,36 @@ int main(void) {
                         "-L", libdir, "-l:libkd_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
         assert int(out[0]) >= 2 and int(out[1]) == len(_declared())
+
+
+def test_ctypes_signatures_match_header():
+    """Every prototype in include/kd_b200.h has the argument kinds (pointer / int / int64 / size_t / float) the
+    ctypes table of speech_distill_b200._lib declares, in the same order: a mismatch is a host-side crash."""
+    import ctypes as c
+
+    from speech_distill_b200 import _lib as L
+
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "kd_b200.h")).read(), flags=re.S)
+    kinds_of = {c.c_void_p: "ptr", c.c_char_p: "ptr", c.c_int: "int", c.c_int64: "int64", c.c_size_t: "size",
+                c.c_float: "float", c.c_ulonglong: "size"}  # 64-bit unsigned either way
+    for name, (_, args) in L.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+        assert m, f"{name} is not declared in kd_b200.h"
+        want = []
+        for p in (x.strip() for x in m.group(1).split(",")):
+            if not p or p == "void":
+                continue
+            if "*" in p:
+                want.append("ptr")
+            elif p.startswith("int64_t"):
+                want.append("int64")
+            elif p.startswith("size_t"):
+                want.append("size")
+            elif p.startswith("float"):
+                want.append("float")
+            elif p.startswith("unsigned long long"):
+                want.append("size")
+            else:
+                want.append("int")
+        got = [kinds_of.get(a, "ptr") for a in args]
+        assert got == want, f"{name}: ctypes {got} != header {want}"
