@@ -279,6 +279,36 @@ __device__ __forceinline__ void student_update(const float (&f)[N], int nvalid, 
   s1 += p1[0] + p1[1];
 }
 
+// The two halves of student_update for callers that already know a bound vm >= every value they are about to add
+// (the fused forward takes the maximum of a 32-column piece once, for the statistics and for the logit cache alike):
+// raise the running maximum to vm, then add values without looking for a new maximum.
+__device__ __forceinline__ void student_raise_max(float vm, float inv_tau, float& m, float& s1, float& st) {
+  if (vm > m) {
+    s1 *= exp_diff(m, vm, kLog2e);
+    st *= exp_diff(m, vm, kLog2e * inv_tau);
+    m = vm;
+  }
+}
+template <bool TAU2, int N>
+__device__ __forceinline__ void student_add(const float (&f)[N], int nvalid, float inv_tau, float m, float& s1,
+                                            float& st) {
+  if (m == -CUDART_INF_F) return;
+  const float c_tau = kLog2e * inv_tau;
+  const float off_one = m * kLog2e, off_tau = off_one * inv_tau;
+  float pt[2] = {0.f, 0.f}, p1[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (i < nvalid) {
+      float et, e1;
+      ExpPair<TAU2>::eval(f[i], c_tau, off_tau, off_one, et, e1);
+      pt[i & 1] += et;
+      p1[i & 1] += e1;
+    }
+  }
+  st += pt[0] + pt[1];
+  s1 += p1[0] + p1[1];
+}
+
 // GUARD = true keeps p == 0 terms at exactly 0 even when the student logit is -inf (user-supplied logits,
 // K2).  GUARD = false (fused path: finite student logits, teacher values already clamped to >= -1e30 by the
 // caller, see clamp_neg_inf_bf16x2) runs the cross term as one subtract and one FMA per element.

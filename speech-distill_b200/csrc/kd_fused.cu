@@ -307,7 +307,7 @@ struct FwdEpi {
       for (int j = 0; j < 16; ++j)
         if (j == (int)d) zl = fz[j];
     }
-    student_update<TAU2, 16>(fz, 16, p.inv_tau, m, s1, st);
+    student_add<TAU2, 16>(fz, 16, p.inv_tau, m, s1, st);  // tile() has raised m over the whole 32-column piece
     if (DENSE) {
       if (ncols >= 16) {
         teacher_update<TAU2, 16, false>(fy, fz, 16, p.inv_tau, mt, t1, tt, a);
@@ -360,31 +360,39 @@ struct FwdEpi {
       const int nrem = p.V - col0;
       const bool live = valid && nrem > 0 && !p.debug_skip_math;
       float ref = 0.f;
-      if (zc_on) {
-        // logit-cache staging buffer (one, as in GradEpi): the previous step's TMA stores must have finished reading
-        // it - they were issued a whole TMEM load + teacher-tile wait ago - before this step's pieces are written
-        if (t.epi_tid == 0) bulk_wait_read_all();
-        named_bar_sync(1, kEpiThreads);
-        if (live) {
-          // piece reference: the smallest integer >= every logit this thread has seen in its columns of this row
-          // so far, the 32 of this step included.  It is <= row max + 1, so |z - ref| <= (row max - z) + 1: the
-          // fp16 rounding error of an entry shrinks with its probability (see LogitCache).
-          float vm = m;
-          if (nrem >= 32) {
+      // logit-cache staging: every epilogue warp owns a [32 rows x 32 columns] fp16 box (2 KB, 64-byte swizzled rows)
+      // of the 32 KB slot and stores it with its own TMA store - no CTA-wide barrier on the store path
+      const uint32_t wbuf = t.g_base + (uint32_t)(t.epi_tid >> 5) * 2048u;
+      const uint32_t wrow = wbuf + (uint32_t)t.lane * 64u;
+      const uint32_t wswz = ((uint32_t)t.lane >> 1) & 3u;
+      if (live) {
+        // maximum of this thread's 32 columns, taken once: it raises the running maximum of the online statistics
+        // and, rounded up to an integer, is the piece reference of the logit cache - the smallest integer >= every
+        // logit this thread has seen in its columns of this row so far.  It is <= row max + 1, so
+        // |z - ref| <= (row max - z) + 1: the fp16 rounding error of an entry shrinks with its probability.
+        float vm = -CUDART_INF_F;
+        if (nrem >= 32) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vm = fmaxf(vm, fmaxf(__uint_as_float(raw0[j]), __uint_as_float(raw1[j])));
-          } else {  // ragged vocabulary edge
+          for (int j = 0; j < 16; ++j) vm = fmaxf(vm, fmaxf(__uint_as_float(raw0[j]), __uint_as_float(raw1[j])));
+        } else {  // ragged vocabulary edge
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < nrem) vm = fmaxf(vm, __uint_as_float(raw0[j]));
-              if (16 + j < nrem) vm = fmaxf(vm, __uint_as_float(raw1[j]));
-            }
+          for (int j = 0; j < 16; ++j) {
+            if (j < nrem) vm = fmaxf(vm, __uint_as_float(raw0[j]));
+            if (16 + j < nrem) vm = fmaxf(vm, __uint_as_float(raw1[j]));
           }
-          ref = fminf(fmaxf(ceilf(vm), -32000.f), 32000.f);
+        }
+        student_raise_max(vm, p.inv_tau, m, s1, st);
+      }
+      if (zc_on) {
+        // the previous step's store (issued by lane 0 a whole TMEM load + teacher-tile wait ago) must have read the box
+        if (t.lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        if (live) {
+          ref = fminf(fmaxf(ceilf(m), -32000.f), 32000.f);
           p.zc_ref[(size_t)(n_blk * 8 + c * kColGroups + t.cgrp) * p.R + row] = (int16_t)ref;
         } else {  // rows that are not scored (and columns past V) store zeros
 #pragma unroll
-          for (int q = 0; q < 4; ++q) sts128(step_piece_addr(t.g_base, t, q), make_uint4(0, 0, 0, 0));
+          for (int q = 0; q < 4; ++q) sts128(wrow + (((uint32_t)q ^ wswz) << 4), make_uint4(0, 0, 0, 0));
         }
       }
       if (live) {
@@ -405,8 +413,8 @@ struct FwdEpi {
           const int nc = nrem - 16 * sub < 16 ? nrem - 16 * sub : 16;
           if (nc <= 0) {  // (ragged edge) nothing to score, but the cache piece must still be defined
             if (zc_on) {
-              sts128(step_piece_addr(t.g_base, t, 2), make_uint4(0, 0, 0, 0));
-              sts128(step_piece_addr(t.g_base, t, 3), make_uint4(0, 0, 0, 0));
+              sts128(wrow + ((2u ^ wswz) << 4), make_uint4(0, 0, 0, 0));
+              sts128(wrow + ((3u ^ wswz) << 4), make_uint4(0, 0, 0, 0));
             }
             break;
           }
@@ -423,29 +431,26 @@ struct FwdEpi {
             if (zc_on) {
               uint4 lo, hi;
               encode16(raw0, ref, lo, hi);
-              sts128(step_piece_addr(t.g_base, t, 0), lo);
-              sts128(step_piece_addr(t.g_base, t, 1), hi);
+              sts128(wrow + ((0u ^ wswz) << 4), lo);
+              sts128(wrow + ((1u ^ wswz) << 4), hi);
             }
             sub_chunk(raw0, fy, col0, nc);
           } else {
             if (zc_on) {
               uint4 lo, hi;
               encode16(raw1, ref, lo, hi);
-              sts128(step_piece_addr(t.g_base, t, 2), lo);
-              sts128(step_piece_addr(t.g_base, t, 3), hi);
+              sts128(wrow + ((2u ^ wswz) << 4), lo);
+              sts128(wrow + ((3u ^ wswz) << 4), hi);
             }
             sub_chunk(raw1, fy, col0 + 16, nc);
           }
         }
       }
       if (zc_on) {
-        // swizzled [128 x kStepCols] fp16 step -> TMA stores (the store path of the gradient tile, GradEpi)
         fence_proxy_async_smem();
-        named_bar_sync(2, kEpiThreads);
-        if (t.epi_tid == 0) {
-#pragma unroll
-          for (int b = 0; b < kStepBoxes; ++b)
-            tma_store_2d(t.tma_g, t.g_base + b * kBoxBytes, n_blk * BN + c * kStepCols + 64 * b, m0);
+        __syncwarp();
+        if (t.lane == 0) {
+          tma_store_2d(t.tma_g, wbuf, n_blk * BN + c * kStepCols + t.cgrp * 32, m0 + (t.row_in_tile & ~31));
           bulk_commit();
         }
       }
@@ -460,7 +465,7 @@ struct FwdEpi {
     }
   }
   __device__ void finish() {
-    if (t.epi_tid == 0) bulk_wait_all();
+    if (t.lane == 0) bulk_wait_all();  // every warp issued its own stores
   }
 };
 
@@ -705,132 +710,175 @@ struct GradCachedParams {
   SparseView sp;
 };
 
-constexpr int kGcThreads = 256;  // 8 warps, one row strip each
-constexpr int kGcUnroll = 2;     // 256-column pieces in flight per warp
+// One warp per row strip, two 256-column pieces in flight per warp.  The kernel mostly runs BESIDE a dW / dH GEMM
+// CTA (640 threads x 64 registers, 192 KB of shared memory), which leaves an SM 24 K registers: 512 threads x 48
+// registers fit once, i.e. 16 warps x 2 KB in flight per SM - with one 256-thread x 64-register CTA (the first
+// version) the kernel was latency-bound at 360 us per chunk and set the pace of the whole backward
+// (profiles/r02a_bwd_trace.log); alone on the GPU two CTAs per SM run.
+constexpr int kGcThreads = 512;
+constexpr int kGcUnroll = 2;
+constexpr int kGcMaxRegs = 48;
+
+struct GcRow {  // per-row constants of the gradient formula (see GradEpi)
+  float c1, c2, c_tau, off1, offt, offy, half_off1, k_tau;
+  int target;
+};
+
+// gradient of 8 consecutive columns starting at vocabulary column `col` (local to this call); nrem = V - col
+template <typename TY, bool DENSE, bool TAU2, bool SPARSE>
+__device__ __forceinline__ uint4 gc_piece8(const GradCachedParams& p, const GcRow& r, int row, int col, int nrem,
+                                           uint4 zv, float ref, const float (&fy)[8]) {
+  float fz[8], gq[8];
+  Vec8<__half> v;
+  v.a = zv;
+  v.unpack(fz);
+  const float ref_tau = fmaf(ref, r.c_tau, -r.half_off1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float gi;
+    if (TAU2) {
+      const float e = ex2(fmaf(fz[i], r.c_tau, ref_tau));
+      gi = e * fmaf(e, r.c1, r.k_tau);
+    } else {
+      const float z = fz[i] + ref;
+      gi = r.c1 * ex2(fmaf(z, kLog2e, -r.off1)) + r.c2 * ex2(fmaf(z, r.c_tau, -r.offt));
+    }
+    if (DENSE) gi = fmaf(-r.c2, ex2(fmaf(fy[i], r.c_tau, -r.offy)), gi);
+    gq[i] = i < nrem ? gi : 0.f;
+  }
+  if (SPARSE) {  // - c2 P with P = scatter(i_k, p_k); duplicate indices accumulate
+    const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + col / BN;  // uniform over the warp's piece
+    const int e_beg = o[0], e_end = o[1];
+    for (int e = e_beg; e < e_end; ++e) {
+      const unsigned ds = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col);
+      if (ds < 8u) {
+        const float pk = r.c2 * p.sp.p[(size_t)row * p.sp.K + e];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i == (int)ds) gq[i] -= pk;
+      }
+    }
+  }
+  const unsigned d = (unsigned)(r.target - col);
+  if (d < 8u) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i == (int)d) gq[i] -= r.c1;
+  }
+  if (p.g_fp16) {
+    Vec8<__half> o;
+    o.pack(gq);
+    return o.a;
+  }
+  Vec8<__nv_bfloat16> o;
+  o.pack(gq);
+  return o.a;
+}
+
+// the ragged pieces of a row (vocabulary edge, unaligned teacher rows): rare, kept out of the streaming loop
+template <typename TY, bool DENSE, bool TAU2, bool SPARSE>
+__device__ __noinline__ void gc_piece_slow(const GradCachedParams& p, const GcRow r, int row, int j) {
+  const int col = p.v0 + j;
+  const int nrem = p.V - col;
+  uint16_t* grow = reinterpret_cast<uint16_t*>(p.G) + (size_t)row * p.g_stride;
+  if (nrem <= 0) {
+    *reinterpret_cast<uint4*>(grow + j) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const uint4 zv = ldg_stream(p.zc.z16 + (size_t)row * p.zc.z_stride + col);
+  const float ref = (float)p.zc.ref[(size_t)(col >> 5) * p.R + row];
+  float fy[8];
+  if (DENSE) {
+    const TY* yrow = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fy[i] = i < nrem ? fmaxf(Elem<TY>::to_f(yrow[i]), -1e30f) : -CUDART_INF_F;
+  }
+  *reinterpret_cast<uint4*>(grow + j) = gc_piece8<TY, DENSE, TAU2, SPARSE>(p, r, row, col, nrem, zv, ref, fy);
+}
 
 template <typename TY, bool DENSE, bool TAU2, bool SPARSE>
-__global__ void __launch_bounds__(kGcThreads) kd_grad_cached_kernel(const GradCachedParams p) {
+__global__ void __maxnreg__(kGcMaxRegs) kd_grad_cached_kernel(const __grid_constant__ GradCachedParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nn = *p.n_norm;
-  float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
-  if (p.g_fp16) inv_n *= g_operand_scale(p.n_norm, p.coef, p.tau);
-  const float c1 = p.coef[0] * inv_n;
-  const float c2 = p.use_kl ? p.coef[1] * p.tau * inv_n : 0.f;
-  const float c_tau = kLog2e / p.tau;
+  GcRow r;
+  {
+    const int nn = *p.n_norm;
+    float inv_n = nn > 0 ? 1.0f / (float)nn : 0.f;
+    if (p.g_fp16) inv_n *= g_operand_scale(p.n_norm, p.coef, p.tau);
+    r.c1 = p.coef[0] * inv_n;
+    r.c2 = p.use_kl ? p.coef[1] * p.tau * inv_n : 0.f;
+    r.c_tau = kLog2e / p.tau;
+  }
   int r_end = p.R;
   if (p.n_rows != nullptr) {  // compacted rows: everything behind the last live 256-row tile is never read
     const int live = (*p.n_rows + 2 * BM - 1) / (2 * BM) * (2 * BM);
     r_end = live < r_end ? live : r_end;
   }
+  const uint64_t pol_stream = l2_policy_evict_first();
+  // columns [0, fast_end) of the chunk take the streaming path: whole 16-byte vectors of z16, teacher and G
+  int fast_end = p.V - p.v0 < p.cols_pad ? p.V - p.v0 : p.cols_pad;
+  fast_end = (DENSE && !p.y_vec_ok) ? 0 : (fast_end & ~7);
   for (int row = blockIdx.x * (kGcThreads / 32) + warp; row < r_end; row += gridDim.x * (kGcThreads / 32)) {
     bool valid;
-    const int target = local_target(p.row_target[row], p.label_off, p.V, valid);
+    r.target = local_target(p.row_target[row], p.label_off, p.V, valid);
     uint16_t* grow = reinterpret_cast<uint16_t*>(p.G) + (size_t)row * p.g_stride;
     if (!valid) {  // rows that are not scored contribute nothing: zeros, no reads
       for (int j = lane * 8; j < p.cols_pad; j += 256) *reinterpret_cast<uint4*>(grow + j) = make_uint4(0, 0, 0, 0);
       continue;
     }
-    const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
-    const float off1 = rs.x * kLog2e, offt = rs.y * kLog2e, offy = rs.z * kLog2e;
-    const float half_off1 = 0.5f * off1;
-    const float k_tau = c2 * ex2(half_off1 - offt);
-    const __half* zrow = p.zc.z16 + (size_t)row * p.zc.z_stride + p.v0;
-    const int16_t* refrow = p.zc.ref + row;
-    const TY* yrow = DENSE ? reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + p.v0 : nullptr;
-    for (int j0 = 0; j0 < p.cols_pad; j0 += 256 * kGcUnroll) {
-      uint4 zv[kGcUnroll];
-      Vec8<TY> yv[kGcUnroll];
-      float ref[kGcUnroll];
-      // ---- loads of all pieces first (memory-level parallelism), then the arithmetic ----
+    {
+      const float4 rs = *reinterpret_cast<const float4*>(p.row_stats + (size_t)row * 4);
+      r.off1 = rs.x * kLog2e;
+      r.offt = rs.y * kLog2e;
+      r.offy = rs.z * kLog2e;
+      r.half_off1 = 0.5f * r.off1;
+      r.k_tau = r.c2 * ex2(r.half_off1 - r.offt);
+    }
+    // per-lane cursors, advanced by constants (lane l owns columns 8 l .. 8 l + 7 of every 256-column piece)
+    const __half* zp = p.zc.z16 + (size_t)row * p.zc.z_stride + p.v0 + lane * 8;
+    const int16_t* refp = p.zc.ref + (size_t)((p.v0 >> 5) + (lane >> 2)) * p.R + row;
+    const TY* yp = DENSE ? reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + p.v0 + lane * 8 : nullptr;
+    uint16_t* gp = grow + lane * 8;
+    const size_t ref_step = (size_t)8 * p.R;  // one 256-column piece = 8 reference pieces
+    for (int j0 = lane * 8; j0 < p.cols_pad; j0 += 256 * kGcUnroll, zp += 256 * kGcUnroll, yp += DENSE ? 256 * kGcUnroll : 0,
+             gp += 256 * kGcUnroll, refp += kGcUnroll * ref_step) {
+      if (j0 + 256 * (kGcUnroll - 1) + 8 <= fast_end) {
+        uint4 zv[kGcUnroll];
+        Vec8<TY> yv[kGcUnroll];
+        float ref[kGcUnroll];
+        // all loads first (memory-level parallelism), then the arithmetic; the streams are dead after this read:
+        // evict-first keeps them from pushing the gradient chunk, which the GEMMs re-read twice, out of L2
 #pragma unroll
-      for (int u = 0; u < kGcUnroll; ++u) {
-        const int j = j0 + u * 256 + lane * 8;
-        const int nrem = p.V - (p.v0 + j);
-        if (j < p.cols_pad && nrem > 0) {
-          zv[u] = ldg_stream(zrow + j);
-          ref[u] = (float)refrow[(size_t)((p.v0 + j) >> 5) * p.R];
-          if (DENSE && nrem >= 8 && p.y_vec_ok) yv[u].load_global(yrow + j);
+        for (int u = 0; u < kGcUnroll; ++u) {
+          zv[u] = ldg_hint(zp + u * 256, pol_stream);
+          ref[u] = (float)refp[u * ref_step];
+          if (DENSE) yv[u].load_global_hint(yp + u * 256, pol_stream);
         }
-      }
 #pragma unroll
-      for (int u = 0; u < kGcUnroll; ++u) {
-        const int j = j0 + u * 256 + lane * 8;
-        if (j >= p.cols_pad) break;
-        const int col = p.v0 + j;
-        const int nrem = p.V - col;
-        float gq[8];
-        if (nrem <= 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gq[i] = 0.f;
-        } else {
-          float fz[8], fy[8];
-          {
-            Vec8<__half> v;
-            v.a = zv[u];
-            v.unpack(fz);
-          }
+        for (int u = 0; u < kGcUnroll; ++u) {
+          const int j = j0 + u * 256;
+          float fy[8];
           if (DENSE) {
-            if (nrem >= 8 && p.y_vec_ok) {
-              if (std::is_same<TY, __nv_bfloat16>::value) {
-                yv[u].a.x = clamp_neg_inf_bf16x2(yv[u].a.x);
-                yv[u].a.y = clamp_neg_inf_bf16x2(yv[u].a.y);
-                yv[u].a.z = clamp_neg_inf_bf16x2(yv[u].a.z);
-                yv[u].a.w = clamp_neg_inf_bf16x2(yv[u].a.w);
-                yv[u].unpack(fy);
-              } else {
-                yv[u].unpack(fy);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) fy[i] = fmaxf(fy[i], -1e30f);
-              }
+            if (std::is_same<TY, __nv_bfloat16>::value) {  // -inf -> most negative finite value, two elements per op
+              yv[u].a.x = clamp_neg_inf_bf16x2(yv[u].a.x);
+              yv[u].a.y = clamp_neg_inf_bf16x2(yv[u].a.y);
+              yv[u].a.z = clamp_neg_inf_bf16x2(yv[u].a.z);
+              yv[u].a.w = clamp_neg_inf_bf16x2(yv[u].a.w);
+              yv[u].unpack(fy);
             } else {
+              yv[u].unpack(fy);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) fy[i] = i < nrem ? fmaxf(Elem<TY>::to_f(yrow[j + i]), -1e30f) : -CUDART_INF_F;
+              for (int i = 0; i < 8; ++i) fy[i] = fmaxf(fy[i], -1e30f);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float z = fz[i] + ref[u];
-            float gi;
-            if (TAU2) {
-              const float e = ex2(fmaf(z, c_tau, -half_off1));
-              gi = e * fmaf(e, c1, k_tau);
-            } else {
-              gi = c1 * ex2(fmaf(z, kLog2e, -off1)) + c2 * ex2(fmaf(z, c_tau, -offt));
-            }
-            if (DENSE) gi = fmaf(-c2, ex2(fmaf(fy[i], c_tau, -offy)), gi);
-            gq[i] = i < nrem ? gi : 0.f;
-          }
-          if (SPARSE) {  // - c2 P with P = scatter(i_k, p_k); duplicate indices accumulate
-            const uint16_t* o = p.sp.off + (size_t)row * p.sp.off_stride + col / BN;  // uniform over the warp's piece
-            const int e_beg = o[0], e_end = o[1];
-            for (int e = e_beg; e < e_end; ++e) {
-              const unsigned ds = (unsigned)(p.sp.idx[(size_t)row * p.sp.K + e] - col);
-              if (ds < 8u) {
-                const float pk = c2 * p.sp.p[(size_t)row * p.sp.K + e];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (i == (int)ds) gq[i] -= pk;
-              }
-            }
-          }
-          const unsigned d = (unsigned)(target - col);
-          if (d < 8u) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i == (int)d) gq[i] -= c1;
-          }
+          *reinterpret_cast<uint4*>(gp + u * 256) =
+              gc_piece8<TY, DENSE, TAU2, SPARSE>(p, r, row, p.v0 + j, 8, zv[u], ref[u], fy);
         }
-        uint4 outv;
-        if (p.g_fp16) {
-          Vec8<__half> v;
-          v.pack(gq);
-          outv = v.a;
-        } else {
-          Vec8<__nv_bfloat16> v;
-          v.pack(gq);
-          outv = v.a;
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < kGcUnroll; ++u) {
+          const int j = j0 + u * 256;
+          if (j < p.cols_pad) gc_piece_slow<TY, DENSE, TAU2, SPARSE>(p, r, row, j);
         }
-        *reinterpret_cast<uint4*>(grow + j) = outv;
       }
     }
   }
@@ -1629,9 +1677,11 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 matrix [outer rows][inner cols] (inner contiguous), box = 64 inner x box_outer rows, 128-byte swizzle
+// bf16 matrix [outer rows][inner cols] (inner contiguous), box = box_inner x box_outer; 128-byte swizzle for the
+// 64-element (128-byte) boxes of the operand / tile rings, 64-byte swizzle for the 32-element boxes of the per-warp
+// logit-cache stores
 static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
-                     uint32_t box_outer, const char* what) {
+                     uint32_t box_outer, const char* what, uint32_t box_inner = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_elems * 2) % 16 != 0) {
@@ -1640,10 +1690,11 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t inner, uint64_t 
   }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_elems * 2};
-  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu)", what, (int)r,
@@ -1956,8 +2007,8 @@ struct TraceScope {  // records e0 now and e1 at scope exit on `s`; inert when t
   }
 };
 
-// ---- backward pipeline: three serial chains on three streams -----------------------------------------
-//   caller's stream : grad(0) grad(1) grad(2) ...          (G chunk c -> buffer c & 1)
+// ---- backward pipeline: three serial chains on three internal streams (forked from / joined into the caller's) -------
+//   stream G        : grad(0) grad(1) grad(2) ...          (G chunk c -> buffer c & 1; + the fp16 operand copies)
 //   stream W        :         dW(0)   dW(1) ...            (waits grad(c))
 //   stream H        :         dH(0)   dH(1) ...            (waits grad(c); serial: fp32 accumulation order is fixed)
 // and grad(c + 2) waits for dW(c) and dH(c) before it overwrites their buffer.  Every kernel is persistent with
@@ -1965,8 +2016,9 @@ struct TraceScope {  // records e0 now and e1 at scope exit on `s`; inert when t
 // 10 CTA pairs a 64-tile dH launch never uses); results are bit-identical to the serial order.
 struct BwdPipe {
   std::mutex enqueue;  // the streams and events are per device: one backward is enqueued at a time
-  cudaStream_t sw = nullptr, sh = nullptr;
+  cudaStream_t sg = nullptr, sw = nullptr, sh = nullptr;
   cudaEvent_t eg[2] = {nullptr, nullptr}, ew[2] = {nullptr, nullptr}, eh[2] = {nullptr, nullptr};
+  cudaEvent_t efork = nullptr, ejoin = nullptr;
   // state that survives from one vocabulary-range call of a backward to the next (reset at KD_RANGE_FIRST): which
   // G buffers still have readers in flight, and the last dW / dH events (the dH chain is joined only at the end)
   bool rec_w[2] = {false, false}, rec_h[2] = {false, false};
@@ -1996,12 +2048,22 @@ static BwdPipe* get_bwd_pipe() {
   if (p.ready) return &p;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+  // Stream priorities decide which pending CTAs the block scheduler places first.  Measured at configs[1] size in a
+  // settled loop (tools/k1_ab.py, profiles/r02c_bwd_prio.log): all three chains at the same (default) priority
+  // 4.20 ms/step; gradient chain high + GEMM chains low 4.34 (the GEMMs starve); GEMM chains high (round 1) 4.26 (the
+  // gradient kernel's small CTAs, which fit BESIDE a GEMM CTA, are not placed while a GEMM kernel still has CTAs
+  // pending and the kernel runs after the GEMMs instead of beside them).  KD_BWD_PRIO=g / w select the other two.
+  int prio_g = lo, prio_mm = lo;
   {
-    const char* e = getenv("KD_BWD_PRIO");  // 0: default-priority side streams (experiment)
-    if (e && e[0] == '0') hi = 0;
+    const char* e = getenv("KD_BWD_PRIO");
+    if (e && e[0] == 'g') prio_g = hi;
+    if (e && e[0] == 'w') prio_mm = hi;
   }
-  if (cudaStreamCreateWithPriority(&p.sw, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-  if (cudaStreamCreateWithPriority(&p.sh, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&p.sg, cudaStreamNonBlocking, prio_g) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&p.sw, cudaStreamNonBlocking, prio_mm) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&p.sh, cudaStreamNonBlocking, prio_mm) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&p.efork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&p.ejoin, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   for (int i = 0; i < 2; ++i) {
     if (cudaEventCreateWithFlags(&p.eg[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&p.ew[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -2100,9 +2162,9 @@ static int launch_grad_cached_t(const GradCachedParams& gp, bool tau2, int block
 }
 
 static int launch_grad_cached(const GradCachedParams& gp, int teacher_kind, int y_dtype, bool tau2, cudaStream_t s) {
-  // one warp per row strip; four CTAs per SM when the kernel has the SMs to itself, one beside a GEMM CTA
+  // one warp per row strip; two CTAs per SM when the kernel has the SMs to itself, one beside a GEMM CTA
   int blocks = cdiv(gp.R, kGcThreads / 32);
-  const int cap = 4 * sm_count();
+  const int cap = 2 * sm_count();
   if (blocks > cap) blocks = cap;
   if (teacher_kind == KD_TEACHER_DENSE) {
     if (y_dtype == KD_DTYPE_BF16) return launch_grad_cached_t<__nv_bfloat16, true, false>(gp, tau2, blocks, s);
@@ -2273,7 +2335,8 @@ static int fused_fwd_impl(const void* h, int64_t h_stride, const void* W, int64_
   if (zc.tiles > 0) {
     fp.zc_tiles = zc.tiles;
     fp.zc_ref = zc.ref;
-    if (make_tmap(&tz, zc.z16, (uint64_t)zc.z_stride, (uint64_t)R, (uint64_t)zc.z_stride, BM, "logit cache")) return 1;
+    if (make_tmap(&tz, zc.z16, (uint64_t)zc.z_stride, (uint64_t)R, (uint64_t)zc.z_stride, 32, "logit cache", 32))
+      return 1;
   }
   const float4* sp_rowc = nullptr;
   const bool y_tma = teacher_kind == KD_TEACHER_DENSE && make_teacher_tmap(&ty, y, y_dtype, y_stride, R, V);
@@ -2432,14 +2495,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   // fp16 gradient operand: dW and dH multiply the fp16 G with fp16 copies of h (once per call) and of the chunk's W rows
   const bool g16 = g_fp16_enabled();
   uint8_t* h16 = wsp + ws.h16_off;
-  if (g16) {
-    // (once per backward: later ranges reuse the copy in the same workspace while dW kernels may still read it)
-    if (range_first) {
-      TraceScope ts(kTraceCast, -1, s);
-      if (cast_bf16_f16(h, h_stride, h16, R, H, s)) return 1;
-    }
-    if (make_tmap(&t_h_mn, h16, (uint64_t)H, (uint64_t)R, (uint64_t)H, 64, "hidden fp16 (MN-major)")) return 1;
-  }
+  if (g16 && make_tmap(&t_h_mn, h16, (uint64_t)H, (uint64_t)R, (uint64_t)H, 64, "hidden fp16 (MN-major)")) return 1;
 
   SparseView sp_view = {};
   if (sparse && prepare_sparse(topk_v, topk_i, K, row_target, R, V, v_offset, tau, ws, wsp + ws.bwd_bytes, &sp_view, nullptr, s,
@@ -2452,7 +2508,7 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
   BwdPipe* pipe = (bwd_pipe_enabled() && (n_chunks > 1 || multi_range)) ? get_bwd_pipe() : nullptr;
   std::unique_lock<std::mutex> pipe_lock;
   if (pipe) pipe_lock = std::unique_lock<std::mutex>(pipe->enqueue);  // host threads sharing a device take turns
-  cudaStream_t s_w = pipe ? pipe->sw : s, s_h = pipe ? pipe->sh : s;
+  cudaStream_t s_g = pipe ? pipe->sg : s, s_w = pipe ? pipe->sw : s, s_h = pipe ? pipe->sh : s;
   BwdPipe local_state;  // serial mode: the flags are unused
   BwdPipe& st = pipe ? *pipe : local_state;
   if (pipe && !range_first && pipe->owner != workspace) {
@@ -2460,8 +2516,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     // ours.  Drain both side chains into the caller's stream and start from a clean slate - rare, and always safe.
     if (check_cuda(cudaEventRecord(pipe->ew[0], s_w), "drain dW")) return 1;
     if (check_cuda(cudaEventRecord(pipe->eh[0], s_h), "drain dH")) return 1;
+    if (check_cuda(cudaEventRecord(pipe->ejoin, s_g), "drain grad")) return 1;
     if (check_cuda(cudaStreamWaitEvent(s, pipe->ew[0], 0), "drain dW")) return 1;
     if (check_cuda(cudaStreamWaitEvent(s, pipe->eh[0], 0), "drain dH")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(s, pipe->ejoin, 0), "drain grad")) return 1;
     st.rec_w[0] = st.rec_w[1] = st.rec_h[0] = st.rec_h[1] = false;
     st.any_w = st.any_h = false;
   }
@@ -2470,6 +2528,15 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     st.any_w = st.any_h = false;
   }
   if (pipe) pipe->owner = workspace;
+  if (pipe) {  // fork: the gradient chain starts behind everything the caller has enqueued so far
+    if (check_cuda(cudaEventRecord(pipe->efork, s), "fork")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(s_g, pipe->efork, 0), "fork")) return 1;
+  }
+  if (g16 && range_first) {
+    // fp16 copy of h, once per backward: later ranges reuse it in the same workspace while dW kernels may still read it
+    TraceScope ts(kTraceCast, -1, s_g);
+    if (cast_bf16_f16(h, h_stride, h16, R, H, s_g)) return 1;
+  }
   bool (&rec_w)[2] = st.rec_w;
   bool (&rec_h)[2] = st.rec_h;
   bool& any_w = st.any_w;
@@ -2483,21 +2550,21 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     const int cols = v_end - v0 < vc ? v_end - v0 : vc;
     const int n_blks = cdiv(cols, BN);  // 256-wide column blocks of this chunk (G is zero-padded to the block)
     const bool need_dw = dW != nullptr && (int64_t)(v0 + cols) > dw_row_begin;
-    // ---- 1. recompute logits tile, form G ----
+    // ---- 1. gradient chunk G: from the logit cache, or by recomputing the logits tile ----
     {
       if (pipe) {  // the buffer's previous readers (chunk c - 2) must be done
-        if (rec_w[b] && check_cuda(cudaStreamWaitEvent(s, pipe->ew[b], 0), "wait dW")) return 1;
-        if (rec_h[b] && check_cuda(cudaStreamWaitEvent(s, pipe->eh[b], 0), "wait dH")) return 1;
+        if (rec_w[b] && check_cuda(cudaStreamWaitEvent(s_g, pipe->ew[b], 0), "wait dW")) return 1;
+        if (rec_h[b] && check_cuda(cudaStreamWaitEvent(s_g, pipe->eh[b], 0), "wait dH")) return 1;
         rec_w[b] = rec_h[b] = false;
         if (!grad_cached_overlap()) {  // experiment: no gradient kernel beside the previous chunk's GEMMs
-          if (rec_w[b ^ 1] && check_cuda(cudaStreamWaitEvent(s, pipe->ew[b ^ 1], 0), "wait dW")) return 1;
-          if (rec_h[b ^ 1] && check_cuda(cudaStreamWaitEvent(s, pipe->eh[b ^ 1], 0), "wait dH")) return 1;
+          if (rec_w[b ^ 1] && check_cuda(cudaStreamWaitEvent(s_g, pipe->ew[b ^ 1], 0), "wait dW")) return 1;
+          if (rec_h[b ^ 1] && check_cuda(cudaStreamWaitEvent(s_g, pipe->eh[b ^ 1], 0), "wait dH")) return 1;
         }
       }
       if (g16 && dH) {  // this chunk's W rows as fp16 (read by dH(c); the buffer's previous reader was dH(c - 2))
         const uint8_t* wrow = reinterpret_cast<const uint8_t*>(W) + (size_t)v0 * (size_t)w_stride * 2;
-        TraceScope ts(kTraceCast, c, s);
-        if (cast_bf16_f16(wrow, w_stride, wsp + ws.w16_off + b * ws.w16_buf_bytes, cols, H, s)) return 1;
+        TraceScope ts(kTraceCast, c, s_g);
+        if (cast_bf16_f16(wrow, w_stride, wsp + ws.w16_off + b * ws.w16_buf_bytes, cols, H, s_g)) return 1;
       }
       int rc;
       if (v0 / BN + n_blks <= zc.tiles) {
@@ -2523,10 +2590,10 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
         cp.G = wsp + ws.g_off + b * ws.g_buf_bytes;
         cp.g_stride = vc;
         cp.sp = sp_view;
-        TraceScope ts(kTraceGrad, c, s);
-        rc = launch_grad_cached(cp, teacher_kind, y_dtype, tau2, s);
+        TraceScope ts(kTraceGrad, c, s_g);
+        rc = launch_grad_cached(cp, teacher_kind, y_dtype, tau2, s_g);
       } else {
-      TraceScope ts(kTraceGradRecompute, c, s);
+      TraceScope ts(kTraceGradRecompute, c, s_g);
       Geom g = {};
       g.num_m_blk = cdiv(R, tile_m());
       g.num_n_blk = n_blks;
@@ -2554,19 +2621,19 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
       gp.sp = sp_view;
       if (teacher_kind == KD_TEACHER_DENSE) {
         rc = y_dtype == KD_DTYPE_BF16
-                 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k[b], g, gp, tau2, s)
-                 : launch_grad<true, float>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
+                 ? launch_grad<true, __nv_bfloat16>(t_h_k, t_w_k, y_tma ? &t_y : nullptr, t_g_k[b], g, gp, tau2, s_g)
+                 : launch_grad<true, float>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s_g);
       } else if (sparse) {
         rc = tau2 ? launch_umma<GradEpi<__nv_bfloat16, false, true, false, true>, false, false>(t_h_k, t_w_k, t_h_k,
-                                                                                                  t_g_k[b], g, gp, s)
+                                                                                                  t_g_k[b], g, gp, s_g)
                   : launch_umma<GradEpi<__nv_bfloat16, false, false, false, true>, false, false>(t_h_k, t_w_k, t_h_k,
-                                                                                                   t_g_k[b], g, gp, s);
+                                                                                                   t_g_k[b], g, gp, s_g);
       } else {
-        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s);
+        rc = launch_grad<false, __nv_bfloat16>(t_h_k, t_w_k, nullptr, t_g_k[b], g, gp, tau2, s_g);
       }
       }
       if (rc) return rc;
-      if (pipe && check_cuda(cudaEventRecord(pipe->eg[b], s), "record grad")) return 1;
+      if (pipe && check_cuda(cudaEventRecord(pipe->eg[b], s_g), "record grad")) return 1;
     }
     // ---- 2. dW[v0 : v0+cols, :] = G^T h   (rows are final: every token is in this GEMM's K) ----
     if (need_dw) {
@@ -2663,6 +2730,8 @@ extern "C" int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const 
     // join: both side chains are serial, so their last events cover everything.  dW is joined after every range
     // (its rows are handed to the all-reduce), dH only after the last one: between ranges the dH chain keeps
     // running and the next range's gradient kernels wait per buffer, as inside a range.
+    if (check_cuda(cudaEventRecord(pipe->ejoin, s_g), "join grad")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(s, pipe->ejoin, 0), "join grad")) return 1;
     if (any_w && check_cuda(cudaStreamWaitEvent(s, pipe->ew[last_w], 0), "join dW")) return 1;
     if (range_last && any_h && check_cuda(cudaStreamWaitEvent(s, pipe->eh[last_h], 0), "join dH")) return 1;
   }

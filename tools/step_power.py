@@ -67,6 +67,40 @@ def step():
     out[0].backward()
 
 
-run("K1 step (8 R H V executed)", step, 8.0 * B * T * H * V)
+from speech_distill_b200 import loss as KL  # noqa: E402
+
+h2, y2, Wd = h.detach().reshape(B * T, H), y.reshape(B * T, V), W.detach()
+row_target, n_valid = KL.prepare_rows(labels, None, B, T, -100, h.device)
+coef = torch.tensor([0.5, 0.5], dtype=torch.float32, device=h.device)
+cache = KL.alloc_logit_cache(B * T, V, 0, h.device)
+sums, row_stats, ws = KL._fused_forward(h2, Wd, y2, row_target, 2.0, 0.5, 0, cache=cache)
+logits = torch.empty(B * T, V, device=h.device, dtype=torch.bfloat16)
+G16 = torch.randn(B * T, 18944, device=h.device).half()
+W16 = Wd[:18944].half()
+h16 = h2.half()
+dWc = torch.empty(18944, H, device=h.device, dtype=torch.half)
+dHc = torch.empty(B * T, H, device=h.device, dtype=torch.half)
+
+
+def fwd_only():
+    KL._fused_forward(h2, Wd, y2, row_target, 2.0, 0.5, 0, cache=cache)
+
+
+def bwd_only():
+    KL._fused_backward(h2, Wd, y2, row_target, row_stats, n_valid, coef, 2.0, 1, 0, 0, torch.bfloat16, True, True, ws,
+                       cache=cache)
+
+
+def cublas_bwd_chunk():  # the library's version of one chunk's dW and dH GEMMs (fp16 operands, same shapes)
+    torch.matmul(G16.t(), h16, out=dWc)
+    torch.matmul(G16, W16, out=dHc)
+
+
+F = 2.0 * B * T * H * V
+run("K1 step (6 R H V algorithmic)", step, 3 * F)
+run("K1 forward only", fwd_only, F)
+run("K1 backward only", bwd_only, 2 * F)
 run("cuBLAS bf16 8192^3", lambda: torch.matmul(A8, B8), 2.0 * 8192 ** 3)
-run("K1 step again", step, 8.0 * B * T * H * V)
+run("cuBLAS lm_head shape", lambda: torch.matmul(h2, Wd.t(), out=logits), F)
+run("cuBLAS dW+dH of one chunk", cublas_bwd_chunk, 2 * 2.0 * B * T * H * 18944)
+run("K1 step again", step, 3 * F)
