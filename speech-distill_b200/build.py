@@ -32,18 +32,22 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant=NAME builds libkd_b200_NAME.so from the same sources with extra -D defines (same-box A/B runs through
+    KD_B200_LIB); objects go to build/NAME/."""
+    lib = LIB if variant is None else os.path.join(HERE, f"libkd_b200_{variant}.so")
+    if variant is None and not force and not _stale():
         return LIB
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build") if variant is None else os.path.join(HERE, "build", variant)
+    os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", path, "-o", obj]
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, *defines, "-c", path, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, obj, p in procs:
@@ -53,18 +57,20 @@ def build(force=False, verbose=False):
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append("==== link\n" + r.stdout)
     if r.returncode != 0:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("link failed")
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+    with open(os.path.join(bdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -51,6 +51,14 @@ constexpr int kSchedSlots = 2;  // work-unit queue depth per CTA (pair): the nex
 #ifndef KD_G_FP16_DEFAULT
 #define KD_G_FP16_DEFAULT 1
 #endif
+// compile-time A/B switches (speech-distill_b200/build.py --variant NAME -DKD_OPT_...=0 builds a second library that
+// tools/k1_abab.sh runs against the default one on the same box; box-to-box spread is larger than most of these)
+#ifndef KD_OPT_FWD_ONE_MAX
+#define KD_OPT_FWD_ONE_MAX 1  // forward epilogue: one maximum per 32-column piece (statistics + logit-cache reference)
+#endif
+#ifndef KD_OPT_GC_CURSOR
+#define KD_OPT_GC_CURSOR 1    // cached-gradient kernel: per-lane cursors and L2 evict-first loads
+#endif
 constexpr int kRecFloats = 8;  // forward partial record: m, s1, st, mt, t1, tt, a, z_label
 // per-row record one vocabulary slice hands to the cross-rank merge (vocab-parallel mode):
 // m, s1, st, mt | t1, tt, a, z_label | y_label, sum p log p, hit value sum, hits
@@ -307,7 +315,11 @@ struct FwdEpi {
       for (int j = 0; j < 16; ++j)
         if (j == (int)d) zl = fz[j];
     }
+#if KD_OPT_FWD_ONE_MAX
     student_add<TAU2, 16>(fz, 16, p.inv_tau, m, s1, st);  // tile() has raised m over the whole 32-column piece
+#else
+    student_update<TAU2, 16>(fz, 16, p.inv_tau, m, s1, st);
+#endif
     if (DENSE) {
       if (ncols >= 16) {
         teacher_update<TAU2, 16, false>(fy, fz, 16, p.inv_tau, mt, t1, tt, a);
@@ -360,6 +372,9 @@ struct FwdEpi {
       const int nrem = p.V - col0;
       const bool live = valid && nrem > 0 && !p.debug_skip_math;
       float ref = 0.f;
+#if !KD_OPT_FWD_ONE_MAX
+      float piece_max = 0.f;
+#endif
       // logit-cache staging: every epilogue warp owns a [32 rows x 32 columns] fp16 box (2 KB, 64-byte swizzled rows)
       // of the 32 KB slot and stores it with its own TMA store - no CTA-wide barrier on the store path
       const uint32_t wbuf = t.g_base + (uint32_t)(t.epi_tid >> 5) * 2048u;
@@ -381,14 +396,22 @@ struct FwdEpi {
             if (16 + j < nrem) vm = fmaxf(vm, __uint_as_float(raw1[j]));
           }
         }
+#if KD_OPT_FWD_ONE_MAX
         student_raise_max(vm, p.inv_tau, m, s1, st);
+#else
+        piece_max = fmaxf(vm, m);
+#endif
       }
       if (zc_on) {
         // the previous step's store (issued by lane 0 a whole TMEM load + teacher-tile wait ago) must have read the box
         if (t.lane == 0) bulk_wait_read_all();
         __syncwarp();
         if (live) {
+#if KD_OPT_FWD_ONE_MAX
           ref = fminf(fmaxf(ceilf(m), -32000.f), 32000.f);
+#else
+          ref = fminf(fmaxf(ceilf(piece_max), -32000.f), 32000.f);
+#endif
           p.zc_ref[(size_t)(n_blk * 8 + c * kColGroups + t.cgrp) * p.R + row] = (int16_t)ref;
         } else {  // rows that are not scored (and columns past V) store zeros
 #pragma unroll
@@ -849,9 +872,15 @@ __global__ void __maxnreg__(kGcMaxRegs) kd_grad_cached_kernel(const __grid_const
         // evict-first keeps them from pushing the gradient chunk, which the GEMMs re-read twice, out of L2
 #pragma unroll
         for (int u = 0; u < kGcUnroll; ++u) {
+#if KD_OPT_GC_CURSOR
           zv[u] = ldg_hint(zp + u * 256, pol_stream);
           ref[u] = (float)refp[u * ref_step];
           if (DENSE) yv[u].load_global_hint(yp + u * 256, pol_stream);
+#else
+          zv[u] = ldg_stream(zp + u * 256);
+          ref[u] = (float)refp[u * ref_step];
+          if (DENSE) yv[u].load_global(yp + u * 256);
+#endif
         }
 #pragma unroll
         for (int u = 0; u < kGcUnroll; ++u) {
