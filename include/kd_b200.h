@@ -42,7 +42,7 @@ extern "C" {
 #define KD_DTYPE_BF16 1
 #define KD_DTYPE_F16 2
 
-#define KD_ABI_VERSION 3
+#define KD_ABI_VERSION 4
 
 /* OR-ed into grad_dtype of the fused backward: dH is written as fp32 (a vocab-parallel caller sums the
  * per-slice partial dH across ranks before rounding) while dW keeps the base dtype. */
@@ -253,6 +253,25 @@ int kd_ce_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64
  * fixed-size scratch and feeds kd_topk_logprobs, so the teacher's [B,T,V] logits never exist as a whole. */
 int kd_linear_bf16(const void* h, int64_t h_stride, const void* W, int64_t w_stride, void* out,
                    int64_t out_stride, int R, int H, int V, void* stream);
+
+/* ---- teacher LM head fused with the top-k selection statistics (train.py:60-94 on-the-fly top-k,
+ * extract_teacher_logits.py:109-129) -----------------------------------------------------------------------------
+ * kd_head_logits_stats = kd_linear_bf16 whose epilogue also leaves, computed from the same bf16-rounded logits,
+ *   pmax [R][pmax_stride] bf16 : maximum of every 32-column piece of a row (pieces past V hold -inf),
+ *   part [R][part_stride] float2: partial (max, sum exp(x - max)) records of the row; *n_part (host int) receives how
+ *                                 many of them are written per row for this (R, V);
+ * kd_head_topk_select then produces log_softmax -> top-k (fp16 values, int32 indices; same ordering, tie rule and
+ * value rounding as kd_topk_logprobs on these logits) by merging the records and reading only the pieces whose
+ * maximum reaches the k-th largest one - a few KB per row instead of the row.  Indices are identical to
+ * kd_topk_logprobs on the same scratch; values agree to the last bit of the fp32 log-sum-exp (other summation order).
+ * kd_head_topk_layout reports the strides to allocate for a vocabulary of V columns (any R). */
+int kd_head_topk_layout(int V, int* pmax_stride, int* part_stride);
+int kd_head_logits_stats(const void* h, int64_t h_stride, const void* W, int64_t w_stride, void* out,
+                         int64_t out_stride, void* pmax, int pmax_stride, void* part, int part_stride,
+                         int* n_part, int R, int H, int V, void* stream);
+int kd_head_topk_select(const void* logits, int64_t row_stride, const void* pmax, int pmax_stride,
+                        const void* part, int part_stride, int n_part, int64_t R, int V, int k, void* out_v,
+                        int32_t* out_i, void* stream);
 
 /* Plain bf16 GEMM on the same tcgen05 pipeline (test hook for the K1 building block), fp32 out:
  *   C[M,N] (ldc) = op(A) * op(B)^T with

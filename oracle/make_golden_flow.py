@@ -53,10 +53,20 @@ def tiny_qwen3(vocab, hidden, seed, head_scale=2.0):
     return model, cfg
 
 
-def run(ref_train, name, top_k, with_cache):
+def bf16_head_input(model):
+    """Test double of a bf16 LM head on an fp32 body: the final norm's output is rounded to bf16 in the forward
+    (straight-through in the backward), so `lm_head(hidden)` multiplies bf16-representable operands exactly as a
+    tensor-core head does.  The model is a fixture; compute_loss / DistillationLoss stay the unmodified reference."""
+    model.model.norm.register_forward_hook(lambda mod, args, out: out + (out.bfloat16().float() - out).detach())
+    return model
+
+
+def run(ref_train, name, top_k, with_cache, bf16_head=False):
     V, Vt, B, T = 512, 544, 2, 40
     student, scfg = tiny_qwen3(V, 32, 1)
     teacher, tcfg = tiny_qwen3(Vt if top_k > 0 else V, 64, 2)
+    if bf16_head:
+        bf16_head_input(student)
     g = torch.Generator().manual_seed(3)
     ids = torch.randint(0, V, (B, T), generator=g)
     labels = ids.clone()
@@ -68,8 +78,13 @@ def run(ref_train, name, top_k, with_cache):
     extra = {}
     if with_cache:  # pre-computed cache as extract_teacher_logits.py:109-129 writes it
         with torch.no_grad():
-            lp = torch.log_softmax(teacher(input_ids=ids).logits[..., :V], dim=-1)
-            v, i = torch.topk(lp, top_k, dim=-1)
+            if bf16_head:  # a bf16 teacher (what the extractor runs on a GPU): bf16 hidden x bf16 W -> bf16 logits
+                hid = teacher.model(input_ids=ids).last_hidden_state.bfloat16().float()
+                logits = (hid @ teacher.lm_head.weight[:V].float().t()).bfloat16()
+                lp = torch.log_softmax(logits, dim=-1)  # bf16 log-probs, as log_softmax of a bf16 tensor returns
+            else:
+                lp = torch.log_softmax(teacher(input_ids=ids).logits[..., :V], dim=-1)
+            v, i = torch.topk(lp.float(), top_k, dim=-1)
         inputs["teacher_top_k_v"] = v.to(torch.float16)
         inputs["teacher_top_k_i"] = i.to(torch.int32)
         extra = {"teacher_top_k_v": inputs["teacher_top_k_v"].numpy(), "teacher_top_k_i": inputs["teacher_top_k_i"].numpy()}
@@ -84,7 +99,7 @@ def run(ref_train, name, top_k, with_cache):
     out = {
         "student_cfg": np.array(repr(scfg)), "teacher_cfg": np.array(repr(tcfg)), "top_k": top_k,
         "input_ids": ids.numpy(), "labels": labels.numpy(), "speech_token_mask": mask.numpy(),
-        "loss": float(loss), "student_loss": logged["student_loss"], "teacher_loss": logged["teacher_loss"],
+        "bf16_head_input": int(bf16_head), "loss": float(loss), "student_loss": logged["student_loss"], "teacher_loss": logged["teacher_loss"],
         "distill_loss": logged["distill_loss"],
         "grad_lm_head": student.lm_head.weight.grad.numpy(), "grad_embed": student.model.embed_tokens.weight.grad.numpy(),
     }
@@ -103,3 +118,6 @@ if __name__ == "__main__":
     run(rt, "dense_teacher", 0, False)
     # (a pre-computed cache, run(rt, "cached_topk16", 16, True), gives the same numbers as the on-the-fly run:
     #  the GPU test derives that case from the first fixture instead of storing the weights twice)
+    # bf16 heads on both sides: the cache comes from a bf16 teacher head and the student's head input is
+    # bf16-representable, so the replay through the tensor-core head has nothing left to differ by (1e-3 bar)
+    run(rt, "bf16head_cached_topk16", 16, True, bf16_head=True)

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("KD_B200_LIB") or os.path.join(_HERE, "libkd_b200.so")
 
 KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
 KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
-ABI_VERSION = 3  # KD_ABI_VERSION in include/kd_b200.h
+ABI_VERSION = 4  # KD_ABI_VERSION in include/kd_b200.h
 KD_RANGE_FIRST, KD_RANGE_LAST = 1, 2
 KD_GRAD_DH_F32 = 0x100
 
@@ -59,6 +59,10 @@ SIGNATURES = {
     "kd_ce_fused_linear_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i64,
                                       _vp, _i64, _i64, _i32, _vp, _sz, _vp, _sz, _vp]),
     "kd_linear_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "kd_head_topk_layout": (_i32, [_i32, _c.POINTER(_i32), _c.POINTER(_i32)]),
+    "kd_head_logits_stats": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i32, _c.POINTER(_i32), _i32, _i32,
+                                    _i32, _vp]),
+    "kd_head_topk_select": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "kd_gemm_bf16": (_i32, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
 }
 
@@ -86,8 +90,46 @@ def load():
         fn.argtypes = args
     if lib.kd_version() != ABI_VERSION:
         raise KdError(f"libkd_b200 ABI version {lib.kd_version()} != {ABI_VERSION}")
+    if os.environ.get("KD_NVTX", "1") != "0":
+        _add_nvtx_ranges(lib)
     _lib = lib
     return lib
+
+
+# entry points that only query (no kernels): no range
+_NO_RANGE = {"kd_head_topk_layout", "kd_version", "kd_last_error", "kd_launch_count", "kd_device_info", "kd_stream_workspace_bytes",
+             "kd_fused_workspace_bytes", "kd_fused_logit_cache_bytes", "kd_fused_merge_workspace_bytes",
+             "kd_fused_bwd_trace_begin", "kd_fused_bwd_trace_read"}
+
+
+def _add_nvtx_ranges(lib):
+    """NVTX range around every launching C-ABI call (tracing row): a timeline tool shows the path's calls
+    by name.  A push / pop pair costs well under a microsecond; KD_NVTX=0 leaves the raw ctypes functions."""
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return
+        push, pop = torch.cuda.nvtx.range_push, torch.cuda.nvtx.range_pop
+        push("kd_b200:init")
+        pop()
+    except Exception:  # NVTX is optional tooling, never a reason to fail
+        return
+
+    def wrap(name, fn):
+        def call(*args):
+            push(name)
+            try:
+                return fn(*args)
+            finally:
+                pop()
+
+        call.__name__ = name
+        return call
+
+    for name in SIGNATURES:
+        if name not in _NO_RANGE:
+            setattr(lib, name, wrap(name, getattr(lib, name)))
 
 
 def check(rc, what):

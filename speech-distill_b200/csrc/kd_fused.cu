@@ -695,6 +695,135 @@ struct GradEpi {
   }
 };
 
+// ---- teacher head feeding the top-k compaction (train.py:60-94, extract_teacher_logits.py:109-129) -------------
+// logits tile -> bf16 -> row-block scratch (per-warp TMA stores, as the forward's logit cache) and, from the SAME
+// rounded values, what the selection kernel (kd_topk.cu, kd_head_select_kernel) needs so that it never re-reads the
+// row: the maximum of every 32-column piece (bf16, exact) and this thread's online (max, sum exp) over its pieces
+// of the work unit.  The k-th largest piece maximum bounds the k-th logit from below, so the selection scans only
+// the ~k pieces (64 bytes each) whose maximum reaches it instead of the row's 2 V bytes.
+struct HeadParams {
+  int R, V;
+  __nv_bfloat16* pmax;  // [R][pmax_stride], piece j = columns [32 j, 32 j + 32); pieces past V hold -inf
+  int pmax_stride;      // = 8 * number of 256-column tiles
+  float2* part;         // [R][part_stride]: (m, s) of (vocabulary range, column group), s = sum 2^((x - m) log2 e)
+  int part_stride;      // = kColGroups * number of ranges
+};
+
+struct HeadEpi {
+  using Params = HeadParams;
+  static constexpr int kYSlots = 0;
+  static constexpr int kGSlots = 1;
+#ifndef KD_HEAD_STAGES
+#define KD_HEAD_STAGES 8  // as many operand stages as fit (6); 4 and 5 measured slower (tools/head_parts.py, r2i)
+#endif
+  static constexpr int kMaxStages = KD_HEAD_STAGES;
+  static constexpr int kBoundThreads = kThreads;
+  const Params& p;
+  EpiThread t;
+  int row, range, m0;
+  bool valid;
+  float m, s;
+
+  __device__ HeadEpi(const Params& p_, const EpiThread& t_) : p(p_), t(t_) {}
+
+  __device__ void begin_unit(const Geom&, int m0_, int range_) {
+    m0 = m0_;
+    row = m0 + t.row_in_tile;
+    range = range_;
+    valid = row < p.R;
+    m = -CUDART_INF_F;
+    s = 0.f;
+  }
+
+  template <int CG>
+  __device__ void tile(const Geom& g, int n_blk, uint32_t tmem_acc, uint32_t tempty_bar) {
+#pragma unroll 1
+    for (int c = 0; c < kSteps; ++c) {
+      uint32_t raw0[16], raw1[16];
+      __syncwarp();
+      const uint32_t taddr = tmem_acc + t.tmem_lane_off + (uint32_t)(c * kStepCols + t.cgrp * 32);
+      tmem_ld16(taddr, raw0);
+      tmem_ld16(taddr + 16u, raw1);
+      tmem_ld_wait();
+      if (c == kSteps - 1) {
+        fence_before_sync();
+        __syncwarp();
+        if (t.lane == 0) release_tmem<CG>(tempty_bar);
+      }
+      const int col0 = n_blk * BN + c * kStepCols + t.cgrp * 32;
+      const int nrem = p.V - col0;
+      // round to bf16 once; everything below (store, maximum, exponentials) sees the rounded values
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(raw0[2 * j]), __uint_as_float(raw0[2 * j + 1]));
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(raw1[2 * j]), __uint_as_float(raw1[2 * j + 1]));
+        w[j] = *reinterpret_cast<uint32_t*>(&h0);
+        w[8 + j] = *reinterpret_cast<uint32_t*>(&h1);
+      }
+      // per-warp [32 rows x 32 columns] box (2 KB, 64-byte swizzled rows) -> TMA store; no CTA-wide barrier
+      const uint32_t wbuf = t.g_base + (uint32_t)(t.epi_tid >> 5) * 2048u;
+      const uint32_t wrow = wbuf + (uint32_t)t.lane * 64u;
+      const uint32_t wswz = ((uint32_t)t.lane >> 1) & 3u;
+      if (t.lane == 0) bulk_wait_read_all();  // the previous step's store has read the box
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sts128(wrow + (((uint32_t)q ^ wswz) << 4), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (t.lane == 0 && nrem > 0) {  // rows >= R and columns >= V are clipped by the tensor map
+        tma_store_2d(t.tma_g, wbuf, col0, m0 + (t.row_in_tile & ~31));
+        bulk_commit();
+      }
+      if (!valid) continue;
+      __nv_bfloat16* pm = p.pmax + (size_t)row * p.pmax_stride + (col0 >> 5);
+      if (nrem <= 0) {  // piece past the vocabulary (last tile only)
+        *pm = __float2bfloat16(-CUDART_INF_F);
+        continue;
+      }
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        f[2 * j] = __uint_as_float(w[j] << 16);
+        f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+      if (nrem < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j >= nrem) f[j] = -CUDART_INF_F;
+      }
+      float vm = f[0];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) vm = fmaxf(vm, f[j]);
+      *pm = __float2bfloat16(vm);  // exact: vm is one of the bf16 values
+      if (vm > m) {
+        s *= exp_diff(m, vm, kLog2e);
+        m = vm;
+      }
+      if (m != -CUDART_INF_F) {
+        const float off = m * kLog2e;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          p0 += ex2(fmaf(f[j], kLog2e, -off));
+          p1 += ex2(fmaf(f[j + 1], kLog2e, -off));
+          p2 += ex2(fmaf(f[j + 2], kLog2e, -off));
+          p3 += ex2(fmaf(f[j + 3], kLog2e, -off));
+        }
+        s += (p0 + p1) + (p2 + p3);
+      }
+    }
+  }
+
+  __device__ void end_unit(const Geom&) {
+    if (valid) p.part[(size_t)row * p.part_stride + range * kColGroups + t.cgrp] = make_float2(m, s);
+  }
+  __device__ void finish() {
+    if (t.lane == 0) bulk_wait_all();
+  }
+};
+
 // ---- backward from the logit cache: gradient chunk without the recompute GEMM ---------------------
 // Logit cache (written by FwdEpi, read here).  The forward keeps the first `tiles` 256-column tiles of the logits
 // of every row in a buffer whose size is a caller-given constant (so the path's peak memory stays independent
@@ -2816,6 +2945,72 @@ extern "C" int kd_linear_bf16(const void* h, int64_t h_stride, const void* W, in
   gp.tau = 1.0f;
   return launch_umma<GradEpi<__nv_bfloat16, false, false, false, false, true>, false, false>(ta, tb, ta, tg, g, gp,
                                                                                              (cudaStream_t)stream);
+}
+
+// ---- teacher head -> top-k without the teacher's [R,V] logits: GEMM + selection statistics --------------------
+// Work units of the head GEMM: n_per_unit consecutive 256-column tiles of one row block (the online (m, s) of a
+// thread lives in registers across them).  A row block is only a few m blocks tall, so the unit count is chosen to
+// fill whole waves of the persistent CTA pairs: the largest n_per_unit within 2 % of the best wave efficiency.
+static int head_n_per_unit(int R, int V) {
+  const int m_blks = cdiv(R, tile_m()), n_blks = cdiv(V, BN);
+  const int slots = sm_count() / cta_group() >= 1 ? sm_count() / cta_group() : 1;
+  double best = 0.0;
+  double eff[33] = {};
+  for (int npu = 1; npu <= 32; ++npu) {
+    const int units = m_blks * cdiv(n_blks, npu);
+    const int waves = cdiv(units, slots);
+    eff[npu] = (double)m_blks * n_blks / ((double)waves * slots * npu);
+    if (eff[npu] > best) best = eff[npu];
+  }
+  for (int npu = 32; npu >= 1; --npu)
+    if (eff[npu] >= best - 0.02) return npu;
+  return 1;
+}
+
+extern "C" int kd_head_topk_layout(int V, int* pmax_stride, int* part_stride) {
+  if (V <= 0 || !pmax_stride || !part_stride) {
+    set_error("kd_head_topk_layout: bad argument");
+    return 1;
+  }
+  *pmax_stride = 8 * cdiv(V, BN);           // 32-column pieces of whole 256-column tiles
+  *part_stride = kColGroups * cdiv(V, BN);  // upper bound (one tile per range)
+  return 0;
+}
+
+extern "C" int kd_head_logits_stats(const void* h, int64_t h_stride, const void* W, int64_t w_stride, void* out,
+                                    int64_t out_stride, void* pmax, int pmax_stride, void* part, int part_stride,
+                                    int* n_part, int R, int H, int V, void* stream) {
+  DeviceGuard device_guard(h);
+  if (check_common(h, h_stride, W, w_stride, R, H, V, 1.0f, "kd_head_logits_stats")) return 1;
+  if (!out || !pmax || !part || !n_part) {
+    set_error("kd_head_logits_stats: null output");
+    return 1;
+  }
+  const int npu = head_n_per_unit(R, V);
+  const int ranges = cdiv(cdiv(V, BN), npu);
+  if (pmax_stride < 8 * cdiv(V, BN) || part_stride < kColGroups * ranges) {
+    set_error("kd_head_logits_stats: pmax_stride / part_stride smaller than kd_head_topk_layout reports");
+    return 1;
+  }
+  *n_part = kColGroups * ranges;
+  CUtensorMap ta, tb, tg;
+  if (make_tmap(&ta, h, (uint64_t)H, (uint64_t)R, (uint64_t)h_stride, BM, "hidden")) return 1;
+  if (make_tmap(&tb, W, (uint64_t)H, (uint64_t)V, (uint64_t)w_stride, b_box_rows(), "lm_head weight")) return 1;
+  if (make_tmap(&tg, out, (uint64_t)V, (uint64_t)R, (uint64_t)out_stride, 32, "logits out", 32)) return 1;
+  Geom g = {};
+  g.num_m_blk = cdiv(R, tile_m());
+  g.num_n_blk = cdiv(V, BN);
+  g.num_k_blk = cdiv(H, BK);
+  g.n_per_unit = npu;
+  g.num_units = g.num_m_blk * ranges;
+  HeadParams hp = {};
+  hp.R = R;
+  hp.V = V;
+  hp.pmax = reinterpret_cast<__nv_bfloat16*>(pmax);
+  hp.pmax_stride = pmax_stride;
+  hp.part = reinterpret_cast<float2*>(part);
+  hp.part_stride = part_stride;
+  return launch_umma<HeadEpi, false, false>(ta, tb, ta, tg, g, hp, (cudaStream_t)stream);
 }
 
 extern "C" int kd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,

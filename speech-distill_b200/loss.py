@@ -260,6 +260,13 @@ class _KDFusedLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, y, row_target, n_valid, n_norm, tau, alpha, dw_row_begin, v_chunk, reduce_fn, grad_dtype,
                 topk_v=None, topk_i=None, grad_sync=None, compact=False, cache_mb=None):
+        # fp32 / fp16 operands (fp32 master weights, autocast training) are cast to bf16 HERE, inside the node, so that
+        # the backward can hand their gradients back from the kernels' fp32 accumulators without a bf16 rounding
+        ctx.in_dtypes = (h.dtype, W.dtype)
+        if h.dtype != torch.bfloat16:
+            h = h.to(torch.bfloat16)
+        if W.dtype != torch.bfloat16:
+            W = W.to(torch.bfloat16)
         inv = n_rows = None
         if compact:  # valid rows to the front; every GEMM tile behind them is skipped (kd_rows.cu)
             perm, inv, row_target, n_rows = compact_rows(row_target)
@@ -299,11 +306,18 @@ class _KDFusedLinear(torch.autograd.Function):
         w_ce = gt * alpha + (zero if g_task is None else g_task.detach().float())
         w_kl = gt * (1.0 - alpha) + (zero if g_distill is None else g_distill.detach().float())
         coef = torch.stack([w_ce.reshape(()), w_kl.reshape(())]).contiguous()
+        h_dt, w_dt = ctx.in_dtypes
+        w_grad_dtype = grad_dtype if w_dt == torch.bfloat16 else torch.float32
+        dh_fp32 = h_dt != torch.bfloat16 and w_grad_dtype != torch.float32  # dH fp32 beside a bf16 dW
         dH, dW = _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_kind, dw_row_begin,
-                                 v_chunk, grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk,
-                                 ctx.grad_sync, n_rows=n_rows, cache=ctx.cache)
+                                 v_chunk, w_grad_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.ws, topk,
+                                 ctx.grad_sync, dh_fp32=dh_fp32, n_rows=n_rows, cache=ctx.cache)
         if inv is not None and dH is not None:
             dH = gather_rows(dH, inv)  # back to the original row order; rows that are not scored get zeros
+        if dH is not None and h_dt != torch.bfloat16 and dH.dtype != h_dt:
+            dH = dH.to(h_dt)
+        if dW is not None and w_dt != torch.bfloat16 and dW.dtype != w_dt:
+            dW = dW.to(w_dt)
         return dH, dW, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
@@ -403,15 +417,14 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     """
     require_cuda(hidden, lm_head_weight)
     # the tensor-core path computes in bf16 with fp32 accumulation; fp32 / fp16 operands (fp32 master weights,
-    # autocast training) are cast here, inside autograd, so their gradients come back in their own dtype
-    if hidden.dtype != torch.bfloat16:
-        if hidden.dtype not in (torch.float32, torch.float16):
-            raise TypeError(f"hidden states must be bf16, fp16 or fp32, got {hidden.dtype}")
-        hidden = hidden.to(torch.bfloat16)
-    if lm_head_weight.dtype != torch.bfloat16:
-        if lm_head_weight.dtype not in (torch.float32, torch.float16):
-            raise TypeError(f"lm_head weight must be bf16, fp16 or fp32, got {lm_head_weight.dtype}")
-        lm_head_weight = lm_head_weight.to(torch.bfloat16)
+    # autocast training) are cast inside the autograd node, and their gradients come back in their own dtype straight
+    # from the kernels' fp32 accumulators (no bf16 rounding in between)
+    if hidden.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+        raise TypeError(f"hidden states must be bf16, fp16 or fp32, got {hidden.dtype}")
+    if lm_head_weight.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+        raise TypeError(f"lm_head weight must be bf16, fp16 or fp32, got {lm_head_weight.dtype}")
+    if _return_ctx:
+        hidden, lm_head_weight = hidden.to(torch.bfloat16), lm_head_weight.to(torch.bfloat16)
     if hidden.dim() != 3:
         raise ValueError("hidden must be [B, T, H]")
     B, T, H = hidden.shape

@@ -65,18 +65,34 @@ def linear_bf16(hidden, weight, out=None):
     return out
 
 
-def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024):
+def head_topk_layout(V):
+    """(pmax_stride, part_stride) of the selection statistics for a vocabulary of V columns (kd_head_topk_layout)."""
+    import ctypes
+
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    check(_lib.load().kd_head_topk_layout(int(V), ctypes.byref(a), ctypes.byref(b)), "kd_head_topk_layout")
+    return a.value, b.value
+
+
+def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024, fused=True):
     """Teacher LM head -> log_softmax -> top-k without the teacher's [B,T,V] logits
     (train.py:60-94 on-the-fly mode, extract_teacher_logits.py:109-129).
 
     hidden [..., H_t] bf16 (the teacher body's last hidden states), lm_head_weight [V_t, H_t] bf16;
     ``vocab_size`` truncates the teacher vocabulary to the student's (train.py:82-83) by dropping weight rows,
-    which is the same as slicing the logits.  Rows are processed ``row_block`` at a time: the head GEMM of
-    block b + 1 (tensor-core bound) runs on the current stream while the compaction of block b (HBM bound) runs
-    on a side stream, through two fixed scratch buffers of row_block x V bf16.
-    Returns (values fp16 [..., k], indices int32 [..., k]) exactly as ``teacher_topk_logprobs`` would on the
-    bf16 logits of the same GEMM.
+    which is the same as slicing the logits.  Rows are processed ``row_block`` at a time through two fixed scratch
+    buffers of row_block x V bf16: the head GEMM of block b + 1 (tensor-core bound, current stream) runs beside the
+    selection of block b (side stream).
+
+    ``fused=True`` (default): the GEMM's epilogue (kd_head_logits_stats) also leaves the maximum of every 32-column
+    piece and partial log-sum-exp records, and the selection (kd_head_topk_select) reads only the ~k pieces per row
+    that can hold a top-k entry - a few KB per row, so it no longer competes with the next block's GEMM for HBM and
+    SMs.  ``fused=False``: plain kd_linear_bf16 + the full-row compaction kernel (kd_topk_logprobs).  Both return
+    (values fp16 [..., k], indices int32 [..., k]); the indices are identical, the values can differ in the last bit
+    of the fp32 log-sum-exp (summation order) before their rounding to bf16 / fp16.
     """
+    import ctypes
+
     require_cuda(hidden, lm_head_weight)
     lead = hidden.shape[:-1]
     H = hidden.shape[-1]
@@ -103,38 +119,67 @@ def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024
         return out_v.reshape(*lead, k), out_i.reshape(*lead, k)
     rb = max(1, min(int(row_block), R))
     ld = -(-V // 8) * 8
-    scratch = [torch.empty((rb, ld), dtype=torch.bfloat16, device=dev) for _ in range(2 if R > rb else 1)]
-    main = torch.cuda.current_stream(dev)
+    n_sets = 2 if R > rb else 1
+    scratch = [torch.empty((rb, ld), dtype=torch.bfloat16, device=dev) for _ in range(n_sets)]
+    if fused:
+        pmax_stride, part_stride = head_topk_layout(V)
+        pmax = [torch.empty((rb, pmax_stride), dtype=torch.bfloat16, device=dev) for _ in range(n_sets)]
+        part = [torch.empty((rb, part_stride, 2), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    caller = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
+    # fused: the GEMMs go to an internal high-priority stream, so that when a GEMM and a selection kernel are both
+    # waiting for SMs the persistent GEMM CTAs are placed first and the selection's CTAs fill the shared memory the
+    # GEMM leaves free (the caller's stream usually has the lowest priority there is and cannot be outranked by less)
+    main = _side_stream(dev, high_priority=True) if fused and n_sets > 1 else caller
+    if main is not caller:
+        main.wait_stream(caller)
     filled = [torch.cuda.Event() for _ in scratch]
     drained = [None for _ in scratch]
     lib = _lib.load()
     for n, r0 in enumerate(range(0, R, rb)):
         r1 = min(r0 + rb, R)
-        s = n % len(scratch)
+        s = n % n_sets
         if drained[s] is not None:
-            main.wait_event(drained[s])  # the compaction that read this scratch two blocks ago is done
-        logits = linear_bf16(h2[r0:r1], W, scratch[s][: r1 - r0, :V])
+            main.wait_event(drained[s])  # the selection that read this scratch two blocks ago is done
+        hb = h2[r0:r1]
+        logits = scratch[s][: r1 - r0, :V]
+        if fused:
+            n_part = ctypes.c_int(0)
+            check(lib.kd_head_logits_stats(hb.data_ptr(), hb.stride(0), W.data_ptr(), W.stride(0), logits.data_ptr(),
+                                           logits.stride(0), pmax[s].data_ptr(), pmax_stride, part[s].data_ptr(),
+                                           part_stride, ctypes.byref(n_part), r1 - r0, H, V, main.cuda_stream),
+                  "kd_head_logits_stats")
+        else:
+            linear_bf16(hb, W, logits)
         filled[s].record(main)
         with torch.cuda.stream(side):
             side.wait_event(filled[s])
-            check(lib.kd_topk_logprobs(logits.data_ptr(), dtype_code(logits.dtype), r1 - r0, V, logits.stride(0),
-                                       int(k), out_v[r0:r1].data_ptr(), out_i[r0:r1].data_ptr(), stream_ptr(dev)),
-                  "kd_topk_logprobs")
+            if fused:
+                check(lib.kd_head_topk_select(logits.data_ptr(), logits.stride(0), pmax[s].data_ptr(), pmax_stride,
+                                              part[s].data_ptr(), part_stride, n_part.value, r1 - r0, V, int(k),
+                                              out_v[r0:r1].data_ptr(), out_i[r0:r1].data_ptr(), stream_ptr(dev)),
+                      "kd_head_topk_select")
+            else:
+                check(lib.kd_topk_logprobs(logits.data_ptr(), dtype_code(logits.dtype), r1 - r0, V, logits.stride(0),
+                                           int(k), out_v[r0:r1].data_ptr(), out_i[r0:r1].data_ptr(), stream_ptr(dev)),
+                      "kd_topk_logprobs")
             ev = torch.cuda.Event()
             ev.record(side)
             drained[s] = ev
     for ev in drained:
         if ev is not None:
-            main.wait_event(ev)
+            caller.wait_event(ev)
+    if main is not caller:
+        caller.wait_stream(main)
     return out_v.reshape(*lead, k), out_i.reshape(*lead, k)
 
 
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+def _side_stream(dev, high_priority=False):
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    key = (idx, bool(high_priority))
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1 if high_priority else 0)
     return _SIDE_STREAMS[key]

@@ -143,7 +143,8 @@ int main(void) {
                  (void*)kd_fused_linear_bwd,
                  (void*)kd_fused_linear_bwd_range, (void*)kd_fused_linear_fwd_partial,
                  (void*)kd_fused_merge_workspace_bytes, (void*)kd_fused_merge_ranks, (void*)kd_ce_fused_linear_fwd,
-                 (void*)kd_ce_fused_linear_bwd, (void*)kd_linear_bf16, (void*)kd_gemm_bf16};
+                 (void*)kd_ce_fused_linear_bwd, (void*)kd_linear_bf16, (void*)kd_head_topk_layout,
+                 (void*)kd_head_logits_stats, (void*)kd_head_topk_select, (void*)kd_gemm_bf16};
   printf("%d %d\n", kd_version(), (int)(sizeof(fns) / sizeof(fns[0])));
   return kd_version() == KD_ABI_VERSION ? 0 : 1;
 }

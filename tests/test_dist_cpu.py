@@ -42,7 +42,7 @@ def _worker(rank, world, port, out_q):
     gw[sl] = grad
     D.allreduce_grad_(gw, bucket_rows=1)
     if rank == 0:
-        out_q.put(([float(x) for x in losses], int(n), gw.numpy()))
+        out_q.put(([float(x.detach()) for x in losses], int(n), gw.numpy()))
     dist.destroy_process_group()
 
 
@@ -65,7 +65,7 @@ def test_token_shard_reduction_matches_single_process():
     lab[0, :5] = -100
     (ref, gref) = O.reference_loss_and_grad(z, lab, teacher_logits=y, temperature=2.0, alpha=0.5)
     assert n == int((lab[:, 1:] != -100).sum())
-    np.testing.assert_allclose(losses, [float(x) for x in ref], rtol=1e-12)
+    np.testing.assert_allclose(losses, [float(x.detach()) for x in ref], rtol=1e-12)
     np.testing.assert_allclose(grad, gref.numpy(), rtol=1e-9, atol=1e-15)
 
 

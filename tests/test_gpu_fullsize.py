@@ -44,7 +44,8 @@ def test_k1_dense_configs1_full_size_vs_oracle():
         assert abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))  # what fp32 statistics deliver
     _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h, W, labels, teacher_logits=y, temperature=2.0, alpha=0.5)
     assert rel_err(gh32, gh_ref) < 1e-3 and rel_err(gw32, gw_ref) < 1e-3    # north_star tolerance (fp32 accumulate)
-    assert rel_err(hc.grad.float(), gh_ref) < 6e-3 and rel_err(Wc.grad.float(), gw_ref) < 6e-3
+    # bf16 outputs: one rounding of the leaf gradients on top (half an ulp = 2e-3 of the largest entry)
+    assert rel_err(hc.grad.float(), gh_ref) < 4e-3 and rel_err(Wc.grad.float(), gw_ref) < 4e-3
     cos = torch.nn.functional.cosine_similarity(Wc.grad.float().flatten(), gw_ref.flatten(), dim=0)
     assert float(cos) > 0.99999
 
@@ -96,13 +97,14 @@ def test_stage1_configs3_full_size_masked_rows():
     loss.backward()
     assert abs(float(loss) - float(loss_ref)) <= 2e-5 * float(loss_ref)
     assert float(Wc.grad[:old].abs().max()) == 0.0
-    assert rel_err(Wc.grad[old:].float(), gw_ref[old:]) < 6e-3
-    assert rel_err(hc.grad.float(), gh_ref) < 6e-3
+    assert rel_err(Wc.grad[old:].float(), gw_ref[old:]) < 4e-3
+    assert rel_err(hc.grad.float(), gh_ref) < 4e-3
 
 
 def test_teacher_head_topk_configs2_full_size():
     """BASELINE configs[2] (teacher part): SoulX-1.7B head, hidden 2048, B=16, T=512 -> top-64; the row-block
-    pipeline equals the compaction of the materialised logits of the same GEMM, bit for bit."""
+    pipeline (GEMM epilogue statistics + piece-wise selection) picks the same indices as the compaction of the
+    materialised logits of the same GEMM, bit for bit."""
     import speech_distill_b200 as K
 
     g = torch.Generator(device="cuda").manual_seed(9)
@@ -112,6 +114,111 @@ def test_teacher_head_topk_configs2_full_size():
     v, i = K.teacher_head_topk(h, W, 64)
     logits = K.linear_bf16(h, W)
     v2, i2 = K.teacher_topk_logprobs(logits, 64)
-    assert torch.equal(i, i2) and torch.equal(v, v2)
+    assert torch.equal(i, i2)  # indices: bit for bit
+    diff = (v.float() - v2.float()).abs()  # values: the fp32 log-sum-exp is summed in another order (GEMM epilogue)
+    assert bool((diff <= 2.0 ** -7 * v2.float().abs()).all()) and float((diff > 0).float().mean()) < 1e-3
+    vu, iu = K.teacher_head_topk(h, W, 64, fused=False)
+    assert torch.equal(iu, i2) and torch.equal(vu, v2)  # the unfused row-block pipeline: bit for bit
     sel = torch.gather(logits.float(), -1, i.long())
     assert torch.equal(sel, torch.topk(logits.float(), 64, -1).values)  # a valid top-k of those logits
+
+
+class _FullSizeRangeStub:
+    """dist.GradSync's interface without a process group (one GPU): the real range plan; `reduce_rows` does what an
+    all-reduce over identical ranks would leave behind on a side stream that waits for the range - it reads and
+    rewrites the finished row block while the next range's GEMMs run."""
+
+    def __init__(self, n_ranges):
+        self.n_ranges, self.blocks = n_ranges, []
+        self.side = torch.cuda.Stream()
+        self.done = []
+
+    def ranges(self, V, row_begin, v_chunk):
+        from speech_distill_b200.dist import plan_ranges
+
+        return plan_ranges(V, row_begin, v_chunk, self.n_ranges)
+
+    def sm_limit(self):
+        return 0
+
+    def reduce_rows(self, grad, r0, r1):
+        self.blocks.append((r0, r1))
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            grad[r0:r1].mul_(2.0)  # world_size = 2 ranks holding the same gradient: SUM = 2 x (exact in bf16)
+            ev = torch.cuda.Event()
+            ev.record()
+        self.done.append(ev)
+
+    def finish(self):
+        for ev in self.done:
+            torch.cuda.current_stream().wait_event(ev)
+        self.done = []
+
+
+def test_gradsync_ranges_configs1_full_size():
+    """The overlapped dW exchange at BASELINE configs[1] size: 6 vocabulary ranges handed to a stand-in all-reduce on
+    a side stream while the following ranges run = the one-call backward (dH bit for bit, dW exactly 2 x)."""
+    import speech_distill_b200 as K
+
+    h, W, y, labels = _inputs(8, 512, 77)
+
+    def run(sync):
+        hc, Wc = h.clone().requires_grad_(True), W.clone().requires_grad_(True)
+        out = K.fused_linear_kd_loss(hc, Wc, labels, teacher_logits=y, temperature=2.0, alpha=0.5, grad_sync=sync)
+        out[0].backward()
+        torch.cuda.synchronize()
+        return hc.grad, Wc.grad
+
+    gh0, gw0 = run(None)
+    stub = _FullSizeRangeStub(6)
+    gh1, gw1 = run(stub)
+    assert len(stub.blocks) == 6 and stub.blocks[0][0] == 0 and stub.blocks[-1][1] == V_FULL
+    assert all(a[1] == b[0] for a, b in zip(stub.blocks, stub.blocks[1:]))
+    assert torch.equal(gh0, gh1)
+    assert torch.equal(gw0 * 2, gw1)
+
+
+@pytest.mark.parametrize("cache_mb", [0, 1024])
+def test_k1_peak_activation_memory_independent_of_V(cache_mb):
+    """north_star: peak activation memory of the fused step does not depend on V.  Measured with the caching
+    allocator's high-water mark around forward + backward at V = 152,936 and 2 V = 305,872 (R = 4096): after
+    subtracting what is resident before the step (inputs, W) and the gradients it returns (dW [V,H], dH [R,H]) the
+    two peaks are equal - gradient chunk buffers, fp32 dH accumulator, fp16 operand copies, row records and a logit
+    cache whose size is a caller-chosen constant (here 0 and 1 GB: six whole 18,944-column chunks at either V)."""
+    import speech_distill_b200 as K
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, T = 8, 512
+    peaks = {}
+    for mult in (1, 2):
+        V = V_FULL * mult
+        h = torch.randn(B, T, H_STUDENT, device="cuda", generator=g).bfloat16().requires_grad_(True)
+        W = (torch.randn(V, H_STUDENT, device="cuda", generator=g) * (2.0 / H_STUDENT ** 0.5)).bfloat16().requires_grad_(True)
+        y = torch.empty(B, T, V, device="cuda", dtype=torch.bfloat16)
+        for b in range(B):
+            y[b] = (torch.randn(T, V, device="cuda", generator=g) * 2).bfloat16()
+        labels = torch.randint(0, V, (B, T), device="cuda", generator=g)
+        for _ in range(2):  # the first call also sizes the library's per-device pools
+            h.grad = W.grad = None
+            out = K.fused_linear_kd_loss(h, W, labels, teacher_logits=y, temperature=2.0, alpha=0.5,
+                                         logit_cache_mb=cache_mb)
+            out[0].backward()
+            del out
+        h.grad = W.grad = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        out = K.fused_linear_kd_loss(h, W, labels, teacher_logits=y, temperature=2.0, alpha=0.5,
+                                     logit_cache_mb=cache_mb)
+        out[0].backward()
+        torch.cuda.synchronize()
+        grads = W.grad.numel() * 2 + h.grad.numel() * 2
+        peaks[mult] = torch.cuda.max_memory_allocated() - base - grads
+        assert float(out[0]) > 0
+        del h, W, y, labels, out
+        torch.cuda.empty_cache()
+    print(f"peak activation bytes (cache budget {cache_mb} MB): V {peaks[1] / 2**20:.1f} MiB, 2V {peaks[2] / 2**20:.1f} MiB")
+    assert abs(peaks[2] - peaks[1]) <= 4 * 2 ** 20, peaks   # allocator rounding only (2 MiB blocks)
+    assert peaks[1] < (cache_mb + 600) * 2 ** 20, peaks        # 2 x 155 MB chunks + 16 MB dH + records (+ cache)

@@ -89,7 +89,7 @@ def _run_fused(h, W, y, labels, tau, alpha, **kw):
                                  temperature=tau, alpha=alpha, **kw)
     out[0].backward()
     torch.cuda.synchronize()
-    return [float(o) for o in out], hc.grad, Wc.grad
+    return [float(o.detach()) for o in out], hc.grad, Wc.grad
 
 
 def test_fused_golden_f64():
@@ -99,8 +99,8 @@ def test_fused_golden_f64():
     y = torch.from_numpy(d["y"]).bfloat16()
     losses, gh, gw = _run_fused(h, W, y, torch.from_numpy(d["labels"]), float(d["tau"]), float(d["alpha"]))
     np.testing.assert_allclose(losses, d["losses"], rtol=1e-3)
-    assert rel_err(gh.float().cpu().numpy(), d["dh"]) < 6e-3  # bf16 G + bf16 output on a 18-row problem
-    assert rel_err(gw.float().cpu().numpy(), d["dW"]) < 6e-3
+    assert rel_err(gh.float().cpu().numpy(), d["dh"]) < 4e-3  # bf16 G + bf16 output on a 18-row problem
+    assert rel_err(gw.float().cpu().numpy(), d["dW"]) < 4e-3
 
 
 @pytest.mark.parametrize("B,T,H,V,tau,alpha,y_dtype", [
@@ -114,7 +114,7 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
     ref, gh_ref, gw_ref = O.fused_linear_reference(h.double(), W.double(), labels, teacher_logits=y.double(),
                                                    temperature=tau, alpha=alpha)
     losses, gh, gw = _run_fused(h, W, y, labels, tau, alpha)
-    for got, want in zip(losses, [float(x) for x in ref]):
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
     eh = rel_err(gh.float().cpu().numpy(), gh_ref.numpy())
     ew = rel_err(gw.float().cpu().numpy(), gw_ref.numpy())
@@ -130,7 +130,7 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
     # bits; the reference's own dlogits are bf16 with 8) against fp16 copies of h and W, so the fp32 accumulators
     # meet north_star's 1e-3; bf16 outputs add their own rounding, 2^-9 on the largest entry.  Bars:
     #  - fp32 accumulators < 1e-3 and better than the reference's all-bf16 GPU pipeline
-    #  - bf16 outputs no worse than 1.25 x that pipeline (or 2.2e-3) and < 6e-3
+    #  - bf16 outputs no worse than that pipeline (never asked to beat bf16's own half ulp, 2^-9) and < 4e-3
     rh, rw = _torch_bf16_pipeline(h, W, y, labels, tau, alpha)
     eh_ref = rel_err(rh.float().cpu().numpy(), gh_ref.numpy())
     ew_ref = rel_err(rw.float().cpu().numpy(), gw_ref.numpy())
@@ -138,8 +138,8 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
           f"torch-bf16 {ew_ref:.2e}")
     assert eh32 < 1e-3 and ew32 < 1e-3, (eh32, ew32)  # north_star: gradients within 1e-3 (fp32 accumulate)
     assert eh32 <= eh_ref and ew32 <= ew_ref, (eh32, eh_ref, ew32, ew_ref)
-    assert eh < 6e-3 and ew < 6e-3, (eh, ew)
-    assert eh <= max(1.25 * eh_ref, 2.2e-3) and ew <= max(1.25 * ew_ref, 2.2e-3), (eh, eh_ref, ew, ew_ref)
+    assert eh < 4e-3 and ew < 4e-3, (eh, ew)
+    assert eh <= max(eh_ref, 2.0 ** -9) and ew <= max(ew_ref, 2.0 ** -9), (eh, eh_ref, ew, ew_ref)
 
 
 def test_fused_equals_streaming_path():
@@ -150,7 +150,7 @@ def test_fused_equals_streaming_path():
     losses, gh, gw = _run_fused(h, W, y, labels, 2.0, 0.5)
     z = (h.cuda().float() @ W.cuda().float().t())
     out = K.kd_loss_on_logits(z, labels.cuda(), teacher_logits=y.cuda())
-    np.testing.assert_allclose(losses, [float(o) for o in out], rtol=2e-4)
+    np.testing.assert_allclose(losses, [float(o.detach()) for o in out], rtol=2e-4)
 
 
 def test_stage1_fused_ce_masks_old_rows():
@@ -166,8 +166,8 @@ def test_stage1_fused_ce_masks_old_rows():
     assert abs(float(loss) - float(loss_ref)) < 1e-3 * float(loss_ref)
     gw = Wc.grad.float().cpu()
     assert float(gw[:old].abs().max()) == 0.0  # stage1.py:53-57: exactly zero
-    assert rel_err(gw[old:].numpy(), gw_ref[old:].numpy()) < 6e-3
-    assert rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()) < 6e-3
+    assert rel_err(gw[old:].numpy(), gw_ref[old:].numpy()) < 4e-3
+    assert rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()) < 4e-3
     _, gh32, gw32 = K.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), teacher_logits=None,
                                                      temperature=1.0, alpha=1.0, dw_row_begin=old, v_chunk=1024)
     assert float(gw32[:old].abs().max()) == 0.0
@@ -191,7 +191,7 @@ def test_dropin_fused_kwargs():
     fn = K.DistillationLoss(temperature=2.0, alpha=0.5)
     out = fn(None, labels.cuda(), teacher_logits=y.cuda(), student_hidden=h.cuda(), lm_head_weight=W.cuda())
     ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_logits=y.float())
-    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-2)  # bf16 scalars
+    np.testing.assert_allclose([float(o.detach()) for o in out], [float(r.detach()) for r in ref], rtol=1e-2)  # bf16 scalars
 
 
 # ---- sparse teacher inside K1 (BASELINE configs[2]: top-k cache + sparse KD, logits never materialised) -------
@@ -222,8 +222,8 @@ def test_fused_sparse_matches_oracle(B, T, H, V, K, tau, alpha, dup):
     out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda(),
                                   temperature=tau, alpha=alpha)
     out[0].backward()
-    losses = [float(o) for o in out]
-    for got, want in zip(losses, [float(x) for x in ref]):
+    losses = [float(o.detach()) for o in out]
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
     _, gh32, gw32 = KD.fused_linear_kd_value_and_grad(h.cuda(), W.cuda(), labels.cuda(), temperature=tau, alpha=alpha,
                                                       teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
@@ -231,7 +231,7 @@ def test_fused_sparse_matches_oracle(B, T, H, V, K, tau, alpha, dup):
     eh, ew = rel_err(hc.grad.float().cpu().numpy(), gh_ref.numpy()), rel_err(Wc.grad.float().cpu().numpy(), gw_ref.numpy())
     print(f"sparse dH err: bf16 {eh:.2e} fp32 {eh32:.2e} | dW err: bf16 {ew:.2e} fp32 {ew32:.2e}")
     assert eh32 < 1e-3 and ew32 < 1e-3, (eh32, ew32)  # same bars as the dense form
-    assert eh < 6e-3 and ew < 6e-3, (eh, ew)
+    assert eh < 4e-3 and ew < 4e-3, (eh, ew)
 
 
 def test_fused_sparse_equals_streaming_sparse():
@@ -247,7 +247,7 @@ def test_fused_sparse_equals_streaming_sparse():
     z = h.cuda().float() @ W.cuda().float().t()
     out2 = KD.kd_loss_on_logits(z, labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda(),
                                 speech_token_mask=mask.cuda())
-    np.testing.assert_allclose([float(o) for o in out1], [float(o) for o in out2], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose([float(o.detach()) for o in out1], [float(o.detach()) for o in out2], rtol=2e-4, atol=1e-6)
 
 
 def test_fused_sparse_no_hit_and_out_of_range():
@@ -262,7 +262,7 @@ def test_fused_sparse_no_hit_and_out_of_range():
     out = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
     assert float(out[3]) == 0.0
     ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
-    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose([float(o.detach()) for o in out], [float(r.detach()) for r in ref], rtol=1e-3, atol=1e-6)
     ti2 = ti.clone()
     ti2[0, 3, 5] = 100000
     out2 = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti2.cuda())
@@ -278,7 +278,7 @@ def test_dropin_fused_sparse_kwargs():
     out = fn(None, labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda(), student_hidden=h.cuda(),
              lm_head_weight=W.cuda())
     ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
-    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-2)
+    np.testing.assert_allclose([float(o.detach()) for o in out], [float(r.detach()) for r in ref], rtol=1e-2)
     assert out[0].dtype == torch.float32 and out[1].dtype == torch.bfloat16  # SURVEY.md a9 sparse dtypes
 
 
@@ -374,7 +374,7 @@ def test_fused_with_compacted_rows_equals_uncompacted(teacher):
         hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
         out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), v_chunk=1024, compact_rows=compact, **kw)
         out[0].backward()
-        res[compact] = ([float(o) for o in out], hc.grad, Wc.grad)
+        res[compact] = ([float(o.detach()) for o in out], hc.grad, Wc.grad)
     np.testing.assert_allclose(res[True][0], res[False][0], rtol=2e-6, atol=1e-7)
     assert torch.equal(res[True][1], res[False][1])
     assert rel_err(res[True][2].float().cpu().numpy(), res[False][2].float().cpu().numpy()) < 4e-3  # bf16 outputs
@@ -392,7 +392,7 @@ def test_fused_compacted_no_valid_row():
     hc, Wc = h.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
     out = KD.fused_linear_kd_loss(hc, Wc, labels.cuda(), teacher_logits=y.cuda(), compact_rows=True)
     out[0].backward()
-    assert [float(o) for o in out] == [0.0, 0.0, 0.0, 0.0]
+    assert [float(o.detach()) for o in out] == [0.0, 0.0, 0.0, 0.0]
     assert float(hc.grad.abs().max()) == 0.0 and float(Wc.grad.abs().max()) == 0.0
 
 
@@ -452,10 +452,10 @@ def test_fused_ragged_hidden_rows_and_vocab(B, T, H, V):
     h, W, y, labels = _case(700 + H, B, T, H, V)
     ref, gh_ref, gw_ref = O.fused_linear_reference(h.double(), W.double(), labels, teacher_logits=y.double())
     losses, gh, gw = _run_fused(h, W, y, labels, 2.0, 0.5)
-    for got, want in zip(losses, [float(x) for x in ref]):
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
-    assert rel_err(gh.float().cpu().numpy(), gh_ref.numpy()) < 6e-3
-    assert rel_err(gw.float().cpu().numpy(), gw_ref.numpy()) < 6e-3
+    assert rel_err(gh.float().cpu().numpy(), gh_ref.numpy()) < 4e-3
+    assert rel_err(gw.float().cpu().numpy(), gw_ref.numpy()) < 4e-3
 
 
 @pytest.mark.parametrize("K", [1, 1024])
@@ -467,7 +467,7 @@ def test_fused_sparse_extreme_k(K):
     tv, ti = _topk_cache(y, K)
     ref = O.reference_loss(h.float() @ W.float().t(), labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
     out = KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=tv.cuda(), teacher_top_k_i=ti.cuda())
-    np.testing.assert_allclose([float(o) for o in out], [float(r) for r in ref], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose([float(o.detach()) for o in out], [float(r.detach()) for r in ref], rtol=1e-3, atol=1e-6)
     with pytest.raises(KD.KdError):
         KD.fused_linear_kd_loss(h.cuda(), W.cuda(), labels.cuda(), teacher_top_k_v=torch.zeros(2, 64, 1025).cuda(),
                                 teacher_top_k_i=torch.zeros(2, 64, 1025, dtype=torch.int32).cuda())

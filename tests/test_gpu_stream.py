@@ -28,7 +28,7 @@ def run_ours(z, labels, **kw):
     z = z.detach().clone().requires_grad_(True)
     out = K.kd_loss_on_logits(z, labels, temperature=tau, alpha=alpha, **kw)
     out[0].backward()
-    return [float(o) for o in out], z.grad
+    return [float(o.detach()) for o in out], z.grad
 
 
 def to_cuda(d, key, dtype=None):
@@ -99,7 +99,7 @@ def test_dense_matches_oracle(B, T, V, dtype, tau, alpha):
                                             speech_token_mask=c["speech"], temperature=tau, alpha=alpha)
     losses, grad = run_ours(c["z"].cuda(), c["labels"].cuda(), teacher_logits=c["y"].cuda(),
                             speech_token_mask=c["speech"].cuda(), temperature=tau, alpha=alpha)
-    for got, want in zip(losses, [float(x) for x in ref]):
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
     assert grad.dtype == dtype
     # gradient is stored in the logits dtype (reference: bf16 in -> bf16 grad): half-ulp of bf16 = 2^-9
@@ -119,7 +119,7 @@ def test_sparse_matches_oracle(B, T, V, dtype, K, tau):
                                             speech_token_mask=c["speech"], temperature=tau, alpha=0.5)
     losses, grad = run_ours(c["z"].cuda(), c["labels"].cuda(), teacher_top_k_v=c["v"].cuda(), teacher_top_k_i=c["i"].cuda(),
                             speech_token_mask=c["speech"].cuda(), temperature=tau, alpha=0.5)
-    for got, want in zip(losses, [float(x) for x in ref]):
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
     tol = 1e-3 if dtype == torch.float32 else 5e-3
     assert rel_err(grad.float().cpu().numpy(), gref.numpy()) < tol
@@ -130,7 +130,7 @@ def test_sparse_duplicate_indices_accumulate():
     c["i"][..., 3] = c["i"][..., 1]  # duplicate index inside a row: gather backward adds both
     (ref, gref) = O.reference_loss_and_grad(c["z"], c["labels"], teacher_top_k_v=c["v"], teacher_top_k_i=c["i"])
     losses, grad = run_ours(c["z"].cuda(), c["labels"].cuda(), teacher_top_k_v=c["v"].cuda(), teacher_top_k_i=c["i"].cuda())
-    np.testing.assert_allclose(losses, [float(x) for x in ref], rtol=2e-5)
+    np.testing.assert_allclose(losses, [float(x.detach()) for x in ref], rtol=2e-5)
     assert rel_err(grad.cpu().numpy(), gref.numpy()) < 2e-5
 
 
@@ -148,7 +148,7 @@ def test_strided_views_and_no_grad():
         out = K.DistillationLoss()(zc, c["labels"].cuda(), teacher_logits=c["y"].cuda(), speech_token_mask=c["speech"].cuda())
     assert all(o.dtype == torch.bfloat16 and o.dim() == 0 for o in out)  # dtypes the reference returns
     out32 = K.kd_loss_on_logits(zc, c["labels"].cuda(), teacher_logits=c["y"].cuda(), speech_token_mask=c["speech"].cuda())
-    np.testing.assert_allclose([float(o) for o in out32], [float(x) for x in ref], rtol=1e-3)
+    np.testing.assert_allclose([float(o.detach()) for o in out32], [float(x.detach()) for x in ref], rtol=1e-3)
 
 
 def test_upstream_grad_scale_and_component_grads():
@@ -170,7 +170,7 @@ def test_empty_mask_returns_zeros_with_graph():
     z = torch.randn(2, 5, 64, device="cuda", requires_grad=True)
     lab = torch.full((2, 5), -100, device="cuda")
     out = K.DistillationLoss()(z, lab, teacher_logits=torch.randn(2, 5, 64, device="cuda"))
-    assert [float(o) for o in out] == [0.0, 0.0, 0.0, 0.0]
+    assert [float(o.detach()) for o in out] == [0.0, 0.0, 0.0, 0.0]
     out[0].backward()  # reference returns graph-less zeros (distillation_loss.py:47-53); ours is a safe superset
     assert float(z.grad.abs().max()) == 0.0
 
@@ -182,7 +182,7 @@ def test_teacher_with_minus_inf_and_fill():
     (ref, gref) = O.reference_loss_and_grad(c["z"], c["labels"], teacher_logits=c["y"])
     losses, grad = run_ours(c["z"].cuda(), c["labels"].cuda(), teacher_logits=c["y"].cuda())
     assert np.isfinite(losses[:3]).all()
-    np.testing.assert_allclose(losses[:3], [float(x) for x in ref][:3], rtol=2e-5)
+    np.testing.assert_allclose(losses[:3], [float(x.detach()) for x in ref][:3], rtol=2e-5)
     assert rel_err(grad.cpu().numpy(), gref.numpy()) < 2e-5
 
 

@@ -68,23 +68,23 @@ def test_vocab_parallel_slices_equal_unsharded(G, V, sparse):
             hg, Wg, lc, v0, teacher_logits_slice=None if sparse else yc[..., v0:v1], temperature=tau, alpha=alpha,
             gather_fn=lambda rec: recs, reduce_fn=lambda x: (part.append(x.clone()), x)[1], **kw)
         out[0].backward()
-        got = [float(o) for o in out]
+        got = [float(o.detach()) for o in out]
         if losses is not None:
             assert got == losses  # identical on every rank, bit for bit
         losses = got
         dh_parts.append(part[0])
         dw_parts.append(Wg.grad)
-    for got, want in zip(losses, [float(x) for x in ref]):
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
         assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
     dH = torch.stack(dh_parts).sum(0).reshape(B, T, H)
     dW = torch.cat(dw_parts, 0)
     assert dW.shape == (V, H) and dW.dtype == torch.bfloat16
     eh, ew = rel_err(dH.cpu().numpy(), gh_ref.numpy()), rel_err(dW.float().cpu().numpy(), gw_ref.numpy())
-    assert eh < 1e-3 and ew < 6e-3, (eh, ew)  # dH: fp32 partial sums; dW slices: bf16 outputs
+    assert eh < 1e-3 and ew < 4e-3, (eh, ew)  # dH: fp32 partial sums; dW slices: bf16 outputs
 
     # against the unsharded kernels: same losses to fp32 merge-order noise, same gradients to bf16-G noise
     out1 = KD.fused_linear_kd_loss(hc, Wc, lc, teacher_logits=None if sparse else yc, temperature=tau, alpha=alpha, **kw)
-    np.testing.assert_allclose(losses, [float(o) for o in out1], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(losses, [float(o.detach()) for o in out1], rtol=2e-6, atol=1e-7)
     _, gh1, gw1 = KD.fused_linear_kd_value_and_grad(hc, Wc, lc, teacher_logits=None if sparse else yc,
                                                     temperature=tau, alpha=alpha, **kw)
     assert rel_err(dH.cpu().numpy(), gh1.cpu().numpy()) < 1e-3

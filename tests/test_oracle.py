@@ -40,7 +40,7 @@ def test_torch_restatement_matches_reference(path):
     d = np.load(path)
     z = torch.from_numpy(d["z"])
     (losses, grad) = O.reference_loss_and_grad(z, torch.from_numpy(d["labels"]), **_torch_kw(_kw(d)))
-    got = np.array([float(x) for x in losses])
+    got = np.array([float(x.detach()) for x in losses])
     # same op sequence, same dtype -> bitwise equal scalars and gradient
     np.testing.assert_array_equal(got, d["losses"])
     np.testing.assert_array_equal(grad.numpy(), d["grad"])
@@ -76,7 +76,7 @@ def test_fused_linear_reference():
         torch.from_numpy(d["h"]), torch.from_numpy(d["W"]), torch.from_numpy(d["labels"]),
         teacher_logits=torch.from_numpy(d["y"]), temperature=float(d["tau"]), alpha=float(d["alpha"]),
     )
-    np.testing.assert_allclose([float(x) for x in losses], d["losses"], rtol=1e-13)
+    np.testing.assert_allclose([float(x.detach()) for x in losses], d["losses"], rtol=1e-13)
     np.testing.assert_allclose(gh.numpy(), d["dh"], rtol=1e-10, atol=1e-15)
     np.testing.assert_allclose(gw.numpy(), d["dW"], rtol=1e-10, atol=1e-15)
     # dH = G W, dW = G^T h with the closed-form G (math sheet)
@@ -159,5 +159,5 @@ def test_oracle_reproduces_reference_compute_loss(name):
     out = O.reference_loss(z, labels, speech_token_mask=mask, temperature=2.0, alpha=0.5, **kw)
     out[0].backward()
     want = [float(d["loss"]), float(d["student_loss"]), float(d["distill_loss"]), float(d["teacher_loss"])]
-    np.testing.assert_allclose([float(o) for o in out], want, rtol=2e-6)
+    np.testing.assert_allclose([float(o.detach()) for o in out], want, rtol=2e-6)
     np.testing.assert_allclose(student.lm_head.weight.grad.numpy(), d["grad_lm_head"], rtol=1e-4, atol=1e-8)

@@ -47,17 +47,20 @@ def _inputs(B, T, H, V, dev, teacher=True, seed=1234):
     return h, W, y, labels
 
 
-def eager_cfg1(iters=5, B=8, T=512, H=1024, V=152936):
+def eager_cfg1(iters=5, allow_port=True, B=8, T=512, H=1024, V=152936):
     import speech_distill_b200 as K
-    from oracle import kd_oracle as O
     from oracle.make_ref import load_reference_module
 
     dev = torch.device("cuda")
-    h, W, y, labels = _inputs(B, T, H, V, dev)
     ref_mod = load_reference_module()
+    if ref_mod is None and not allow_port:
+        return {"unavailable": "oracle/_ref/distillation_loss.py absent (run oracle/make_ref.py where the reference is mounted)"}
+    h, W, y, labels = _inputs(B, T, H, V, dev)
     if ref_mod is not None:
         loss_fn, kind = ref_mod.DistillationLoss(temperature=2.0, alpha=0.5), "unmodified reference class (oracle/_ref)"
     else:
+        from oracle import kd_oracle as O
+
         def loss_fn(student_logits, labels, teacher_logits):
             return O.reference_loss(student_logits, labels, teacher_logits=teacher_logits, temperature=2.0, alpha=0.5)
         kind = "oracle restatement (oracle/_ref absent)"
@@ -88,7 +91,7 @@ def eager_cfg1(iters=5, B=8, T=512, H=1024, V=152936):
     }
 
 
-def liger_cfg3(iters=5, B=8, T=2048, H=1024, V=152936, new_rows=1000):
+def liger_cfg3(iters=5, allow_port=True, B=8, T=2048, H=1024, V=152936, new_rows=1000):
     import speech_distill_b200 as K
 
     dev = torch.device("cuda")
@@ -130,11 +133,13 @@ def liger_cfg3(iters=5, B=8, T=2048, H=1024, V=152936, new_rows=1000):
     return out
 
 
-def run(iters=5):
+def run(iters=5, allow_port=True):
+    """allow_port=False (bench.py): only the unmodified reference class is timed as the eager baseline; the oracle's
+    restatement is used in its place only when this tool is run by hand without oracle/_ref."""
     res = {}
     for name, fn in (("eager_cfg1", eager_cfg1), ("liger_cfg3", liger_cfg3)):
         try:
-            res[name] = fn(iters)
+            res[name] = fn(iters, allow_port)
         except Exception as e:
             res[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
         torch.cuda.empty_cache()
