@@ -105,6 +105,24 @@ int kd_scale_inplace(void* x, int dtype, int64_t n, const float* scale, void* st
 int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k,
                      void* out_v, int32_t* out_i, void* stream);
 
+/* The same call with a caller-provided workspace of kd_topk_workspace_bytes(R, V) bytes (256-byte aligned; about 1/32
+ * of the logits): the two-kernel form - a statistics sweep over (row, 8192-element segment) work items (piece maxima
+ * + partial log-sum-exp records into the workspace) beside the selection of the previous row block, which reads the
+ * ~k pieces of a row that can hold a top-k entry.  Same outputs as kd_topk_logprobs (values agree to the last bit of
+ * the fp32 log-sum-exp: other summation order).  Unaligned rows, k > 128 or a null / short workspace fall back to
+ * kd_topk_logprobs.  Replaces extract_teacher_logits.py:114-117 / train.py:82-91 like kd_topk_logprobs. */
+size_t kd_topk_workspace_bytes(int64_t R, int V);
+int kd_topk_logprobs_ws(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k,
+                        void* out_v, int32_t* out_i, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- measurement aid: read-only streaming bandwidth of this GPU ------------------------------
+ * Not on the reference's path: bench.py / tools/read_probe.py time it to state what a read-only stream (K2 forward,
+ * K3) can reach next to MEASURED_PEAKS.json's copy figure.  mode 0: ld.global.nc 16-byte loads, `unroll` in flight
+ * per thread; mode 1: the same with an L2 evict_first policy; mode 2: cp.async.bulk (TMA) into a shared-memory ring
+ * of `unroll` 16 KB stages.  scratch4: 4 writable device bytes. */
+int kd_probe_read_bandwidth(const void* p, size_t bytes, int mode, int ctas_per_sm, int unroll, void* scratch4,
+                            void* stream);
+
 /* ---- stage1 frozen-vocabulary row mask -----------------------------------------------------
  * stage1.py:53-57 / 67-71: grad[:old_vocab] = 0, in place on a [V,H] gradient. */
 int kd_mask_rows(void* grad, int dtype, int64_t old_vocab, int64_t H, void* stream);

@@ -36,7 +36,10 @@ SIGNATURES = {
                                  _vp, _f32, _vp, _vp, _vp, _sz, _vp]),
     "kd_scale_inplace": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "kd_topk_logprobs": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "kd_topk_workspace_bytes": (_sz, [_i64, _i32]),
+    "kd_topk_logprobs_ws": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "kd_mask_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
+    "kd_probe_read_bandwidth": (_i32, [_vp, _sz, _i32, _i32, _i32, _vp, _vp]),
     "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "kd_fused_logit_cache_bytes": (_sz, [_i32, _i32, _i32, _sz]),
     "kd_compact_rows": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -99,7 +102,7 @@ def load():
 # entry points that only query (no kernels): no range
 _NO_RANGE = {"kd_head_topk_layout", "kd_version", "kd_last_error", "kd_launch_count", "kd_device_info", "kd_stream_workspace_bytes",
              "kd_fused_workspace_bytes", "kd_fused_logit_cache_bytes", "kd_fused_merge_workspace_bytes",
-             "kd_fused_bwd_trace_begin", "kd_fused_bwd_trace_read"}
+             "kd_fused_bwd_trace_begin", "kd_fused_bwd_trace_read", "kd_topk_workspace_bytes"}
 
 
 def _add_nvtx_ranges(lib):

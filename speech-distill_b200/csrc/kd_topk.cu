@@ -14,7 +14,9 @@
 // tie-break and equals torch.topk(log_softmax(x)) index-for-index on tie-free rows
 // (hard part 4).  Rows whose candidate list overflows (massive ties, constant
 // rows) take an exact but slow bisection path.
+#include <cstdint>
 #include <cstdlib>
+#include <mutex>
 
 #include "kd_common.cuh"
 
@@ -445,6 +447,11 @@ __device__ __forceinline__ uint16_t bf16_bits_rd(float x) {
   return *reinterpret_cast<const uint16_t*>(&b);
 }
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+// piece maximum -> stored key: bf16 rows hold bf16 values, so the key is the float's upper half (no conversion)
+template <typename T>
+__device__ __forceinline__ uint16_t piece_key(float x) { return bf16_bits_rd(x); }
+template <>
+__device__ __forceinline__ uint16_t piece_key<__nv_bfloat16>(float x) { return (uint16_t)(__float_as_uint(x) >> 16); }
 // 16-bit order key <-> bf16 bit pattern (same map as order_key on the top half of a float)
 __device__ __forceinline__ uint32_t key16_to_bf16_bits(uint32_t k) { return (k & 0x8000u) ? (k & 0x7fffu) : (~k & 0xffffu); }
 constexpr uint16_t kBf16NegInf = 0xFF80;
@@ -649,55 +656,140 @@ __device__ __forceinline__ void warp_select_emit(const T* __restrict__ row, int 
 // pass 1 of the warp form: one sweep over the row -> piece maxima in shared memory, row maximum and log of the exp sum.
 // Two register batches of U vectors per lane: while one batch is reduced the other's loads are in flight, so a
 // row-warp always has U..2U 16-byte loads outstanding (a single batch alternated between "all in flight" and "none").
+// maximum of the 8 elements of a vector.  16-bit rows: three packed maxima (HMNMX2) on the raw words + one across the
+// two halves instead of 8 conversions + 7 FMNMX (pass 1 is issue-bound once enough loads are in flight); NaN handling
+// is fmaxf's (the other operand wins).
+template <typename T>
+__device__ __forceinline__ float vec_max8(const Vec8<T>& v) {
+  float f[8];
+  v.unpack(f);
+  return fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+}
+template <>
+__device__ __forceinline__ float vec_max8<__nv_bfloat16>(const Vec8<__nv_bfloat16>& v) {
+  const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v.a.x),
+                                   *reinterpret_cast<const __nv_bfloat162*>(&v.a.y));
+  const __nv_bfloat162 b = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v.a.z),
+                                   *reinterpret_cast<const __nv_bfloat162*>(&v.a.w));
+  const __nv_bfloat162 c = __hmax2(a, b);
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(&c);
+  return fmaxf(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float vec_max8<__half>(const Vec8<__half>& v) {
+  const __half2 a = __hmax2(*reinterpret_cast<const __half2*>(&v.a.x), *reinterpret_cast<const __half2*>(&v.a.y));
+  const __half2 b = __hmax2(*reinterpret_cast<const __half2*>(&v.a.z), *reinterpret_cast<const __half2*>(&v.a.w));
+  const float2 c = __half22float2(__hmax2(a, b));
+  return fmaxf(c.x, c.y);
+}
+
+// packed 16-bit pairs: maximum of two words, low element as a float
+template <typename T>
+struct Pair16;
+template <>
+struct Pair16<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float low(uint32_t w) { return __uint_as_float(w << 16); }
+};
+template <>
+struct Pair16<__half> {
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float low(uint32_t w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+};
+
+// One register batch of the statistics sweep (shared by the warp-per-row kernel and kd_topk_stats_kernel): lane l holds
+// vectors base + 32 u + l (u < U) of a row; four neighbouring lanes hold one 32-element piece.  Writes the piece maxima
+// (16-bit keys) to `pieces` (indexed by piece number; shared or global memory) and folds the batch into the lane's
+// online (m, s) = (reference maximum, sum e^{x - m}).
+// FULL = every vector of the batch lies inside the row: no per-vector predicates.  The sweep is issue-bound, not
+// HBM-bound (ncu: 10.6 issued instructions per element in the first version, 66 % issue utilisation at 0.54 of the
+// DRAM peak), so the 16-bit FULL path is written for instruction count: piece maxima stay packed (HMNMX2 on the raw
+// words, one shuffle for both halves), the lane's reference maximum is the maximum of its PIECES (a superset of its
+// own elements - any upper bound taken from the row serves the online sum), and the four keys of a lane group leave
+// in one 32-lane store per four vectors.
+template <typename T, int U, bool FULL>
+__device__ __forceinline__ void sweep_batch(const Vec8<T> (&v)[U], int base, int nvec, int lane,
+                                            uint16_t* __restrict__ pieces, float& m, float& s) {
+  float vm = -CUDART_INF_F;
+  bool skip[U];
+  if constexpr (FULL && sizeof(T) == 2 && (U % 4) == 0) {
+    float pmf[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t c = Pair16<T>::max2(Pair16<T>::max2(v[u].a.x, v[u].a.y), Pair16<T>::max2(v[u].a.z, v[u].a.w));
+      c = Pair16<T>::max2(c, __shfl_xor_sync(0xffffffffu, c, 1));
+      c = Pair16<T>::max2(c, __shfl_xor_sync(0xffffffffu, c, 2));
+      c = Pair16<T>::max2(c, __byte_perm(c, 0, 0x1032));  // both halves = the piece maximum
+      pmf[u] = Pair16<T>::low(c);
+      vm = fmaxf(vm, pmf[u]);
+      skip[u] = false;
+    }
+#pragma unroll
+    for (int u0 = 0; u0 < U; u0 += 4) {  // lane (l & 3) = j stores the key of vector u0 + j: one store per 4 vectors
+      const int j = lane & 3;
+      const float mine = j == 0 ? pmf[u0] : (j == 1 ? pmf[u0 + 1] : (j == 2 ? pmf[u0 + 2] : pmf[u0 + 3]));
+      pieces[((base + (u0 + j) * 32) >> 2) + (lane >> 2)] = piece_key<T>(mine);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * 32 + lane;
+      float x = (FULL || idx < nvec) ? vec_max8<T>(v[u]) : -CUDART_INF_F;
+      skip[u] = !FULL && x == -CUDART_INF_F;  // past the end of the row: the registers hold stale data
+      vm = fmaxf(vm, x);
+      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));  // four lanes = one 32-element piece
+      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 2));
+      if ((lane & 3) == 0 && (FULL || idx < nvec)) pieces[idx >> 2] = piece_key<T>(x);
+    }
+  }
+  if (vm > m) {
+    s *= exp_diff(m, vm, kLog2e);
+    m = vm;
+  }
+  if (m != -CUDART_INF_F) {
+    const float off = m * kLog2e;
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (skip[u]) continue;
+      float f[8];
+      v[u].unpack(f);  // an -inf element gives ex2(-inf) = 0 (m is finite here)
+      p0 += ex2(fmaf(f[0], kLog2e, -off)) + ex2(fmaf(f[4], kLog2e, -off));
+      p1 += ex2(fmaf(f[1], kLog2e, -off)) + ex2(fmaf(f[5], kLog2e, -off));
+      p2 += ex2(fmaf(f[2], kLog2e, -off)) + ex2(fmaf(f[6], kLog2e, -off));
+      p3 += ex2(fmaf(f[3], kLog2e, -off)) + ex2(fmaf(f[7], kLog2e, -off));
+    }
+    s += (p0 + p1) + (p2 + p3);
+  }
+}
+
+#ifndef KD_TOPK_WARP_U
+#define KD_TOPK_WARP_U 8  // 16-byte loads per lane and register batch (two batches): 8..16 in flight per lane
+#endif
+
 template <typename T, int U>
 struct Pass1Batch {
   Vec8<T> v[U];
   __device__ __forceinline__ void load(const T* __restrict__ row, int base, int nvec, int lane) {
+    const T* p0 = row + (size_t)(base + lane) * 8;
+    if (base + 32 * U <= nvec) {  // whole batch inside the row: one address, immediate offsets, no predicates
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * 32 + lane;
-      if (idx < nvec) v[u].load_global(row + (size_t)idx * 8);
+      for (int u = 0; u < U; ++u) v[u].load_global(p0 + u * 256);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (base + u * 32 + lane < nvec) v[u].load_global(p0 + u * 256);
     }
   }
   __device__ __forceinline__ void reduce(int base, int nvec, int lane, uint16_t* pv, float& m, float& s) {
-    float vmx[U];
-    float vm = -CUDART_INF_F;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * 32 + lane;
-      float f[8];
-      if (idx < nvec) {
-        v[u].unpack(f);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = -CUDART_INF_F;
-      }
-      float x = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
-      vmx[u] = x;
-      vm = fmaxf(vm, x);
-      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));  // four lanes = one 32-element piece
-      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 2));
-      if ((lane & 3) == 0 && idx < nvec) pv[idx >> 2] = bf16_bits_rd(x);
-    }
-    if (vm > m) {
-      s *= exp_diff(m, vm, kLog2e);
-      m = vm;
-    }
-    if (m != -CUDART_INF_F) {
-      const float off = m * kLog2e;
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (vmx[u] == -CUDART_INF_F) continue;  // past the end of the row (or an all -inf vector): contributes 0
-        float f[8];
-        v[u].unpack(f);
-        p0 += ex2(fmaf(f[0], kLog2e, -off)) + ex2(fmaf(f[4], kLog2e, -off));
-        p1 += ex2(fmaf(f[1], kLog2e, -off)) + ex2(fmaf(f[5], kLog2e, -off));
-        p2 += ex2(fmaf(f[2], kLog2e, -off)) + ex2(fmaf(f[6], kLog2e, -off));
-        p3 += ex2(fmaf(f[3], kLog2e, -off)) + ex2(fmaf(f[7], kLog2e, -off));
-      }
-      s += (p0 + p1) + (p2 + p3);
-    }
+    if (base + 32 * U <= nvec) sweep_batch<T, U, true>(v, base, nvec, lane, pv, m, s);
+    else sweep_batch<T, U, false>(v, base, nvec, lane, pv, m, s);
   }
 };
 
@@ -744,7 +836,7 @@ __device__ __forceinline__ void warp_pass1(const T* __restrict__ row, int V, uin
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32 * kWrWarps) kd_topk_warp_kernel(const T* __restrict__ logits, int64_t R, int V,
+__global__ void __launch_bounds__(32 * kWrWarps, 2) kd_topk_warp_kernel(const T* __restrict__ logits, int64_t R, int V,
                                                                        int64_t row_stride, int k,
                                                                        __half* __restrict__ out_v,
                                                                        int32_t* __restrict__ out_i, int n_pieces_pad) {
@@ -754,10 +846,11 @@ __global__ void __launch_bounds__(32 * kWrWarps) kd_topk_warp_kernel(const T* __
   const int n_pieces = (V + kWrPiece - 1) / kWrPiece;
   for (int i = n_pieces + lane; i < n_pieces_pad; i += 32) w.pv[i] = kBf16NegInf;  // padding: never >= a threshold
   __syncwarp();
-  for (int64_t r = (int64_t)blockIdx.x * kWrWarps + warp; r < R; r += (int64_t)gridDim.x * kWrWarps) {
+  const int n_warps = blockDim.x >> 5;  // rows per CTA (warp_form_config)
+  for (int64_t r = (int64_t)blockIdx.x * n_warps + warp; r < R; r += (int64_t)gridDim.x * n_warps) {
     const T* row = logits + r * row_stride;
     float lm, ll;
-    warp_pass1<T, (sizeof(T) == 2 ? 4 : 2)>(row, V, w.pv, lane, lm, ll);
+    warp_pass1<T, (sizeof(T) == 2 ? KD_TOPK_WARP_U : KD_TOPK_WARP_U / 2)>(row, V, w.pv, lane, lm, ll);
     warp_select_emit<T>(row, V, k, w, n_pieces, n_pieces_pad, lm, ll, r, out_v, out_i, lane);
     __syncwarp();
   }
@@ -767,19 +860,20 @@ __global__ void __launch_bounds__(32 * kWrWarps) kd_topk_warp_kernel(const T* __
 // Same output as kd_topk_logprobs on the block's bf16 logits, without the sweep over the row: the head GEMM's epilogue
 // left (a) the maximum of every 32-column piece and (b) partial (max, sum exp) records, so a row costs the merge of
 // n_part records (~2 KB), the piece maxima (~10 KB) and the ~k pieces of 64 bytes that can hold a top-k entry.
-__global__ void __launch_bounds__(32 * kWrWarps) kd_head_select_kernel(const __nv_bfloat16* __restrict__ logits, int64_t R,
+template <typename T>
+__global__ void __launch_bounds__(32 * kWrWarps) kd_head_select_kernel(const T* __restrict__ logits, int64_t R,
                                                                          int V, int64_t row_stride, int k,
                                                                          const __nv_bfloat16* __restrict__ pmax,
                                                                          int pmax_stride, const float2* __restrict__ part,
                                                                          int part_stride, int n_part,
                                                                          __half* __restrict__ out_v,
                                                                          int32_t* __restrict__ out_i, int n_pieces_pad) {
-  using T = __nv_bfloat16;
   extern __shared__ __align__(16) unsigned char wr_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const WarpRow w = warp_row_smem(wr_smem, warp, n_pieces_pad);
   const int n_pieces = (V + kWrPiece - 1) / kWrPiece;
-  for (int64_t r = (int64_t)blockIdx.x * kWrWarps + warp; r < R; r += (int64_t)gridDim.x * kWrWarps) {
+  const int n_warps = blockDim.x >> 5;  // rows per CTA (warp_form_config)
+  for (int64_t r = (int64_t)blockIdx.x * n_warps + warp; r < R; r += (int64_t)gridDim.x * n_warps) {
     const T* row = logits + r * row_stride;
     // piece maxima (already bf16): straight copy, 8 per 16-byte load; entries past the vocabulary hold -inf
     const uint4* pm = reinterpret_cast<const uint4*>(pmax + r * pmax_stride);
@@ -803,35 +897,199 @@ __global__ void __launch_bounds__(32 * kWrWarps) kd_head_select_kernel(const __n
   }
 }
 
+
+// ---- two-kernel form of kd_topk_logprobs: statistics sweep + selection ----------------------------------------------
+// The warp-per-row kernel above keeps a row's piece maxima in shared memory, so an SM holds 16 rows at a time: the
+// rows of a launch advance in lock step (8192 rows on 2368 row slots = 3.46 rounds cost 4), and a slot does not stream
+// while it selects.  Here the sweep and the selection are separate kernels that overlap row block by row block:
+//   kd_topk_stats_kernel : work item = (row, 8192-element segment), one warp each, taken round robin - fine-grained, no
+//                          shared memory, nothing but streaming: piece maxima (bf16, rounded down) and one (max, sum exp)
+//                          record per item go to a workspace (1/32 of the logits' bytes);
+//   kd_head_select_kernel: the selection behind the teacher head GEMM, unchanged - it reads the piece maxima, the
+//                          records and the ~k qualifying 64-byte pieces of every row.
+// The sweep of row block b + 1 (internal high-priority stream) runs beside the selection of block b (caller's stream):
+// three 256-thread sweep CTAs (<= 64 registers) and one selection CTA fit an SM together.
+constexpr int kStatSeg = 8192;                // elements per work item (256 pieces)
+constexpr int kStatThreads = 256;
+constexpr int kStatCtasPerSm = 3;
+constexpr int kStatU = 4;                     // 16-byte loads per lane and register batch (two batches)
+constexpr int kStatMaxBlocks = 8;             // row blocks of the sweep / selection pipeline
+#ifndef KD_STAT_MINB
+#define KD_STAT_MINB 4                        // sweep CTAs the register budget allows per SM (4: <= 64 registers)
+#endif
+
+// position of a warp in its sequence of batches: item wid + j * wstride, batch b of the item; (row, seg) are carried
+// along instead of being divided out of the item number for every batch
+struct StatCursor {
+  int64_t item, row;
+  int seg, b;
+};
+
+template <typename T, int U>
+struct StatBatch {
+  Vec8<T> v[U];
+  const T* rowp;
+  int64_t row;
+  int seg, vbase;
+  bool live, last;
+  template <int NB>
+  __device__ __forceinline__ void load(StatCursor& c, int64_t wstride, int64_t drow, int dseg, int64_t n_items, int n_seg,
+                                       int nvec, const T* __restrict__ logits, int64_t row_stride, int lane) {
+    live = c.item < n_items;
+    if (!live) return;
+    last = c.b == NB - 1;
+    row = c.row;
+    seg = c.seg;
+    rowp = logits + row * row_stride;
+    vbase = seg * (kStatSeg / 8) + c.b * (32 * U);
+    const T* p0 = rowp + (size_t)(vbase + lane) * 8;
+    if (vbase + 32 * U <= nvec) {  // whole batch inside the row: one address, immediate offsets, no predicates
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u].load_global(p0 + u * 256);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (vbase + u * 32 + lane < nvec) v[u].load_global(p0 + u * 256);
+    }
+    if (++c.b == NB) {  // next item of this warp
+      c.b = 0;
+      c.item += wstride;
+      c.row += drow;
+      c.seg += dseg;
+      if (c.seg >= n_seg) {
+        c.seg -= n_seg;
+        ++c.row;
+      }
+    }
+  }
+  __device__ __forceinline__ void reduce(int nvec, int lane, uint16_t* __restrict__ pm_row, float& m, float& s) const {
+    if (vbase + 32 * U <= nvec) sweep_batch<T, U, true>(v, vbase, nvec, lane, pm_row, m, s);
+    else sweep_batch<T, U, false>(v, vbase, nvec, lane, pm_row, m, s);
+  }
+};
+
+template <typename T, int U>
+__global__ void __launch_bounds__(kStatThreads, KD_STAT_MINB)
+kd_topk_stats_kernel(const T* __restrict__ logits, int64_t R, int V, int64_t row_stride, uint16_t* __restrict__ pmax,
+                     int pmax_stride, float2* __restrict__ part, int part_stride) {
+  constexpr int NB = kStatSeg / 8 / (32 * U);  // batches per item
+  static_assert(NB >= 2 && (NB & 1) == 0, "two register batches alternate inside an item");
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (kStatThreads / 32) + (threadIdx.x >> 5);
+  const int64_t wstride = (int64_t)gridDim.x * (kStatThreads / 32);
+  const int nvec = V >> 3;
+  const int n_seg = (V + kStatSeg - 1) / kStatSeg;
+  const int n_pieces = (V + kWrPiece - 1) / kWrPiece;
+  const int64_t n_items = R * n_seg;
+  const int64_t drow = wstride / n_seg;
+  const int dseg = (int)(wstride - drow * n_seg);
+  StatCursor cur;
+  cur.item = wid;
+  cur.row = wid / n_seg;
+  cur.seg = (int)(wid - cur.row * n_seg);
+  cur.b = 0;
+  float m = -CUDART_INF_F, s = 0.f;
+  StatBatch<T, U> b0, b1;
+  b0.template load<NB>(cur, wstride, drow, dseg, n_items, n_seg, nvec, logits, row_stride, lane);
+#pragma unroll 1
+  while (b0.live) {
+    // NB is even: b0 holds the even batches of an item, b1 the odd ones - an item always ends in b1
+    b1.template load<NB>(cur, wstride, drow, dseg, n_items, n_seg, nvec, logits, row_stride, lane);
+    b0.reduce(nvec, lane, pmax + b0.row * pmax_stride, m, s);
+    const int64_t row1 = b1.row;
+    const int seg1 = b1.seg;
+    const T* rowp1 = b1.rowp;
+    const bool last1 = b1.last;
+    b1.reduce(nvec, lane, pmax + row1 * pmax_stride, m, s);
+    b0.template load<NB>(cur, wstride, drow, dseg, n_items, n_seg, nvec, logits, row_stride, lane);
+    if (last1) {  // the item's last batch has been reduced: publish its record
+      uint16_t* pm_row = pmax + row1 * pmax_stride;
+      if (seg1 == n_seg - 1) {
+        // row end: the V % 8 elements behind the last whole vector (lane 0, scalar) and the padding of the piece maxima
+        __syncwarp();
+        const int tail0 = nvec << 3;
+        if (lane == 0 && tail0 < V) {
+          const int piece = tail0 / kWrPiece;
+          float pmx = -CUDART_INF_F;
+          for (int c = piece * kWrPiece; c < V; ++c) {  // the whole last piece again: <= 31 elements
+            const float x = Elem<T>::to_f(rowp1[c]);
+            pmx = fmaxf(pmx, x);
+            if (c >= tail0) {
+              if (x > m) {
+                s *= exp_diff(m, x, kLog2e);
+                m = x;
+              }
+              if (m != -CUDART_INF_F) s += ex2((x - m) * kLog2e);
+            }
+          }
+          pm_row[piece] = bf16_bits_rd(pmx);
+        }
+        for (int i = n_pieces + lane; i < pmax_stride; i += 32) pm_row[i] = kBf16NegInf;  // never >= a threshold
+      }
+      const float wm = warp_max(m);
+      const float ws = warp_sum(s * exp_diff(m, wm, kLog2e));
+      if (lane == 0) part[row1 * part_stride + seg1] = make_float2(wm, ws);
+      m = -CUDART_INF_F;
+      s = 0.f;
+    }
+  }
+}
+
+struct TopkPipe {
+  std::mutex enqueue;
+  cudaStream_t hi = nullptr;
+  cudaEvent_t fork = nullptr, swept[kStatMaxBlocks] = {};
+  bool ready = false;
+};
 }  // namespace kd
 
 using namespace kd;
 
-// launch geometry of the warp-per-row kernels: 8 row-warps per CTA, as many CTAs per SM as the shared memory holds
-// (at most 4); returns false when a row's piece keys do not fit (V beyond ~3.4 M columns)
+// launch geometry of the warp-per-row kernels: up to 8 row-warps per CTA, as many CTAs per SM as the shared memory
+// holds (at most 4); returns false when a row's piece keys do not fit (V beyond ~3.4 M columns).
+// The rows of a launch advance in rounds (every row slot takes its next row at about the same time) and the kernels
+// are issue-bound, so a round's duration grows with the row-warps per SM: 8192 rows on 148 x 2 x 8 slots are 3.46 -> 4
+// rounds of 8-warp CTAs, but also 4 rounds of 7-warp CTAs, which finish 1/8 sooner.  `warps` = the rows-per-CTA in
+// [4, 8] that minimises rounds x warps.
 template <typename Kern>
-static bool warp_form_config(Kern kern, int64_t R, int V, int* grid, size_t* smem, int* n_pieces_pad) {
+static bool warp_form_config(Kern kern, int64_t R, int V, int* grid, size_t* smem, int* n_pieces_pad, int* warps) {
   const int n_pieces = (V + kWrPiece - 1) / kWrPiece;
   *n_pieces_pad = (n_pieces + 7) & ~7;
-  *smem = (size_t)kWrWarps * warp_row_bytes(*n_pieces_pad);
-  if (*smem > 226 * 1024 || n_pieces > 65535) return false;  // piece indices are kept as 16-bit values
-  int per_sm = (int)((size_t)232448 / (*smem + 1024));
+  const size_t smem_max = (size_t)kWrWarps * warp_row_bytes(*n_pieces_pad);
+  if (smem_max > 226 * 1024 || n_pieces > 65535) return false;  // piece indices are kept as 16-bit values
+  int per_sm = (int)((size_t)232448 / (smem_max + 1024));
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t ctas = (R + kWrWarps - 1) / kWrWarps;
+  int best_w = kWrWarps;
+  int64_t best_cost = INT64_MAX;
+  for (int w = kWrWarps; w >= 4; --w) {
+    const int64_t slots = (int64_t)sms * per_sm * w;
+    const int64_t cost = ((R + slots - 1) / slots) * w;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_w = w;
+    }
+  }
+  *warps = best_w;
+  *smem = (size_t)best_w * warp_row_bytes(*n_pieces_pad);
+  const int64_t ctas = (R + best_w - 1) / best_w;
   *grid = (int)(ctas < (int64_t)sms * per_sm ? ctas : (int64_t)sms * per_sm);
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
   return true;
 }
-// Which form takes a call of kd_topk_logprobs: a row is one warp's work in the warp form (~0.2 ms per row at
-// V = 152,936), so it needs at least two rows for each of the 16 row-warps an SM holds to beat the CTA-per-row form,
-// which spreads a row over 256 threads.  KD_TOPK_FORM=cta / warp forces one of them (A/B runs).
+// Which form takes a call of kd_topk_logprobs: a row is one warp's work in the warp form (~0.15 ms per row at
+// V = 152,936 however few rows there are), the CTA-per-row form spreads a row over 256 threads.  Measured at k = 64
+// (tools/k3_forms.py, us, L2 flushed between launches):  R      256  1024  2048  4096  8192
+//                                                        cta     53   125   252   498  1026
+//                                                        warp   102   115   158   299   588
+//                                                        two     61   104   203   358   670
+// -> warp form from half an SM's row slots per SM upwards.  KD_TOPK_FORM=cta / warp forces one of them (A/B runs).
 static bool topk_use_warp_form(int64_t R) {
   static int v = -1;
   if (v < 0) {
@@ -843,7 +1101,7 @@ static bool topk_use_warp_form(int64_t R) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return R >= (int64_t)sms * 2 * kWrWarps * 2;
+  return R >= (int64_t)sms * kWrWarps;
 }
 
 extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k, void* out_v,
@@ -862,27 +1120,27 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * es) % 16 == 0) ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (vec_ok && k <= kWrCap / 2 && topk_use_warp_form(R)) {  // warp-per-row form (see above)
-    int grid = 0, npp = 0;
+    int grid = 0, npp = 0, nw = 0;
     size_t smem = 0;
     bool launched = false;
     switch (dtype) {
       case KD_DTYPE_F32:
-        if (warp_form_config(kd_topk_warp_kernel<float>, R, V, &grid, &smem, &npp)) {
-          kd_topk_warp_kernel<float><<<grid, 32 * kWrWarps, smem, s>>>((const float*)logits, R, V, row_stride, k,
+        if (warp_form_config(kd_topk_warp_kernel<float>, R, V, &grid, &smem, &npp, &nw)) {
+          kd_topk_warp_kernel<float><<<grid, 32 * nw, smem, s>>>((const float*)logits, R, V, row_stride, k,
                                                                        (__half*)out_v, out_i, npp);
           launched = true;
         }
         break;
       case KD_DTYPE_BF16:
-        if (warp_form_config(kd_topk_warp_kernel<__nv_bfloat16>, R, V, &grid, &smem, &npp)) {
-          kd_topk_warp_kernel<__nv_bfloat16><<<grid, 32 * kWrWarps, smem, s>>>((const __nv_bfloat16*)logits, R, V,
+        if (warp_form_config(kd_topk_warp_kernel<__nv_bfloat16>, R, V, &grid, &smem, &npp, &nw)) {
+          kd_topk_warp_kernel<__nv_bfloat16><<<grid, 32 * nw, smem, s>>>((const __nv_bfloat16*)logits, R, V,
                                                                                row_stride, k, (__half*)out_v, out_i, npp);
           launched = true;
         }
         break;
       case KD_DTYPE_F16:
-        if (warp_form_config(kd_topk_warp_kernel<__half>, R, V, &grid, &smem, &npp)) {
-          kd_topk_warp_kernel<__half><<<grid, 32 * kWrWarps, smem, s>>>((const __half*)logits, R, V, row_stride, k,
+        if (warp_form_config(kd_topk_warp_kernel<__half>, R, V, &grid, &smem, &npp, &nw)) {
+          kd_topk_warp_kernel<__half><<<grid, 32 * nw, smem, s>>>((const __half*)logits, R, V, row_stride, k,
                                                                         (__half*)out_v, out_i, npp);
           launched = true;
         }
@@ -941,6 +1199,147 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
   return check_launch("kd_topk launch");
 }
 
+// ---- two-kernel form: host side -------------------------------------------------------------------------------------
+static TopkPipe* get_topk_pipe() {
+  static TopkPipe pipes[kMaxDevices];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  TopkPipe& p = pipes[dev];
+  if (p.ready) return &p;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+  // the sweep's CTAs are placed first; the selection (caller's stream) takes the room they leave on every SM
+  if (cudaStreamCreateWithPriority(&p.hi, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  for (int i = 0; i < kStatMaxBlocks; ++i)
+    if (cudaEventCreateWithFlags(&p.swept[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  p.ready = true;
+  return &p;
+}
+
+static inline int topk_pmax_stride(int V) { return (((V + kWrPiece - 1) / kWrPiece) + 7) & ~7; }
+static inline int topk_part_stride(int V) { return (V + kStatSeg - 1) / kStatSeg; }
+static inline size_t topk_pmax_bytes(int64_t R, int V) {
+  return (((size_t)R * topk_pmax_stride(V) * 2) + 255) & ~(size_t)255;
+}
+
+extern "C" size_t kd_topk_workspace_bytes(int64_t R, int V) {
+  if (R <= 0 || V <= 0) return 0;
+  return topk_pmax_bytes(R, V) + (size_t)R * topk_part_stride(V) * sizeof(float2);
+}
+
+template <typename T>
+static int topk_two_kernel(const T* logits, int64_t R, int V, int64_t row_stride, int k, __half* out_v, int32_t* out_i,
+                           uint8_t* ws, cudaStream_t s) {
+  TopkPipe* pipe = get_topk_pipe();
+  if (!pipe) return -1;
+  int sel_grid = 0, npp = 0, sel_warps = 0;
+  size_t sel_smem = 0;
+  if (!warp_form_config(kd_head_select_kernel<T>, R, V, &sel_grid, &sel_smem, &npp, &sel_warps)) return -1;
+  sel_warps = kWrWarps;  // the row blocks differ in size: keep full CTAs
+  sel_smem = (size_t)kWrWarps * warp_row_bytes(npp);
+  const int pmax_stride = topk_pmax_stride(V), part_stride = topk_part_stride(V);
+  uint16_t* pmax = reinterpret_cast<uint16_t*>(ws);
+  float2* part = reinterpret_cast<float2*>(ws + topk_pmax_bytes(R, V));
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // row blocks: enough of them that the last block's selection (the only one nothing hides) is short, each big enough
+  // to fill the GPU's sweep warps a few times over
+  int n_blk = (int)(R / 1024);
+  n_blk = n_blk < 1 ? 1 : (n_blk > kStatMaxBlocks ? kStatMaxBlocks : n_blk);
+  // diagnosis knobs (tools/k3_ab.py): KD_TOPK_BLOCKS, KD_TOPK_SWEEP_CTAS (sweep CTAs per SM), KD_TOPK_PHASE=sweep /
+  // select runs one of the two kernels only (the results are then stale or missing)
+  static int env_blocks = -1, env_ctas = 0, env_phase = 0;
+  if (env_blocks < 0) {
+    const char* e = getenv("KD_TOPK_BLOCKS");
+    const char* c = getenv("KD_TOPK_SWEEP_CTAS");
+    const char* ph = getenv("KD_TOPK_PHASE");
+    env_ctas = c ? atoi(c) : 0;
+    env_phase = !ph ? 0 : (ph[0] == 's' && ph[1] == 'w' ? 1 : (ph[0] == 's' && ph[1] == 'e' ? 2 : 0));
+    env_blocks = e ? atoi(e) : 0;
+  }
+  if (env_blocks > 0) n_blk = env_blocks > kStatMaxBlocks ? kStatMaxBlocks : env_blocks;
+  const int sweep_ctas = env_ctas > 0 ? env_ctas : kStatCtasPerSm;
+  const int64_t rows_per_blk = ((R + n_blk - 1) / n_blk + kWrWarps - 1) / kWrWarps * kWrWarps;
+  std::lock_guard<std::mutex> lock(pipe->enqueue);
+  if (check_cuda(cudaEventRecord(pipe->fork, s), "topk fork")) return 1;
+  if (check_cuda(cudaStreamWaitEvent(pipe->hi, pipe->fork, 0), "topk fork")) return 1;
+  int b = 0;
+  for (int64_t r0 = 0; r0 < R; r0 += rows_per_blk, ++b) {
+    const int64_t rows = R - r0 < rows_per_blk ? R - r0 : rows_per_blk;
+    const int64_t items = rows * part_stride;
+    const int64_t warps = (int64_t)sms * sweep_ctas * (kStatThreads / 32);
+    const int grid = (int)((items < warps ? items : warps) + kStatThreads / 32 - 1) / (kStatThreads / 32);
+    if (env_phase != 2) {
+      kd_topk_stats_kernel<T, (sizeof(T) == 2 ? kStatU : kStatU / 2)><<<grid, kStatThreads, 0, pipe->hi>>>(
+          logits + r0 * row_stride, rows, V, row_stride, pmax + r0 * pmax_stride, pmax_stride, part + r0 * part_stride,
+          part_stride);
+      if (check_launch("kd_topk_stats launch")) return 1;
+    }
+    if (check_cuda(cudaEventRecord(pipe->swept[b], pipe->hi), "topk swept")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(s, pipe->swept[b], 0), "topk swept")) return 1;
+    const int64_t ctas = (rows + kWrWarps - 1) / kWrWarps;
+    const int g = (int)(ctas < sel_grid ? ctas : sel_grid);
+    if (env_phase != 1) {
+      kd_head_select_kernel<T><<<g, 32 * kWrWarps, sel_smem, s>>>(
+          logits + r0 * row_stride, rows, V, row_stride, k, reinterpret_cast<const __nv_bfloat16*>(pmax + r0 * pmax_stride),
+          pmax_stride, part + r0 * part_stride, part_stride, part_stride, out_v + r0 * k, out_i + r0 * k, npp);
+      if (check_launch("kd_topk select launch")) return 1;
+    }
+  }
+  return 0;
+}
+
+// kd_topk_logprobs with a caller-provided workspace of kd_topk_workspace_bytes(R, V): the two-kernel form (statistics
+// sweep beside the selection of the previous row block).  Shapes it does not take (unaligned rows, k > 128) and a
+// null / short workspace run the single-kernel forms of kd_topk_logprobs: same results.
+extern "C" int kd_topk_logprobs_ws(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k, void* out_v,
+                                   int32_t* out_i, void* workspace, size_t workspace_bytes, void* stream) {
+  kd::DeviceGuard device_guard(logits);
+  // KD_TOPK_FORM=cta / warp force a single-kernel form, =two the two-kernel form (A/B runs).  Default: the two-kernel
+  // form for launches too small to give every row-warp slot of the warp form a row (its work items are row segments),
+  // the warp form above that - measured on B200 at V = 152,936, k = 64 (tools/k3_direct.py): see DESIGN.md, K3.
+  static int form_env = -1;
+  if (form_env < 0) {
+    const char* e = getenv("KD_TOPK_FORM");
+    form_env = !e ? 0 : ((e[0] == 'c' || e[0] == 'w') ? 1 : (e[0] == 't' ? 2 : 0));
+  }
+  int form = form_env;
+  if (form == 0) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    form = R < (int64_t)sms * kWrWarps ? 2 : 1;
+  }
+  const size_t es = dtype == KD_DTYPE_F32 ? 4 : 2;
+  const bool vec_ok = logits && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * es) % 16 == 0;
+  const bool ws_ok = workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && R > 0 && V > 0 &&
+                     workspace_bytes >= kd_topk_workspace_bytes(R, V);
+  if (form == 2 && vec_ok && ws_ok && out_v && out_i && k > 0 && k <= V && k <= kWrCap / 2 && V >= 8) {
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    int rc = -1;
+    switch (dtype) {
+      case KD_DTYPE_F32:
+        rc = topk_two_kernel<float>((const float*)logits, R, V, row_stride, k, (__half*)out_v, out_i, ws, s);
+        break;
+      case KD_DTYPE_BF16:
+        rc = topk_two_kernel<__nv_bfloat16>((const __nv_bfloat16*)logits, R, V, row_stride, k, (__half*)out_v, out_i, ws, s);
+        break;
+      case KD_DTYPE_F16:
+        rc = topk_two_kernel<__half>((const __half*)logits, R, V, row_stride, k, (__half*)out_v, out_i, ws, s);
+        break;
+      default:
+        break;
+    }
+    if (rc >= 0) return rc;  // -1: this shape / device cannot take the form
+  }
+  return kd_topk_logprobs(logits, dtype, R, V, row_stride, k, out_v, out_i, stream);
+}
+
 extern "C" int kd_head_topk_select(const void* logits, int64_t row_stride, const void* pmax, int pmax_stride,
                                    const void* part, int part_stride, int n_part, int64_t R, int V, int k, void* out_v,
                                    int32_t* out_i, void* stream) {
@@ -957,13 +1356,13 @@ extern "C" int kd_head_topk_select(const void* logits, int64_t row_stride, const
   }
   if (R == 0) return 0;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (row_stride * 2) % 16 == 0) ? 1 : 0;
-  int grid = 0, npp = 0;
+  int grid = 0, npp = 0, nw = 0;
   size_t smem = 0;
-  if (!vec_ok || k > kWrCap / 2 || !warp_form_config(kd_head_select_kernel, R, V, &grid, &smem, &npp)) {
+  if (!vec_ok || k > kWrCap / 2 || !warp_form_config(kd_head_select_kernel<__nv_bfloat16>, R, V, &grid, &smem, &npp, &nw)) {
     // shapes the warp form does not take: the full-row compaction of the scratch logits gives the same result
     return kd_topk_logprobs(logits, KD_DTYPE_BF16, R, V, row_stride, k, out_v, out_i, stream);
   }
-  kd_head_select_kernel<<<grid, 32 * kWrWarps, smem, (cudaStream_t)stream>>>(
+  kd_head_select_kernel<__nv_bfloat16><<<grid, 32 * nw, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)logits, R, V, row_stride, k, (const __nv_bfloat16*)pmax, pmax_stride, (const float2*)part,
       part_stride, n_part, (__half*)out_v, out_i, npp);
   return check_launch("kd_head_select launch");

@@ -15,7 +15,8 @@ def teacher_topk_logprobs(teacher_logits, k, vocab_size=None):
 
     ``vocab_size`` mirrors train.py:82-83 (truncate the teacher to the student's vocabulary).
     Order: log-prob descending; equal logits by ascending index (hard part 4).
-    No [.., V] temporary is written: one read of the logits.
+    No [.., V] temporary is written: one read of the logits (plus the ~k 64-byte pieces per row that can hold a
+    top-k entry).
     """
     require_cuda(teacher_logits)
     lib = _lib.load()
@@ -34,8 +35,14 @@ def teacher_topk_logprobs(teacher_logits, k, vocab_size=None):
     out_v = torch.empty((R, k), dtype=torch.float16, device=dev)
     out_i = torch.empty((R, k), dtype=torch.int32, device=dev)
     if R > 0:
-        check(lib.kd_topk_logprobs(x2.data_ptr(), dtype_code(x2.dtype), R, V, x2.stride(0), int(k), out_v.data_ptr(),
-                                   out_i.data_ptr(), stream_ptr(dev)), "kd_topk_logprobs")
+        # workspace of the two-kernel form (piece maxima + partial log-sum-exp records, ~1/32 of the logits); the
+        # library's internal sweep stream reads and writes it, but every use is joined back into the current stream
+        # before the call's last kernel, so the caching allocator's stream bookkeeping stays valid
+        ws_bytes = int(lib.kd_topk_workspace_bytes(R, V))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
+        check(lib.kd_topk_logprobs_ws(x2.data_ptr(), dtype_code(x2.dtype), R, V, x2.stride(0), int(k), out_v.data_ptr(),
+                                      out_i.data_ptr(), ws_ptr, ws_bytes, stream_ptr(dev)), "kd_topk_logprobs_ws")
     return out_v.reshape(*lead, k), out_i.reshape(*lead, k)
 
 
