@@ -521,6 +521,11 @@ def run_ours(args):
             torch.cuda.empty_cache()
             extra["kernels"] = _guard(bench_kernels.run)
             extra["gpu_baselines"] = _guard(gpu_baselines.run, 5, False)
+            from tools import read_probe
+
+            # what a read-only stream can reach on this box (K2 forward and K3 are read-only; MEASURED_PEAKS' HBM
+            # figure is a copy) - context for the `kernels` fractions, which stay against the measured copy peak
+            extra["read_probe"] = _guard(read_probe.probe, 1 << 30)
         if not args.no_cpu_baseline:
             torch.cuda.empty_cache()
             extra["cpu_baseline"] = cpu_baseline_subprocess()
@@ -611,7 +616,8 @@ def run_ours(args):
         }
         if multi is not None:
             line["multi_gpu"] = multi
-        for k in ("e2e_topk_cache", "kernels", "gpu_baselines"):
+        line["box"] = box_info(torch)
+        for k in ("e2e_topk_cache", "kernels", "gpu_baselines", "read_probe"):
             if k in extra:
                 line[k] = extra[k]
         if "cpu_baseline" in extra:
@@ -623,6 +629,24 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def box_info(torch):
+    """Driver / GPU identity of the box that ran this line: the pool's boxes differ (driver 580.159 vs 580.178, settled
+    SM clocks 1180 - 1400 MHz under the same 1 kW cap), and run-to-run comparisons need to know which one they got."""
+    info = {"gpu": torch.cuda.get_device_name(0), "torch": torch.__version__}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        info["driver"] = pynvml.nvmlSystemGetDriverVersion()
+        info["vbios"] = pynvml.nvmlDeviceGetVbiosVersion(h)
+        info["uuid_tail"] = pynvml.nvmlDeviceGetUUID(h)[-8:]
+        info["power_limit_w"] = pynvml.nvmlDeviceGetPowerManagementLimit(h) / 1000.0
+    except Exception as e:  # noqa: BLE001 - context only
+        info["nvml_error"] = str(e)[:80]
+    return info
 
 
 def cublas_same_shape(torch, h2, Wd):

@@ -915,7 +915,7 @@ constexpr int kStatCtasPerSm = 3;
 constexpr int kStatU = 4;                     // 16-byte loads per lane and register batch (two batches)
 constexpr int kStatMaxBlocks = 8;             // row blocks of the sweep / selection pipeline
 #ifndef KD_STAT_MINB
-#define KD_STAT_MINB 4                        // sweep CTAs the register budget allows per SM (4: <= 64 registers)
+#define KD_STAT_MINB 3                        // sweep CTAs the register budget allows per SM (3: <= 80 registers, no spills; 4 = 64 registers spilled and measured 10 % slower)
 #endif
 
 // position of a warp in its sequence of batches: item wid + j * wstride, batch b of the item; (row, seg) are carried

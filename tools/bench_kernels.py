@@ -109,9 +109,15 @@ def run(seconds=0.3):
     R, k = 16 * 512, 64
     x = _logits(16, 512, dev, 1).reshape(R, V)
     t, n = _time(lambda: K.teacher_topk_logprobs(x, k), seconds)
-    out["k3_topk64 configs[2] shape R=8192"] = _hbm("kd_topk_kernel", t, n, 2.0 * R * V + 6.0 * R * k,
+    out["k3_topk64 configs[2] shape R=8192"] = _hbm("kd_topk_warp_kernel (warp-per-row form: sweep + selection)", t, n,
+                                                    2.0 * R * V + 6.0 * R * k,
                                                     "read logits (bf16) + write fp16 values and int32 indices", hbm)
-    del x
+    xs = x[:1024]
+    t, n = _time(lambda: K.teacher_topk_logprobs(xs, k), seconds)
+    out["k3_topk64 R=1024 (configs[0] row count)"] = _hbm(
+        "kd_topk_stats_kernel + kd_head_select_kernel (two-kernel form; the rows fit the 126 MB L2 only in part)", t, n,
+        2.0 * 1024 * V + 6.0 * 1024 * k, "read logits (bf16) + write fp16 values and int32 indices", hbm)
+    del x, xs
     torch.cuda.empty_cache()
 
     # ---- configs[2]: teacher head -> top-64 without [R,V] logits, then the sparse K1 step on the same tokens ----
