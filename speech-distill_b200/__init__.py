@@ -7,6 +7,7 @@ Host-side mirror of the reference interface over libkd_b200.so (C ABI: include/k
 * ``fused_linear_kd_loss``        - LM head + KD without materialising logits (K1)
 * ``teacher_topk_logprobs``       - reference ``extract_teacher_logits.py:114-129`` / ``train.py:82-91``
 * ``freeze_model_weights`` / ``fused_linear_cross_entropy`` / ``mask_old_rows_`` - reference ``stage1.py:29-93``
+* ``ops``                         - the two loss entry points as ``torch.library`` custom ops (``torch.compile``-traceable)
 """
 from ._lib import KdError, LIB_PATH, load as load_library  # noqa: F401
 from .loss import (DistillationLoss, fused_linear_kd_loss, fused_linear_kd_value_and_grad,  # noqa: F401

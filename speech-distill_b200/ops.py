@@ -22,7 +22,8 @@ from torch import Tensor
 
 from . import _lib
 from . import loss as L
-from ._lib import IGNORE_INDEX, require_cuda
+from ._lib import require_cuda
+from .loss import IGNORE_INDEX
 
 _NS = "speech_distill_b200"
 
@@ -109,9 +110,10 @@ def _teacher_args(B, T, dev, teacher_logits, teacher_top_k_v, teacher_top_k_i):
 def _fused_linear_kd(hidden: Tensor, weight: Tensor, labels: Tensor, teacher_logits: Optional[Tensor],
                      teacher_top_k_v: Optional[Tensor], teacher_top_k_i: Optional[Tensor],
                      speech_token_mask: Optional[Tensor], temperature: float, alpha: float, ignore_index: int,
-                     logit_cache_mb: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                     logit_cache_mb: float, old_vocab_size: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """hidden [B,T,H] bf16, weight [V,H] bf16 -> (losses [4], row_stats [R,4], row_target [R] int32, n_valid [1] int32,
-    logit cache uint8 [n]); everything the backward op needs travels as op outputs."""
+    logit cache uint8 [n]); everything the backward op needs travels as op outputs.  ``old_vocab_size`` is only
+    handed on to the backward (stage1's frozen rows of dW)."""
     B, T, H = hidden.shape
     dev = hidden.device
     h2 = hidden.reshape(B * T, H)
@@ -132,7 +134,7 @@ def _fused_linear_kd(hidden: Tensor, weight: Tensor, labels: Tensor, teacher_log
 
 @_fused_linear_kd.register_fake
 def _(hidden, weight, labels, teacher_logits, teacher_top_k_v, teacher_top_k_i, speech_token_mask, temperature, alpha,
-      ignore_index, logit_cache_mb):
+      ignore_index, logit_cache_mb, old_vocab_size):
     B, T, H = hidden.shape
     R, V = B * T, weight.shape[0]
     nbytes = int(_lib.load().kd_fused_logit_cache_bytes(int(R), int(V), 0, L.logit_cache_budget(logit_cache_mb)))
@@ -172,18 +174,19 @@ def _(hidden, weight, teacher_logits, teacher_top_k_v, teacher_top_k_i, row_stat
 
 
 def _fused_setup(ctx, inputs, output):
-    (hidden, weight, labels, teacher_logits, topk_v, topk_i, mask, temperature, alpha, ignore_index, cache_mb) = inputs
+    (hidden, weight, labels, teacher_logits, topk_v, topk_i, mask, temperature, alpha, ignore_index, cache_mb,
+     old_vocab_size) = inputs
     losses, row_stats, row_target, n_valid, cache = output
     ctx.save_for_backward(hidden, weight, teacher_logits, topk_v, topk_i, row_stats, row_target, n_valid, cache)
-    ctx.cfg = (temperature, alpha)
+    ctx.cfg = (temperature, alpha, old_vocab_size)
 
 
 def _fused_backward_formula(ctx, g_losses, g_row_stats, g_row_target, g_n_valid, g_cache):
     hidden, weight, teacher_logits, topk_v, topk_i, row_stats, row_target, n_valid, cache = ctx.saved_tensors
-    temperature, alpha = ctx.cfg
+    temperature, alpha, old_vocab_size = ctx.cfg
     dH, dW = _fused_linear_kd_bwd(hidden, weight, teacher_logits, topk_v, topk_i, row_stats, row_target, n_valid, cache,
-                                  g_losses[0], temperature, alpha, getattr(ctx, "old_vocab_size", 0))
-    return dH, dW, None, None, None, None, None, None, None, None, None
+                                  g_losses[0], temperature, alpha, old_vocab_size)
+    return dH, dW, None, None, None, None, None, None, None, None, None, None
 
 
 _fused_linear_kd.register_autograd(_fused_backward_formula, setup_context=_fused_setup)
@@ -191,10 +194,11 @@ _fused_linear_kd.register_autograd(_fused_backward_formula, setup_context=_fused
 
 def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, teacher_top_k_v=None, teacher_top_k_i=None,
                          speech_token_mask=None, temperature=2.0, alpha=0.5, ignore_index=IGNORE_INDEX,
-                         logit_cache_mb=None):
+                         logit_cache_mb=None, old_vocab_size=0):
     """LM head + KD loss without logits as registered ops: ``(total, task, distill, teacher_task)``; hidden
     ``[B,T,H]`` and lm_head_weight ``[V,H]`` in bf16.  With no teacher at all the loss is the plain cross-entropy
-    (``total == task``), as in ``loss.fused_linear_kd_loss``."""
+    (``total == task``), as in ``loss.fused_linear_kd_loss``; ``old_vocab_size`` > 0 leaves the dW rows of the old
+    vocabulary uncomputed and zero (stage1.py:29-73)."""
     require_cuda(hidden, lm_head_weight)
     if hidden.dim() != 3:
         raise ValueError("hidden must be [B, T, H]")
@@ -207,6 +211,7 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, te
         teacher_top_k_v, teacher_top_k_i = teacher_top_k_v.detach(), teacher_top_k_i.detach()
     mb = float(L.logit_cache_budget(logit_cache_mb)) / float(1 << 20)
     losses = _fused_linear_kd(hidden, lm_head_weight, labels, teacher_logits, teacher_top_k_v, teacher_top_k_i,
-                              speech_token_mask, float(temperature), float(alpha), int(ignore_index), mb)[0]
+                              speech_token_mask, float(temperature), float(alpha), int(ignore_index), mb,
+                              int(old_vocab_size))[0]
     rest = losses.detach()
     return losses[0], rest[1], rest[2], rest[3]

@@ -81,7 +81,7 @@ def head_topk_layout(V):
     return a.value, b.value
 
 
-def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024, fused=True):
+def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=2048, fused=True):
     """Teacher LM head -> log_softmax -> top-k without the teacher's [B,T,V] logits
     (train.py:60-94 on-the-fly mode, extract_teacher_logits.py:109-129).
 
@@ -89,7 +89,10 @@ def teacher_head_topk(hidden, lm_head_weight, k, vocab_size=None, row_block=1024
     ``vocab_size`` truncates the teacher vocabulary to the student's (train.py:82-83) by dropping weight rows,
     which is the same as slicing the logits.  Rows are processed ``row_block`` at a time through two fixed scratch
     buffers of row_block x V bf16: the head GEMM of block b + 1 (tensor-core bound, current stream) runs beside the
-    selection of block b (side stream).
+    selection of block b (side stream).  Every block re-reads the teacher's lm_head weight (626 MB for SoulX-1.7B), so
+    larger blocks cost less: measured at configs[2] size (tools/head_topk_sweep.py, one B200, fused) 4.90 ms with
+    1024-row blocks, 4.70 ms with 2048 (default: 2 x 0.63 GB of scratch), 4.33 ms with 4096 (2 x 1.25 GB - the size of
+    the whole [B*T, V] logits this function exists to avoid at B*T = 8192), 3.34 ms for the head GEMM alone.
 
     ``fused=True`` (default): the GEMM's epilogue (kd_head_logits_stats) also leaves the maximum of every 32-column
     piece and partial log-sum-exp records, and the selection (kd_head_topk_select) reads only the ~k pieces per row

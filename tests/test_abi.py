@@ -192,3 +192,31 @@ def test_ctypes_signatures_match_header():
                 want.append("int")
         got = [kinds_of.get(a, "ptr") for a in args]
         assert got == want, f"{name}: ctypes {got} != header {want}"
+
+
+def test_custom_ops_registered_with_fake_kernels():
+    """speech_distill_b200.ops registers the loss entry points with torch.library; their fake (meta) kernels give the
+    output shapes a compiler traces with - checked here on fake CUDA tensors, no GPU needed."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    import speech_distill_b200  # noqa: F401
+    from speech_distill_b200 import ops  # noqa: F401
+
+    ns = torch.ops.speech_distill_b200
+    for name in ("kd_loss", "fused_linear_kd", "fused_linear_kd_bwd"):
+        assert hasattr(ns, name)
+    with FakeTensorMode():
+        h = torch.empty(2, 8, 64, dtype=torch.bfloat16, device="cuda")
+        W = torch.empty(1000, 64, dtype=torch.bfloat16, device="cuda")
+        lab = torch.empty(2, 8, dtype=torch.int64, device="cuda")
+        y = torch.empty(2, 8, 1000, dtype=torch.bfloat16, device="cuda")
+        losses, row_stats, row_target, n_valid, cache = ns.fused_linear_kd(h, W, lab, y, None, None, None, 2.0, 0.5, -100,
+                                                                           1536.0, 0)
+        assert tuple(losses.shape) == (4,) and losses.dtype == torch.float32
+        assert tuple(row_stats.shape) == (16, 4) and tuple(row_target.shape) == (16,) and cache.dtype == torch.uint8
+        dH, dW = ns.fused_linear_kd_bwd(h, W, y, None, None, row_stats, row_target, n_valid, cache, losses[0], 2.0, 0.5, 0)
+        assert dH.shape == h.shape and dW.shape == W.shape
+        z = torch.empty(2, 8, 1000, dtype=torch.bfloat16, device="cuda")
+        l4, dz = ns.kd_loss(z, lab, y, None, None, None, 2.0, 0.5, -100)
+        assert tuple(l4.shape) == (4,) and dz.shape == z.shape and dz.dtype == z.dtype
