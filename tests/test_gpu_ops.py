@@ -36,7 +36,7 @@ def test_kd_loss_op_matches_function_path():
     (ref[0] * 1.5).backward()
     (got[0] * 1.5).backward()
     for a, b in zip(ref, got):
-        assert float(a) == float(b)  # same kernel, same inputs
+        assert float(a.detach()) == float(b.detach())  # same kernel, same inputs
     assert not got[1].requires_grad and not got[3].requires_grad
     assert float((za.grad.float() - zb.grad.float()).abs().max()) <= 2.0 ** -8 * float(za.grad.float().abs().max())
     # sparse teacher
@@ -44,7 +44,7 @@ def test_kd_loss_op_matches_function_path():
     ref = K.kd_loss_on_logits(z, labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
     got = ops.kd_loss(z, labels, teacher_top_k_v=tv, teacher_top_k_i=ti)
     for a, b in zip(ref, got):
-        assert float(a) == float(b)
+        assert float(a.detach()) == float(b.detach())
     with pytest.raises(ValueError):
         ops.kd_loss(z, labels)
 
@@ -67,7 +67,7 @@ def test_fused_op_matches_function_path(teacher):
     ref[0].backward()
     got[0].backward()
     for a, b in zip(ref, got):
-        assert float(a) == float(b)
+        assert float(a.detach()) == float(b.detach())
     assert torch.equal(ha.grad, hb.grad) and torch.equal(Wa.grad, Wb.grad)  # same kernels, same order
 
 
@@ -96,7 +96,7 @@ def test_ops_trace_under_torch_compile():
     compiled = torch.compile(m, backend="aot_eager", fullgraph=True)  # fullgraph: a graph break at the op would raise
     out = compiled(hc, labels, y)
     out[0].backward()
-    assert float(out[0]) == float(eager[0]) and float(out[1]) == float(eager[1])
+    assert float(out[0].detach()) == float(eager[0].detach()) and float(out[1]) == float(eager[1])
     assert torch.equal(hc.grad, g_eager[0]) and torch.equal(m.weight.grad, g_eager[1])
 
     def on_logits(z, labels, teacher):
@@ -105,4 +105,4 @@ def test_ops_trace_under_torch_compile():
     z = (h.float() @ W.float().t()).bfloat16().requires_grad_(True)
     e = on_logits(z, labels, y)
     c = torch.compile(on_logits, backend="aot_eager", fullgraph=True)(z, labels, y)
-    assert float(e) == float(c)
+    assert float(e.detach()) == float(c.detach())
