@@ -184,11 +184,12 @@ def _fused_workspace(R, H, V, v_chunk, device, K=0):
 
 def logit_cache_budget(mb=None):
     """Bytes the forward may spend on the logit cache (include/kd_b200.h, "Logit cache"): a constant chosen by the
-    caller - ``mb`` megabytes, else KD_LOGIT_CACHE_MB, else 1536 - never a function of V."""
+    caller - ``mb`` megabytes, else KD_LOGIT_CACHE_MB, else 6144 - never a function of V.  (The buffer itself is
+    min(budget, what the R x V logits need in fp16): 1.23 GB at configs[1], the full 6 GB at configs[3]'s 16,384 rows.)"""
     import os
 
     if mb is None:
-        mb = float(os.environ.get("KD_LOGIT_CACHE_MB", "1536"))
+        mb = float(os.environ.get("KD_LOGIT_CACHE_MB", "6144"))
     return max(int(mb * (1 << 20)), 0)
 
 
@@ -408,7 +409,7 @@ def fused_linear_kd_loss(hidden, lm_head_weight, labels, teacher_logits=None, sp
     (the reference's boolean row gather, distillation_loss.py:37-45, without its host sync).  Default (None):
     on for the top-k cache and for plain CE, where only [R,H] / [R,K] rows move; off for a dense teacher, whose
     [R,V] rows would have to be copied (worth it from roughly 15 % ignored rows on: pass True).
-    ``logit_cache_mb``: budget of the forward's logit cache (None = KD_LOGIT_CACHE_MB or 1536 MB, 0 = off).  The
+    ``logit_cache_mb``: budget of the forward's logit cache (None = KD_LOGIT_CACHE_MB or 6144 MB, 0 = off).  The
     cache is a constant-size buffer, independent of V: vocabulary chunks that fit are differentiated from the cached
     logits by an HBM-bound kernel beside the dW / dH GEMMs, the rest is recomputed on the tensor cores.
     ``reduce_fn`` / ``count_reduce_fn`` / ``grad_sync``: token-shard data-parallel hooks (dist.py): all-reduce of
