@@ -330,7 +330,9 @@ def run_ours(args):
     if sync_mode == "overlap":
         max_ctas = int(os.environ.get("KD_BENCH_NCCL_CTAS", "32"))
         sync = KD.GradSync(group=KD.GradSync.new_group(max_ctas), n_ranges=int(os.environ.get("KD_BENCH_RANGES", "6")),
-                           max_ctas=max_ctas, reserve_sms=os.environ.get("KD_BENCH_SM_LIMIT", "0") == "1")
+                           max_ctas=max_ctas, reserve_sms=os.environ.get("KD_BENCH_SM_LIMIT", "0") == "1",
+                           backend=os.environ.get("KD_BENCH_BACKEND", "nccl"),
+                           multimem_ctas=int(os.environ.get("KD_BENCH_MM_CTAS", "16")))
 
     def step(hh, yy, ll, grad_sync=sync, reduce=True):
         out = K.fused_linear_kd_loss(hh, W, ll, teacher_logits=yy, temperature=TAU, alpha=ALPHA,
@@ -831,7 +833,7 @@ def vocab_parallel_block(K, dist, torch, dev, rank, world, steps):
     ref[0].backward()
     torch.cuda.synchronize()
     errs = torch.tensor([
-        max(abs(float(a) - float(b)) / max(1.0, abs(float(b))) for a, b in zip(out, ref)),
+        max(abs(float(a.detach()) - float(b.detach())) / max(1.0, abs(float(b.detach()))) for a, b in zip(out, ref)),
         float((hs.grad.float() - hu.grad.float()).abs().max() / hu.grad.float().abs().max()),
         float((Ws.grad.float() - Wu.grad[v0:v1].float()).abs().max() / Wu.grad.float().abs().max())], device=dev)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)

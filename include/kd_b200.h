@@ -42,7 +42,7 @@ extern "C" {
 #define KD_DTYPE_BF16 1
 #define KD_DTYPE_F16 2
 
-#define KD_ABI_VERSION 4
+#define KD_ABI_VERSION 5
 
 /* OR-ed into grad_dtype of the fused backward: dH is written as fp32 (a vocab-parallel caller sums the
  * per-slice partial dH across ranks before rounding) while dW keeps the base dtype. */
@@ -114,6 +114,15 @@ int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V, int64_t ro
 size_t kd_topk_workspace_bytes(int64_t R, int V);
 int kd_topk_logprobs_ws(const void* logits, int dtype, int64_t R, int V, int64_t row_stride, int k,
                         void* out_v, int32_t* out_i, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- token-shard gradient all-reduce through the NVSwitch (NVLS multicast) ---------------------
+ * The SUM all-reduce of lm_head.weight.grad that train.py's data-parallel wrapper (accelerate / DDP) performs, for a
+ * gradient that lives in a symmetric buffer with one multicast address (torch.distributed._symmetric_memory): this
+ * rank reduces its 1/world share of [byte_offset, byte_offset + bytes) in the switch (multimem.ld_reduce, fp32
+ * accumulation) and stores the sums into every replica (multimem.st).  The caller brackets the call with cross-GPU
+ * barriers on the same stream (all replicas written before, all sums stored after).  dtype: KD_DTYPE_BF16 / _F32. */
+int kd_multimem_allreduce(void* multicast_base, size_t byte_offset, size_t bytes, int dtype, int rank, int world,
+                          int ctas, void* stream);
 
 /* ---- measurement aid: read-only streaming bandwidth of this GPU ------------------------------
  * Not on the reference's path: bench.py / tools/read_probe.py time it to state what a read-only stream (K2 forward,
@@ -203,6 +212,9 @@ int kd_fused_linear_bwd(const void* h, int64_t h_stride, const void* W, int64_t 
  * data-parallel caller can all-reduce finished dW row blocks while later ones are computed:
  * dW rows of the range are final when the call's work completes; dH is accumulated in the workspace across
  * calls (same workspace every call): KD_RANGE_FIRST starts the accumulation, KD_RANGE_LAST writes dH.
+ * dw_ready_stream (may be null): the stream that will consume a finished range's dW rows (the gradient all-reduce).
+ * Non-null: after every range but the last, THAT stream waits for the rows and the caller's stream does not, so the
+ * next range's kernels follow without a pipeline drain; the last range always joins into `stream`.
  * sm_limit > 0 caps the SMs the GEMM kernels occupy (leave the rest to the collective's CTAs).
  * v_offset: 0, or the first vocabulary index of this rank's slice in vocab-parallel mode (see below). */
 #define KD_RANGE_FIRST 1
@@ -215,7 +227,8 @@ int kd_fused_linear_bwd_range(const void* h, int64_t h_stride, const void* W, in
                               const float* grad_coef, int grad_dtype, void* dH, int64_t dh_stride, void* dW,
                               int64_t dw_stride, int64_t dw_row_begin, int v_chunk, int v_begin, int v_end,
                               int range_flags, int sm_limit, int v_offset, const void* logit_cache,
-                              size_t logit_cache_bytes, void* workspace, size_t workspace_bytes, void* stream);
+                              size_t logit_cache_bytes, void* workspace, size_t workspace_bytes,
+                              void* dw_ready_stream, void* stream);
 
 /* Measurement hooks (no arithmetic).  kd_launch_count: kernels this library has launched in this process so far.
  * kd_fused_bwd_trace_begin arms a trace of the following kd_fused_linear_bwd* calls: every kernel they launch is

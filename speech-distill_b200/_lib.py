@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("KD_B200_LIB") or os.path.join(_HERE, "libkd_b200.so")
 
 KD_DTYPE_F32, KD_DTYPE_BF16, KD_DTYPE_F16 = 0, 1, 2
 KD_TEACHER_NONE, KD_TEACHER_DENSE, KD_TEACHER_SPARSE = 0, 1, 2
-ABI_VERSION = 4  # KD_ABI_VERSION in include/kd_b200.h
+ABI_VERSION = 5  # KD_ABI_VERSION in include/kd_b200.h
 KD_RANGE_FIRST, KD_RANGE_LAST = 1, 2
 KD_GRAD_DH_F32 = 0x100
 
@@ -40,6 +40,7 @@ SIGNATURES = {
     "kd_topk_logprobs_ws": (_i32, [_vp, _i32, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "kd_mask_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
     "kd_probe_read_bandwidth": (_i32, [_vp, _sz, _i32, _i32, _i32, _vp, _vp]),
+    "kd_multimem_allreduce": (_i32, [_vp, _sz, _sz, _i32, _i32, _i32, _i32, _vp]),
     "kd_fused_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "kd_fused_logit_cache_bytes": (_sz, [_i32, _i32, _i32, _sz]),
     "kd_compact_rows": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -52,7 +53,7 @@ SIGNATURES = {
                                    _vp, _sz, _vp]),
     "kd_fused_linear_bwd_range": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp,
                                          _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32,
-                                         _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp]),
+                                         _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp, _vp]),
     "kd_fused_linear_fwd_partial": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp,
                                            _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp, _sz, _vp]),
     "kd_fused_merge_workspace_bytes": (_sz, []),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkd_b200.so")
-SOURCES = ["kd_api.cu", "kd_stream.cu", "kd_topk.cu", "kd_rows.cu", "kd_probe.cu", "kd_fused.cu"]
+SOURCES = ["kd_api.cu", "kd_stream.cu", "kd_topk.cu", "kd_rows.cu", "kd_probe.cu", "kd_multimem.cu", "kd_fused.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -98,7 +98,8 @@ class GradSync:
     32 CTAs without a reservation is the fastest setting.
     """
 
-    def __init__(self, group=None, n_ranges=6, max_ctas=32, sm_count=None, reserve_sms=False):
+    def __init__(self, group=None, n_ranges=6, max_ctas=32, sm_count=None, reserve_sms=False, backend="nccl",
+                 multimem_ctas=16):
         self.group = group
         self.n_ranges = int(n_ranges)
         self.max_ctas = int(max_ctas)
@@ -106,6 +107,54 @@ class GradSync:
         self._sm_count = sm_count
         self._pending = []
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        # backend "multimem": the gradient lives in a symmetric buffer and every range is reduced in the NVSwitch by
+        # kd_multimem_allreduce (csrc/kd_multimem.cu) - 2/G of the bytes through this GPU's SMs instead of a ring's
+        # 2 (G-1)/G, a few CTAs for ~0.1 ms per range.  Needs NVLS multicast (torch symmetric memory reports it); falls
+        # back to NCCL otherwise.
+        self.backend = backend if self.active else "nccl"
+        self.multimem_ctas = int(multimem_ctas)
+        self._symm = None       # (buffer tensor [V, H], handle, key)
+        self._side = None
+        self._mm_ranges = 0
+        self._out = None        # this backward's result tensor (the reduced rows are copied out range by range)
+
+    def _new_out(self, V, H, dtype, device, zero_rows):
+        self._out = (torch.zeros if zero_rows > 0 else torch.empty)((int(V), int(H)), dtype=dtype, device=device)
+        self._out.record_stream(self._side)  # written on the side stream, range by range
+
+    def result(self):
+        """The reduced gradient of the backward that just finished (multimem backend): an ordinary tensor of its own -
+        the symmetric buffer is overwritten by the next backward."""
+        out, self._out = self._out, None
+        return out
+
+    def grad_buffer(self, V, H, dtype, device, zero_rows=0):
+        """The [V, H] tensor the backward should write dW into: a symmetric (multicast-mapped) buffer for the multimem
+        backend, None for NCCL (the backward allocates as usual).  Allocated and exchanged once per shape."""
+        if self.backend != "multimem":
+            return None
+        key = (int(V), int(H), dtype, torch.device(device))
+        if self._symm is not None and self._symm[2] == key:
+            self._new_out(V, H, dtype, device, zero_rows)
+            return self._symm[0]
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty((int(V), int(H)), dtype=dtype, device=device)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)  # every rank of the job holds a replica
+            if not int(getattr(hdl, "multicast_ptr", 0)):
+                raise RuntimeError("no NVLS multicast support on this system")
+        except Exception as e:  # noqa: BLE001 - any failure means: use NCCL
+            import warnings
+
+            warnings.warn(f"GradSync: multimem backend unavailable ({type(e).__name__}: {e}); using NCCL")
+            self.backend = "nccl"
+            return None
+        self._symm = (buf, hdl, key)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        self._new_out(V, H, dtype, device, zero_rows)
+        return buf
 
     @staticmethod
     def new_group(max_ctas=32, **kw):
@@ -132,11 +181,52 @@ class GradSync:
         lim = self._sm_count - self.max_ctas
         return lim - (lim % 2) if lim >= 2 else 0  # CTA pairs
 
-    def reduce_rows(self, grad, r0, r1):
-        if self.active and r1 > r0:
-            self._pending.append(dist.all_reduce(grad[r0:r1], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+    def ready_stream_ptr(self, device):
+        """Raw handle of the stream the finished rows of a range are handed to (kd_fused_linear_bwd_range's
+        dw_ready_stream): the all-reduce of every range but the last is enqueued there, so the caller's stream - from
+        which the next range's kernels fork - never waits for a range's dW chain.  0 when inactive."""
+        if not self.active:
+            return 0
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side.cuda_stream
+
+    def reduce_rows(self, grad, r0, r1, last=True):
+        """``last=False``: the rows' completion was handed to the ready stream (see ready_stream_ptr), the collective is
+        enqueued behind it there; ``last=True`` (or no ready stream): behind the current stream."""
+        if not (self.active and r1 > r0):
+            return
+        on_side = (not last) and self._side is not None
+        if self.backend == "multimem" and self._symm is not None and grad.data_ptr() == self._symm[0].data_ptr():
+            from . import _lib
+
+            buf, hdl, _ = self._symm
+            row_bytes = buf.stride(0) * buf.element_size()
+            if not on_side:  # the range's dW rows are final on the current stream
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(grad.device))
+            with torch.cuda.stream(self._side):
+                if not on_side:
+                    self._side.wait_event(ready)
+                hdl.barrier(channel=0)  # every rank has written its rows of the range
+                _lib.check(_lib.load().kd_multimem_allreduce(int(hdl.multicast_ptr), int(r0) * row_bytes,
+                                                             int(r1 - r0) * row_bytes, _lib.dtype_code(buf.dtype),
+                                                             int(hdl.rank), int(hdl.world_size), self.multimem_ctas,
+                                                             self._side.cuda_stream), "kd_multimem_allreduce")
+                hdl.barrier(channel=1)  # every rank's sums have landed in every replica
+                self._out[r0:r1].copy_(buf[r0:r1], non_blocking=True)
+            self._mm_ranges += 1
+            return
+        if on_side:  # NCCL's stream waits for the stream that is current at the call: make it the ready stream
+            with torch.cuda.stream(self._side):
+                self._pending.append(dist.all_reduce(grad[r0:r1], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
+        self._pending.append(dist.all_reduce(grad[r0:r1], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):
         for w in self._pending:
             w.wait()
         self._pending = []
+        if self._mm_ranges:
+            torch.cuda.current_stream(self._symm[0].device).wait_stream(self._side)
+            self._mm_ranges = 0

@@ -335,9 +335,16 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
     dH = torch.empty((R, H), dtype=torch.float32 if dh_fp32 else grad_dtype, device=dev) if need_h else None
     dW = None
     gcode = dtype_code(grad_dtype) | (_lib.KD_GRAD_DH_F32 if dh_fp32 else 0)
+    symm = None
     if need_w:
         # rows below dw_row_begin are never computed (stage1 frozen vocabulary): they stay zero
-        dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
+        symm = None
+        if grad_sync is not None and hasattr(grad_sync, "grad_buffer"):
+            symm = grad_sync.grad_buffer(V, H, grad_dtype, dev, int(dw_row_begin))
+        if symm is not None:  # multimem backend: dW is written into (and reduced inside) the symmetric buffer
+            dW = symm
+        else:
+            dW = (torch.zeros if dw_row_begin > 0 else torch.empty)((V, H), dtype=grad_dtype, device=dev)
         if n_rows is not None and dw_row_begin <= 0:
             # compacted rows and not a single live one: the dW GEMM is skipped, the gradient is zero (:47-53)
             check(lib.kd_zero_if_empty(dW.data_ptr(), dW.numel() * dW.element_size(), n_rows.data_ptr(),
@@ -347,6 +354,10 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
     ranges = [(0, V)]
     if grad_sync is not None and need_w:
         ranges = grad_sync.ranges(V, int(dw_row_begin), int(v_chunk))
+    # the stream on which the all-reduce of a finished range is enqueued (0: the current stream)
+    ready_stream = 0
+    if grad_sync is not None and need_w and len(ranges) > 1 and hasattr(grad_sync, "ready_stream_ptr"):
+        ready_stream = grad_sync.ready_stream_ptr(dev)
     for n, (v0, v1) in enumerate(ranges):
         flags = (_lib.KD_RANGE_FIRST if n == 0 else 0) | (_lib.KD_RANGE_LAST if n == len(ranges) - 1 else 0)
         # while an all-reduce is in flight its CTAs keep their SMs: the persistent GEMMs take the others
@@ -357,12 +368,14 @@ def _fused_backward(h, W, y, row_target, row_stats, n_norm, coef, tau, teacher_k
             _ptr(topk[0]) if K else 0, _ptr(topk[1]) if K else 0, K, row_target.data_ptr(), _ptr(n_rows),
             row_stats.data_ptr(), R, H, V, float(tau), n_norm.data_ptr(), coef.data_ptr(), gcode, _ptr(dH), H, _ptr(dW), H,
             int(dw_row_begin), int(v_chunk), int(v0), int(v1), flags, int(sm_limit), int(v_offset), _ptr(cache),
-            cache.numel() if cache is not None else 0, ws.data_ptr(), ws.numel(), stream_ptr(dev))
+            cache.numel() if cache is not None else 0, ws.data_ptr(), ws.numel(), ready_stream, stream_ptr(dev))
         check(rc, "kd_fused_linear_bwd_range")
         if grad_sync is not None and need_w:
-            grad_sync.reduce_rows(dW, max(v0, int(dw_row_begin)), v1)
+            grad_sync.reduce_rows(dW, max(v0, int(dw_row_begin)), v1, last=(n == len(ranges) - 1) or not ready_stream)
     if grad_sync is not None and need_w:
         grad_sync.finish()
+        if symm is not None:
+            dW = grad_sync.result()  # the reduced rows, copied out of the symmetric buffer range by range
     return dH, dW
 
 

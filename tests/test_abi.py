@@ -138,7 +138,8 @@ int main(void) {
                  (void*)kd_fused_bwd_trace_read, (void*)kd_device_info, (void*)kd_prepare_rows,
                  (void*)kd_finalize_losses, (void*)kd_stream_workspace_bytes, (void*)kd_dense_fwd_bwd,
                  (void*)kd_sparse_fwd_bwd, (void*)kd_scale_inplace, (void*)kd_topk_logprobs, (void*)kd_topk_workspace_bytes,
-                 (void*)kd_topk_logprobs_ws, (void*)kd_probe_read_bandwidth, (void*)kd_mask_rows,
+                 (void*)kd_topk_logprobs_ws, (void*)kd_probe_read_bandwidth, (void*)kd_multimem_allreduce,
+                 (void*)kd_mask_rows,
                  (void*)kd_compact_rows, (void*)kd_gather_rows, (void*)kd_zero_if_empty,
                  (void*)kd_fused_workspace_bytes, (void*)kd_fused_logit_cache_bytes, (void*)kd_fused_linear_fwd,
                  (void*)kd_fused_linear_bwd,

@@ -128,10 +128,13 @@ class _FullSizeRangeStub:
     all-reduce over identical ranks would leave behind on a side stream that waits for the range - it reads and
     rewrites the finished row block while the next range's GEMMs run."""
 
-    def __init__(self, n_ranges):
+    def __init__(self, n_ranges, ready=False):
         self.n_ranges, self.blocks = n_ranges, []
         self.side = torch.cuda.Stream()
         self.done = []
+        self.ready = ready
+        if ready:  # GradSync.ready_stream_ptr: finished rows are handed to the side stream, the caller's stream never
+            self.ready_stream_ptr = lambda device: self.side.cuda_stream  # waits for a range's dW chain
 
     def ranges(self, V, row_begin, v_chunk):
         from speech_distill_b200.dist import plan_ranges
@@ -141,9 +144,10 @@ class _FullSizeRangeStub:
     def sm_limit(self):
         return 0
 
-    def reduce_rows(self, grad, r0, r1):
+    def reduce_rows(self, grad, r0, r1, last=True):
         self.blocks.append((r0, r1))
-        self.side.wait_stream(torch.cuda.current_stream())
+        if last or not self.ready:  # otherwise the library already made the side stream wait for the rows
+            self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             grad[r0:r1].mul_(2.0)  # world_size = 2 ranks holding the same gradient: SUM = 2 x (exact in bf16)
             ev = torch.cuda.Event()
@@ -156,9 +160,11 @@ class _FullSizeRangeStub:
         self.done = []
 
 
-def test_gradsync_ranges_configs1_full_size():
+@pytest.mark.parametrize("ready", [False, True])
+def test_gradsync_ranges_configs1_full_size(ready):
     """The overlapped dW exchange at BASELINE configs[1] size: 6 vocabulary ranges handed to a stand-in all-reduce on
-    a side stream while the following ranges run = the one-call backward (dH bit for bit, dW exactly 2 x)."""
+    a side stream while the following ranges run = the one-call backward (dH bit for bit, dW exactly 2 x); with and
+    without the dw_ready_stream hand-over of kd_fused_linear_bwd_range."""
     import speech_distill_b200 as K
 
     h, W, y, labels = _inputs(8, 512, 77)
@@ -171,7 +177,7 @@ def test_gradsync_ranges_configs1_full_size():
         return hc.grad, Wc.grad
 
     gh0, gw0 = run(None)
-    stub = _FullSizeRangeStub(6)
+    stub = _FullSizeRangeStub(6, ready)
     gh1, gw1 = run(stub)
     assert len(stub.blocks) == 6 and stub.blocks[0][0] == 0 and stub.blocks[-1][1] == V_FULL
     assert all(a[1] == b[0] for a, b in zip(stub.blocks, stub.blocks[1:]))

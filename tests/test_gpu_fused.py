@@ -296,7 +296,7 @@ class _RangeStub:
     def sm_limit(self):
         return self._lim
 
-    def reduce_rows(self, grad, r0, r1):
+    def reduce_rows(self, grad, r0, r1, last=True):
         self.blocks.append((r0, r1))
 
     def finish(self):
