@@ -438,7 +438,9 @@ __global__ void __launch_bounds__(NT) kd_topk_kernel(const T* __restrict__ logit
 // restricted to the qualifying pieces.  16 row-warps per SM stream concurrently while others select.
 constexpr int kWrCap = 256;     // candidates / qualifying pieces per row (k <= 128)
 constexpr int kWrWarps = 8;     // rows per CTA
-constexpr int kWrPiece = 32;    // elements per piece (the head GEMM's epilogue produces the same pieces)
+constexpr int kWrPiece = 32;    // elements per piece behind the head GEMM and in the two-kernel form (its epilogue produces them)
+constexpr int kWarpPiece = 64;  // alternative piece size of the warp-per-row kernel (-DKD_TOPK_WARP_PIECE=kWarpPiece): half the
+                                // keys per row, 24 row-warps per SM instead of 16 - measured slower, see kd_topk_warp_kernel
 
 // Piece maxima live in shared memory as bf16 bit patterns rounded DOWN (exact for bf16 rows), so that counting
 // "pieces >= t" is one packed hardware compare (HSET2.BF16) + one packed add per two pieces.
@@ -509,18 +511,18 @@ __device__ __forceinline__ uint32_t warp_kth_largest_piece(const uint16_t* pv, i
 }
 
 // visit every element of the pieces whose maximum reaches tf (lanes take pieces round robin; slow path only)
-template <typename T, typename F>
+template <typename T, int PIECE, typename F>
 __device__ __forceinline__ void for_each_in_pieces(const T* __restrict__ row, int V, const uint16_t* pv, int n_pieces,
                                                    float tf, int lane, F&& fn) {
   for (int i = lane; i < n_pieces; i += 32) {
     if (!(bf16_bits_to_float(pv[i]) >= tf)) continue;
-    const int c0 = i * kWrPiece;
-    if (c0 + kWrPiece <= V) {
-      Vec8<T> e[4];
+    const int c0 = i * PIECE;
+    if (c0 + PIECE <= V) {
+      Vec8<T> e[PIECE / 8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) e[q].load_global(row + c0 + 8 * q);
+      for (int q = 0; q < PIECE / 8; ++q) e[q].load_global(row + c0 + 8 * q);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < PIECE / 8; ++q) {
         float g8[8];
         e[q].unpack(g8);
 #pragma unroll
@@ -532,16 +534,16 @@ __device__ __forceinline__ void for_each_in_pieces(const T* __restrict__ row, in
   }
 }
 
-template <typename T, typename P>
+template <typename T, int PIECE, typename P>
 __device__ __forceinline__ int warp_count_if(const T* row, int V, const uint16_t* pv, int n_pieces, float tf, int lane,
                                              P&& pred) {
   int c = 0;
-  for_each_in_pieces<T>(row, V, pv, n_pieces, tf, lane, [&](float x, int idx) { c += pred(order_key(x), idx) ? 1 : 0; });
+  for_each_in_pieces<T, PIECE>(row, V, pv, n_pieces, tf, lane, [&](float x, int idx) { c += pred(order_key(x), idx) ? 1 : 0; });
   return __reduce_add_sync(0xffffffffu, c);
 }
 
 // threshold -> candidates -> (slow path) -> the k outputs of row r; lm / ll = row maximum and log of the exp sum
-template <typename T>
+template <typename T, int PIECE>
 __device__ __forceinline__ void warp_select_emit(const T* __restrict__ row, int V, int k, const WarpRow& w, int n_pieces,
                                                  int n_pieces_pad, float lm, float ll, int64_t r,
                                                  __half* __restrict__ out_v, int32_t* __restrict__ out_i, int lane) {
@@ -585,13 +587,13 @@ __device__ __forceinline__ void warp_select_emit(const T* __restrict__ row, int 
   const int np = w.count[1];
   if (np <= kWrCap) {
     for (int j = lane; j < np; j += 32) {
-      const int c0 = (int)w.plist[j] * kWrPiece;
-      if (c0 + kWrPiece <= V) {
-        Vec8<T> e[4];
+      const int c0 = (int)w.plist[j] * PIECE;
+      if (c0 + PIECE <= V) {
+        Vec8<T> e[PIECE / 8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) e[q].load_global(row + c0 + 8 * q);
+        for (int q = 0; q < PIECE / 8; ++q) e[q].load_global(row + c0 + 8 * q);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < PIECE / 8; ++q) {
           float g8[8];
           e[q].unpack(g8);
 #pragma unroll
@@ -613,16 +615,16 @@ __device__ __forceinline__ void warp_select_emit(const T* __restrict__ row, int 
     uint32_t lo = order_key(tf), hi = 0xffffffffu;  // invariant: count(key >= lo) >= k
     while (lo < hi) {
       const uint32_t mid = lo + (uint32_t)(((uint64_t)hi - lo + 1) >> 1);
-      const int c = warp_count_if<T>(row, V, w.pv, n_pieces, tf, lane, [&](uint32_t key, int) { return key >= mid; });
+      const int c = warp_count_if<T, PIECE>(row, V, w.pv, n_pieces, tf, lane, [&](uint32_t key, int) { return key >= mid; });
       if (c >= k) lo = mid; else hi = mid - 1;
     }
     const uint32_t kth = lo;
-    const int above = warp_count_if<T>(row, V, w.pv, n_pieces, tf, lane, [&](uint32_t key, int) { return key > kth; });
+    const int above = warp_count_if<T, PIECE>(row, V, w.pv, n_pieces, tf, lane, [&](uint32_t key, int) { return key > kth; });
     const int need = k - above;
     int jl = 0, jh = V - 1;
     while (jl < jh) {
       const int mid = jl + ((jh - jl) >> 1);
-      const int c = warp_count_if<T>(row, V, w.pv, n_pieces, tf, lane,
+      const int c = warp_count_if<T, PIECE>(row, V, w.pv, n_pieces, tf, lane,
                                      [&](uint32_t key, int idx) { return key == kth && idx <= mid; });
       if (c >= need) jh = mid; else jl = mid + 1;
     }
@@ -630,7 +632,7 @@ __device__ __forceinline__ void warp_select_emit(const T* __restrict__ row, int 
     __syncwarp();
     if (lane == 0) w.count[0] = 0;
     __syncwarp();
-    for_each_in_pieces<T>(row, V, w.pv, n_pieces, tf, lane, [&](float x, int idx) {
+    for_each_in_pieces<T, PIECE>(row, V, w.pv, n_pieces, tf, lane, [&](float x, int idx) {
       const uint32_t key = order_key(x);
       if (key > kth || (key == kth && idx <= jmax)) push(x, idx);
     });
@@ -713,9 +715,11 @@ struct Pair16<__half> {
 // words, one shuffle for both halves), the lane's reference maximum is the maximum of its PIECES (a superset of its
 // own elements - any upper bound taken from the row serves the online sum), and the four keys of a lane group leave
 // in one 32-lane store per four vectors.
-template <typename T, int U, bool FULL>
+template <typename T, int U, bool FULL, int PIECE = kWrPiece>
 __device__ __forceinline__ void sweep_batch(const Vec8<T> (&v)[U], int base, int nvec, int lane,
                                             uint16_t* __restrict__ pieces, float& m, float& s) {
+  constexpr int LP = PIECE / 8;  // lanes (16-byte vectors) per piece: 4 or 8
+  static_assert(LP == 4 || LP == 8, "a piece is 32 or 64 elements");
   float vm = -CUDART_INF_F;
   bool skip[U];
   if constexpr (FULL && sizeof(T) == 2 && (U % 4) == 0) {
@@ -725,16 +729,17 @@ __device__ __forceinline__ void sweep_batch(const Vec8<T> (&v)[U], int base, int
       uint32_t c = Pair16<T>::max2(Pair16<T>::max2(v[u].a.x, v[u].a.y), Pair16<T>::max2(v[u].a.z, v[u].a.w));
       c = Pair16<T>::max2(c, __shfl_xor_sync(0xffffffffu, c, 1));
       c = Pair16<T>::max2(c, __shfl_xor_sync(0xffffffffu, c, 2));
+      if (LP == 8) c = Pair16<T>::max2(c, __shfl_xor_sync(0xffffffffu, c, 4));
       c = Pair16<T>::max2(c, __byte_perm(c, 0, 0x1032));  // both halves = the piece maximum
       pmf[u] = Pair16<T>::low(c);
       vm = fmaxf(vm, pmf[u]);
       skip[u] = false;
     }
 #pragma unroll
-    for (int u0 = 0; u0 < U; u0 += 4) {  // lane (l & 3) = j stores the key of vector u0 + j: one store per 4 vectors
-      const int j = lane & 3;
+    for (int u0 = 0; u0 < U; u0 += 4) {  // lane j of a piece's lane group stores the key of vector u0 + j: one store
+      const int j = lane & (LP - 1);     // per 4 vectors (all 32 lanes for 32-element pieces, 16 for 64-element ones)
       const float mine = j == 0 ? pmf[u0] : (j == 1 ? pmf[u0 + 1] : (j == 2 ? pmf[u0 + 2] : pmf[u0 + 3]));
-      pieces[((base + (u0 + j) * 32) >> 2) + (lane >> 2)] = piece_key<T>(mine);
+      if (LP == 4 || j < 4) pieces[((base + (u0 + (j & 3)) * 32) / LP) + (lane / LP)] = piece_key<T>(mine);
     }
   } else {
 #pragma unroll
@@ -743,9 +748,10 @@ __device__ __forceinline__ void sweep_batch(const Vec8<T> (&v)[U], int base, int
       float x = (FULL || idx < nvec) ? vec_max8<T>(v[u]) : -CUDART_INF_F;
       skip[u] = !FULL && x == -CUDART_INF_F;  // past the end of the row: the registers hold stale data
       vm = fmaxf(vm, x);
-      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));  // four lanes = one 32-element piece
+      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));  // LP lanes = one piece
       x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 2));
-      if ((lane & 3) == 0 && (FULL || idx < nvec)) pieces[idx >> 2] = piece_key<T>(x);
+      if (LP == 8) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
+      if ((lane & (LP - 1)) == 0 && (FULL || idx < nvec)) pieces[idx / LP] = piece_key<T>(x);
     }
   }
   if (vm > m) {
@@ -769,11 +775,19 @@ __device__ __forceinline__ void sweep_batch(const Vec8<T> (&v)[U], int base, int
   }
 }
 
+// warp-per-row kernel: 16-byte loads per lane and register batch (two batches), elements per piece, CTAs per SM the
+// register budget allows (compile-time A/B switches: speech-distill_b200/build.py --variant NAME -D...).
 #ifndef KD_TOPK_WARP_U
-#define KD_TOPK_WARP_U 8  // 16-byte loads per lane and register batch (two batches): 8..16 in flight per lane
+#define KD_TOPK_WARP_U 8
+#endif
+#ifndef KD_TOPK_WARP_PIECE
+#define KD_TOPK_WARP_PIECE kWrPiece
+#endif
+#ifndef KD_TOPK_WARP_MINB
+#define KD_TOPK_WARP_MINB 2
 #endif
 
-template <typename T, int U>
+template <typename T, int U, int PIECE>
 struct Pass1Batch {
   Vec8<T> v[U];
   __device__ __forceinline__ void load(const T* __restrict__ row, int base, int nvec, int lane) {
@@ -788,17 +802,17 @@ struct Pass1Batch {
     }
   }
   __device__ __forceinline__ void reduce(int base, int nvec, int lane, uint16_t* pv, float& m, float& s) {
-    if (base + 32 * U <= nvec) sweep_batch<T, U, true>(v, base, nvec, lane, pv, m, s);
-    else sweep_batch<T, U, false>(v, base, nvec, lane, pv, m, s);
+    if (base + 32 * U <= nvec) sweep_batch<T, U, true, PIECE>(v, base, nvec, lane, pv, m, s);
+    else sweep_batch<T, U, false, PIECE>(v, base, nvec, lane, pv, m, s);
   }
 };
 
-template <typename T, int U>
+template <typename T, int U, int PIECE>
 __device__ __forceinline__ void warp_pass1(const T* __restrict__ row, int V, uint16_t* pv, int lane, float& lm, float& ll) {
   const int nvec = V >> 3;
   constexpr int kStep = 32 * U;
   float m = -CUDART_INF_F, s = 0.f;
-  Pass1Batch<T, U> b0, b1;
+  Pass1Batch<T, U, PIECE> b0, b1;
   b0.load(row, 0, nvec, lane);
 #pragma unroll 1
   for (int base = 0; base < nvec; base += 2 * kStep) {
@@ -823,9 +837,9 @@ __device__ __forceinline__ void warp_pass1(const T* __restrict__ row, int V, uin
   }
   __syncwarp();
   if (lane == 0 && tail0 < V) {
-    const int piece = tail0 / kWrPiece;
-    // the tail opens a new piece when nvec is a multiple of 4, else it joins the last one
-    const float prev = (nvec & 3) ? bf16_bits_to_float(pv[piece]) : -CUDART_INF_F;
+    const int piece = tail0 / PIECE;
+    // the tail opens a new piece when the whole vectors fill their pieces, else it joins the last one
+    const float prev = (nvec % (PIECE / 8)) ? bf16_bits_to_float(pv[piece]) : -CUDART_INF_F;
     pv[piece] = bf16_bits_rd(fmaxf(prev, tmax));
   }
   const float wm = warp_max(m);
@@ -835,23 +849,29 @@ __device__ __forceinline__ void warp_pass1(const T* __restrict__ row, int V, uin
   __syncwarp();
 }
 
+// (Measured and not kept, configs[2] size on one B200: 64-element pieces with 4 loads per batch and three CTAs per SM -
+//  21 - 24 row-warps per SM instead of 16 - 717 us; a per-lane cp.async ring of 12 x 16 bytes in shared memory instead
+//  of the register double buffer 842 us; the configuration below 590 us.  More row-warps lengthen every row in
+//  proportion: the SM's XU / issue / load-path mix is saturated at ~0.11 rows per microsecond either way.)
 template <typename T>
-__global__ void __launch_bounds__(32 * kWrWarps, 2) kd_topk_warp_kernel(const T* __restrict__ logits, int64_t R, int V,
+__global__ void __launch_bounds__(32 * kWrWarps, sizeof(T) == 2 ? KD_TOPK_WARP_MINB : 2) kd_topk_warp_kernel(const T* __restrict__ logits, int64_t R, int V,
                                                                        int64_t row_stride, int k,
                                                                        __half* __restrict__ out_v,
                                                                        int32_t* __restrict__ out_i, int n_pieces_pad) {
   extern __shared__ __align__(16) unsigned char wr_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PIECE = KD_TOPK_WARP_PIECE;
   const WarpRow w = warp_row_smem(wr_smem, warp, n_pieces_pad);
-  const int n_pieces = (V + kWrPiece - 1) / kWrPiece;
+  const int n_pieces = (V + PIECE - 1) / PIECE;
   for (int i = n_pieces + lane; i < n_pieces_pad; i += 32) w.pv[i] = kBf16NegInf;  // padding: never >= a threshold
   __syncwarp();
   const int n_warps = blockDim.x >> 5;  // rows per CTA (warp_form_config)
   for (int64_t r = (int64_t)blockIdx.x * n_warps + warp; r < R; r += (int64_t)gridDim.x * n_warps) {
     const T* row = logits + r * row_stride;
     float lm, ll;
-    warp_pass1<T, (sizeof(T) == 2 ? KD_TOPK_WARP_U : KD_TOPK_WARP_U / 2)>(row, V, w.pv, lane, lm, ll);
-    warp_select_emit<T>(row, V, k, w, n_pieces, n_pieces_pad, lm, ll, r, out_v, out_i, lane);
+    warp_pass1<T, (sizeof(T) == 2 ? KD_TOPK_WARP_U : (KD_TOPK_WARP_U > 2 ? KD_TOPK_WARP_U / 2 : 2)), PIECE>(row, V, w.pv, lane,
+                                                                                                        lm, ll);
+    warp_select_emit<T, PIECE>(row, V, k, w, n_pieces, n_pieces_pad, lm, ll, r, out_v, out_i, lane);
     __syncwarp();
   }
 }
@@ -892,7 +912,7 @@ __global__ void __launch_bounds__(32 * kWrWarps) kd_head_select_kernel(const T* 
     const float lm = warp_max(m);
     const float ll = ln_acc(warp_sum(s * exp_diff(m, lm, kLog2e)));
     __syncwarp();
-    warp_select_emit<T>(row, V, k, w, n_pieces, n_pieces_pad, lm, ll, r, out_v, out_i, lane);
+    warp_select_emit<T, kWrPiece>(row, V, k, w, n_pieces, n_pieces_pad, lm, ll, r, out_v, out_i, lane);
     __syncwarp();
   }
 }
@@ -1052,13 +1072,14 @@ using namespace kd;
 // rounds of 8-warp CTAs, but also 4 rounds of 7-warp CTAs, which finish 1/8 sooner.  `warps` = the rows-per-CTA in
 // [4, 8] that minimises rounds x warps.
 template <typename Kern>
-static bool warp_form_config(Kern kern, int64_t R, int V, int* grid, size_t* smem, int* n_pieces_pad, int* warps) {
-  const int n_pieces = (V + kWrPiece - 1) / kWrPiece;
+static bool warp_form_config(Kern kern, int64_t R, int V, int* grid, size_t* smem, int* n_pieces_pad, int* warps,
+                             int piece = kWrPiece, int max_per_sm = 4) {
+  const int n_pieces = (V + piece - 1) / piece;
   *n_pieces_pad = (n_pieces + 7) & ~7;
   const size_t smem_max = (size_t)kWrWarps * warp_row_bytes(*n_pieces_pad);
   if (smem_max > 226 * 1024 || n_pieces > 65535) return false;  // piece indices are kept as 16-bit values
   int per_sm = (int)((size_t)232448 / (smem_max + 1024));
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > max_per_sm) per_sm = max_per_sm;
   if (per_sm < 1) per_sm = 1;
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
@@ -1125,21 +1146,21 @@ extern "C" int kd_topk_logprobs(const void* logits, int dtype, int64_t R, int V,
     bool launched = false;
     switch (dtype) {
       case KD_DTYPE_F32:
-        if (warp_form_config(kd_topk_warp_kernel<float>, R, V, &grid, &smem, &npp, &nw)) {
+        if (warp_form_config(kd_topk_warp_kernel<float>, R, V, &grid, &smem, &npp, &nw, KD_TOPK_WARP_PIECE, KD_TOPK_WARP_MINB)) {
           kd_topk_warp_kernel<float><<<grid, 32 * nw, smem, s>>>((const float*)logits, R, V, row_stride, k,
                                                                        (__half*)out_v, out_i, npp);
           launched = true;
         }
         break;
       case KD_DTYPE_BF16:
-        if (warp_form_config(kd_topk_warp_kernel<__nv_bfloat16>, R, V, &grid, &smem, &npp, &nw)) {
+        if (warp_form_config(kd_topk_warp_kernel<__nv_bfloat16>, R, V, &grid, &smem, &npp, &nw, KD_TOPK_WARP_PIECE, KD_TOPK_WARP_MINB)) {
           kd_topk_warp_kernel<__nv_bfloat16><<<grid, 32 * nw, smem, s>>>((const __nv_bfloat16*)logits, R, V,
                                                                                row_stride, k, (__half*)out_v, out_i, npp);
           launched = true;
         }
         break;
       case KD_DTYPE_F16:
-        if (warp_form_config(kd_topk_warp_kernel<__half>, R, V, &grid, &smem, &npp, &nw)) {
+        if (warp_form_config(kd_topk_warp_kernel<__half>, R, V, &grid, &smem, &npp, &nw, KD_TOPK_WARP_PIECE, KD_TOPK_WARP_MINB)) {
           kd_topk_warp_kernel<__half><<<grid, 32 * nw, smem, s>>>((const __half*)logits, R, V, row_stride, k,
                                                                         (__half*)out_v, out_i, npp);
           launched = true;
