@@ -5,7 +5,8 @@ the tracked evidence that the hot kernels are tcgen05 / TMEM / TMA code.
 
 Mnemonics (B200_PROFILING.md): UTCHMMA / UTCQMMA = tcgen05.mma (".2CTA" = cta_group::2), LDTM / STTM = tcgen05.ld / st
 (TMEM), UTCBAR = tcgen05.commit, UTMALDG / UTMASTG = TMA tensor load / store (cp.async.bulk.tensor), UBLKCP = cp.async.bulk,
-SYNCS = mbarrier ops, HMMA / IMMA = legacy mma.sync (must be absent from the GEMM kernels).
+SYNCS = mbarrier ops, LDGMC = multimem.ld_reduce (NVLS in-switch reduction), HMMA / IMMA = legacy mma.sync (must be absent
+from the GEMM kernels).
 """
 import collections
 import os
@@ -17,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "speech-distill_b200", "libkd_b200.so")
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UBLKRED", "SYNCS",
        "HMMA", "IMMA", "MUFU.EX2", "MUFU.LG2", "REDUX", "ATOMG", "ATOMS", "RED", "LDG", "STG", "LDS", "STS", "BAR", "MEMBAR",
-       "ELECT", "FENCE", "CCTL", "UCGABAR", "ACQBULK", "CGAERRBAR")
+       "ELECT", "FENCE", "CCTL", "UCGABAR", "ACQBULK", "CGAERRBAR", "LDGMC")
 
 
 def family(name):
