@@ -209,11 +209,16 @@ struct Vec8<__half> {
   }
 };
 
-// Two packed bf16 values with -inf (0xFF80) replaced by the most negative finite bf16 below -1e30: for negative
-// floats the bit pattern grows with the magnitude, positives have a clear sign bit and stay below the bound,
-// so one unsigned 16x2 minimum does it (p = e^{(y - max)/tau} is still exactly 0 for such an entry, and
+// Floor for -inf teacher logits where the unguarded cross term is used.  A POWER OF TWO on purpose: while a thread has
+// seen nothing but floored entries the floor is its running maximum, and the exponent's argument
+// fma(y, c, -(max * log2e) / tau) must then be exactly 0 - with -1e30 the rounding of max * log2e left +-8e22 there,
+// i.e. e^x = inf, and inf * 0 = NaN at the next rescale (a row whose first 16 teacher columns are all -inf).
+constexpr float kTeacherFloor = -0x1p100f;  // -1.27e30
+// Two packed bf16 values with -inf (0xFF80) replaced by the floor (bf16 0xF180): for negative floats the bit pattern
+// grows with the magnitude, positives have a clear sign bit and stay below the bound, so one unsigned 16x2 minimum
+// does it (p = e^{(y - max)/tau} is still exactly 0 for such an entry once a real logit has been seen, and
 // 0 * (y - z) is then 0 instead of NaN - the xlogy convention of nn.KLDivLoss, distillation_loss.py:68).
-__device__ __forceinline__ uint32_t clamp_neg_inf_bf16x2(uint32_t w) { return __vminu2(w, 0xF14AF14Au); }
+__device__ __forceinline__ uint32_t clamp_neg_inf_bf16x2(uint32_t w) { return __vminu2(w, 0xF180F180u); }
 
 // ---- warp helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {
@@ -249,7 +254,9 @@ struct ExpPair {
   }
 };
 
-template <bool TAU2, int N>
+// FSQ (tau == 2 only): the tau = 1 sum takes e^{x-m} = et^2 through one FMA (p1 = et * et + p1) instead of a
+// multiply and an add - one instruction less per element for the issue-bound streaming kernel (K2)
+template <bool TAU2, int N, bool FSQ = false>
 __device__ __forceinline__ void student_update(const float (&f)[N], int nvalid, float inv_tau, float& m, float& s1,
                                                float& st) {
   float vm = -CUDART_INF_F;
@@ -272,7 +279,8 @@ __device__ __forceinline__ void student_update(const float (&f)[N], int nvalid, 
       float et, e1;
       ExpPair<TAU2>::eval(f[i], c_tau, off_tau, off_one, et, e1);
       pt[i & 1] += et;
-      p1[i & 1] += e1;
+      if (TAU2 && FSQ) p1[i & 1] = fmaf(et, et, p1[i & 1]);
+      else p1[i & 1] += e1;
     }
   }
   st += pt[0] + pt[1];
@@ -310,9 +318,9 @@ __device__ __forceinline__ void student_add(const float (&f)[N], int nvalid, flo
 }
 
 // GUARD = true keeps p == 0 terms at exactly 0 even when the student logit is -inf (user-supplied logits,
-// K2).  GUARD = false (fused path: finite student logits, teacher values already clamped to >= -1e30 by the
+// K2).  GUARD = false (fused path: finite student logits, teacher values already clamped to >= kTeacherFloor by the
 // caller, see clamp_neg_inf_bf16x2) runs the cross term as one subtract and one FMA per element.
-template <bool TAU2, int N, bool GUARD = true>
+template <bool TAU2, int N, bool GUARD = true, bool FSQ = false>
 __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float (&fz)[N], int nvalid, float inv_tau,
                                                float& mt, float& t1, float& tt, float& a) {
   float vm = -CUDART_INF_F;
@@ -336,11 +344,12 @@ __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float
       float et, e1;
       ExpPair<TAU2>::eval(fy[i], c_tau, off_tau, off_one, et, e1);
       pt[i & 1] += et;
-      p1[i & 1] += e1;
+      if (TAU2 && FSQ) p1[i & 1] = fmaf(et, et, p1[i & 1]);
+      else p1[i & 1] += e1;
       if (GUARD) {
         // p = 0 contributes exactly 0 (xlogy semantics of nn.KLDivLoss, distillation_loss.py:68);
         // the clamp keeps 0 * (-inf - z) from producing NaN when the teacher holds -inf
-        const float d = fmaxf(fy[i], -1e30f) - fz[i];
+        const float d = fmaxf(fy[i], kTeacherFloor) - fz[i];
         pa[i & 1] = (et > 0.f) ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
       } else {
         pa[i & 1] = fmaf(et, fy[i] - fz[i], pa[i & 1]);

@@ -168,11 +168,11 @@ __device__ __forceinline__ void load_row16(const TY* __restrict__ p, bool vec_ok
       float t8[8];
       v.unpack(t8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[8 * q + j] = fmaxf(t8[j], -1e30f);  // -inf teacher entries: see teacher_update
+      for (int j = 0; j < 8; ++j) f[8 * q + j] = fmaxf(t8[j], kTeacherFloor);  // -inf teacher entries: see teacher_update
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = j < ncols ? fmaxf(Elem<TY>::to_f(p[j]), -1e30f) : -CUDART_INF_F;
+    for (int j = 0; j < 16; ++j) f[j] = j < ncols ? fmaxf(Elem<TY>::to_f(p[j]), kTeacherFloor) : -CUDART_INF_F;
   }
 }
 
@@ -943,7 +943,7 @@ __device__ __noinline__ void gc_piece_slow(const GradCachedParams& p, const GcRo
   if (DENSE) {
     const TY* yrow = reinterpret_cast<const TY*>(p.y) + (int64_t)row * p.y_stride + col;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) fy[i] = i < nrem ? fmaxf(Elem<TY>::to_f(yrow[i]), -1e30f) : -CUDART_INF_F;
+    for (int i = 0; i < 8; ++i) fy[i] = i < nrem ? fmaxf(Elem<TY>::to_f(yrow[i]), kTeacherFloor) : -CUDART_INF_F;
   }
   *reinterpret_cast<uint4*>(grow + j) = gc_piece8<TY, DENSE, TAU2, SPARSE>(p, r, row, col, nrem, zv, ref, fy);
 }
@@ -1025,7 +1025,7 @@ __global__ void __maxnreg__(kGcMaxRegs) kd_grad_cached_kernel(const __grid_const
             } else {
               yv[u].unpack(fy);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) fy[i] = fmaxf(fy[i], -1e30f);
+              for (int i = 0; i < 8; ++i) fy[i] = fmaxf(fy[i], kTeacherFloor);
             }
           }
           *reinterpret_cast<uint4*>(gp + u * 256) =

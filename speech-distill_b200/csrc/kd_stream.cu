@@ -36,6 +36,8 @@ struct StreamParams {
   void* dlogits;
   float* partials;  // [CTAs][kNumPartialSlots]
   int vec_ok;       // 16-byte vector path legal for every row pointer
+  int n_stash;      // dense + gradient: leading register sets of a row kept in shared memory for sweep 2
+  int l2_ahead;     // sweep 1: thread 0 asks the L2 for the row's bytes this many sets ahead of the loads (0 = off)
 };
 
 struct Stats7 {
@@ -73,6 +75,13 @@ __device__ __forceinline__ Stats7 warp_merge(Stats7 s, float inv_tau) {
 // ------------------------------------------------------------------------------------------
 constexpr int kRowThreadsMax = 1024;
 
+// one instruction brings a contiguous range of global memory into L2 (no registers, no shared memory, no completion to
+// wait for); `bytes` is a multiple of 16
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy)
+               : "memory");
+}
+
 struct RowShared {
   Stats7 warp_stats[kRowThreadsMax / 32];
   Stats7 row_stats;
@@ -86,7 +95,16 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
   __shared__ RowShared sh;
   float* sp_p = reinterpret_cast<float*>(dyn_smem);  // sparse teacher only: p_k and i_k of the current row
   int32_t* sp_i = reinterpret_cast<int32_t*>(sp_p + p.K);
+  // dense teacher with gradient: the first n_stash register sets of a row (set = the 4 pieces one thread holds: 2 of z,
+  // 2 of y) are kept in shared memory by the thread that loaded them, so that sweep 2 reads them back from there and
+  // only the rest of the row has to stay in L2: 148 rows x 612 KB = 90 MB of evict_last lines do not fit one 63 MB L2
+  // partition (ncu: 24 % of sweep 2's sectors missed, 0.6 GB of extra DRAM reads at the configs[1] shape)
+  constexpr bool kStash = DENSE && GRAD;
+  constexpr int kSetBytes = kRowThreads * 2 * (int)(sizeof(Vec8<TZ>) + sizeof(Vec8<TY>));
+  const int n_stash = kStash ? p.n_stash : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint8_t* const stash_z = dyn_smem + (size_t)tid * sizeof(Vec8<TZ>);
+  uint8_t* const stash_y = dyn_smem + (size_t)kRowThreads * 2 * sizeof(Vec8<TZ>) + (size_t)tid * sizeof(Vec8<TY>);
   const float inv_tau = 1.0f / p.tau;
   const int V = p.V;
   const bool vec_ok = p.vec_ok != 0;
@@ -137,10 +155,10 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
     s.m = s.mt = -CUDART_INF_F;
     s.s1 = s.st = s.t1 = s.tt = s.a = 0.f;
     {
-      // thread `tid` takes pieces tid, tid + T, ... in pairs (q, q + kRowThreads); the pair after next is loaded
-      // before the current one is reduced
-      Vec8<TZ> z0, z1, nz0, nz1;
-      Vec8<TY> y0, y1, ny0, ny1;
+      // thread `tid` takes pieces tid, tid + T, ... in pairs (q, q + kRowThreads); in the fast loop the next pair is
+      // loaded before the current one is reduced
+      Vec8<TZ> z0, z1;
+      Vec8<TY> y0, y1;
       int q = tid;
       auto load_pair = [&](int qq, Vec8<TZ>& a, Vec8<TZ>& bb, Vec8<TY>& c, Vec8<TY>& d) {
         if (qq < nvec) {
@@ -152,9 +170,102 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
           if (DENSE) d.load_global_hint(yrow + (size_t)(qq + kRowThreads) * 8, pol_keep);
         }
       };
-      load_pair(q, z0, z1, y0, y1);
-      for (; q < nvec; q += 2 * kRowThreads) {
-        load_pair(q + 2 * kRowThreads, nz0, nz1, ny0, ny1);
+      // Fast loop (ncu: the kernel issues 38 instructions per element at 61 % issue and 56 % XU utilisation with DRAM
+      // at 48 % - it is bound by instruction issue, 2.8 of them register copies of the prefetch and ~6 predicates and
+      // addressing): whole pairs only, two register sets that alternate instead of being copied, no predicates, the
+      // teacher's -inf clamped on the packed words so that the cross term needs no per-element guard.
+      {
+        struct Set {
+          Vec8<TZ> z0, z1;
+          Vec8<TY> y0, y1;
+        };
+        // sets below n_stash go to shared memory as well (thread-private slots: no barrier) and are not kept in L2
+        auto load_full = [&](Set& p, int qq, int i) {
+          const uint64_t pol = (kStash && i < n_stash) ? pol_drop : pol_keep;
+          p.z0.load_global_hint(zrow + (size_t)qq * 8, pol);
+          p.z1.load_global_hint(zrow + (size_t)(qq + kRowThreads) * 8, pol);
+          if (DENSE) {
+            p.y0.load_global_hint(yrow + (size_t)qq * 8, pol);
+            p.y1.load_global_hint(yrow + (size_t)(qq + kRowThreads) * 8, pol);
+          }
+        };
+        auto reduce16 = [&](Set& p, int i) {
+          if (kStash && i < n_stash) {
+            uint8_t* sz = stash_z + (size_t)i * kSetBytes;
+            uint8_t* sy = stash_y + (size_t)i * kSetBytes;
+            p.z0.store_shared(reinterpret_cast<TZ*>(sz));
+            p.z1.store_shared(reinterpret_cast<TZ*>(sz + kRowThreads * sizeof(Vec8<TZ>)));
+            p.y0.store_shared(reinterpret_cast<TY*>(sy));
+            p.y1.store_shared(reinterpret_cast<TY*>(sy + kRowThreads * sizeof(Vec8<TY>)));
+          }
+          float fz[16], fy[16], t8[8];
+          p.z0.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fz[j] = t8[j];
+          p.z1.unpack(t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) fz[8 + j] = t8[j];
+          student_update<TAU2, 16, DENSE>(fz, 16, inv_tau, s.m, s.s1, s.st);
+          if (DENSE) {
+            constexpr bool kPacked = std::is_same<TY, __nv_bfloat16>::value;  // -inf -> most negative finite, 2 per op
+            if (kPacked) {
+              p.y0.a.x = clamp_neg_inf_bf16x2(p.y0.a.x); p.y0.a.y = clamp_neg_inf_bf16x2(p.y0.a.y);
+              p.y0.a.z = clamp_neg_inf_bf16x2(p.y0.a.z); p.y0.a.w = clamp_neg_inf_bf16x2(p.y0.a.w);
+              p.y1.a.x = clamp_neg_inf_bf16x2(p.y1.a.x); p.y1.a.y = clamp_neg_inf_bf16x2(p.y1.a.y);
+              p.y1.a.z = clamp_neg_inf_bf16x2(p.y1.a.z); p.y1.a.w = clamp_neg_inf_bf16x2(p.y1.a.w);
+            }
+            p.y0.unpack(t8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fy[j] = t8[j];
+            p.y1.unpack(t8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fy[8 + j] = t8[j];
+            // a finite student logit is all the unguarded cross term needs once the teacher is clamped; a student
+            // -inf gives inf / NaN here as it does in the reference (kl_div of a -inf log-probability)
+            teacher_update<TAU2, 16, !kPacked, true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
+          }
+        };
+        // L2 prefetch: the loads of a set leave when the previous set is being reduced, i.e. 64 bytes per thread = 32 KB
+        // per SM are on their way to registers at any time, and ncu puts 14 % of all warp samples on the first use
+        // of a sweep-1 load.  Thread 0 therefore asks the L2 for sets l2_ahead .. ahead of the loads (16 KB of z and
+        // of y per instruction): the register loads then find their lines in L2, whatever DRAM's latency is.
+        // (Gradient launches only: the forward-only form - two 256-thread CTAs per SM - measured 3 % slower with it;
+        // asking for the head of a row that will be drawn a few microseconds later changed nothing either way.)
+        constexpr bool kL2Fetch = GRAD;
+        const int l2_ahead = kL2Fetch ? p.l2_ahead : 0;
+        auto l2_fetch_set = [&](int i) {
+          const int first = i * 2 * kRowThreads;  // first 16-byte piece of set i
+          if (first >= nvec) return;
+          const int n = nvec - first < 2 * kRowThreads ? nvec - first : 2 * kRowThreads;
+          const uint64_t pol = (kStash && i < n_stash) ? pol_drop : pol_keep;
+          l2_prefetch_bulk(zrow + (size_t)first * 8, (uint32_t)n * (uint32_t)sizeof(Vec8<TZ>), pol);
+          if (DENSE) l2_prefetch_bulk(yrow + (size_t)first * 8, (uint32_t)n * (uint32_t)sizeof(Vec8<TY>), pol);
+        };
+        if (kL2Fetch && tid == 0 && l2_ahead > 0) {
+          for (int i = 1; i <= l2_ahead; ++i) l2_fetch_set(i);  // set 0 is being loaded right now
+        }
+        if (q + kRowThreads < nvec) {
+          Set a, b;
+          int si = 0;  // set index of `a`: set i holds pieces q = tid + 2 i S and q + S
+          load_full(a, q, 0);
+          while (q + 5 * kRowThreads < nvec) {  // pairs q, q + 2S and q + 4S lie inside the row
+            if (kL2Fetch && tid == 0 && l2_ahead > 0) {
+              l2_fetch_set(si + l2_ahead + 1);
+              l2_fetch_set(si + l2_ahead + 2);
+            }
+            load_full(b, q + 2 * kRowThreads, si + 1);
+            reduce16(a, si);
+            load_full(a, q + 4 * kRowThreads, si + 2);
+            reduce16(b, si + 1);
+            q += 4 * kRowThreads;
+            si += 2;
+          }
+          reduce16(a, si);
+          q += 2 * kRowThreads;
+        }
+      }
+      for (; q < nvec; q += 2 * kRowThreads) {  // what the fast loop left: at most two pairs, possibly partial
+        load_pair(q, z0, z1, y0, y1);
         float fz[16], fy[16];
         const bool two = q + kRowThreads < nvec;
         {
@@ -185,8 +296,6 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
           student_update<TAU2, 16>(fz, 8, inv_tau, s.m, s.s1, s.st);
           if (DENSE) teacher_update<TAU2, 16>(fy, fz, 8, inv_tau, s.mt, s.t1, s.tt, s.a);
         }
-        z0 = nz0; z1 = nz1;
-        if (DENSE) { y0 = ny0; y1 = ny1; }
       }
       for (int i = nvec * 8 + tid; i < V; i += kRowThreads) {  // scalar tail / unaligned rows
         float fz[8], fy[8];
@@ -308,8 +417,8 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
         }
       };
       {
-        Vec8<TZ> z0, z1, nz0, nz1;
-        Vec8<TY> y0, y1, ny0, ny1;
+        Vec8<TZ> z0, z1;
+        Vec8<TY> y0, y1;
         int q = tid;
         auto load_pair = [&](int qq, Vec8<TZ>& a, Vec8<TZ>& bb, Vec8<TY>& c, Vec8<TY>& d) {
           if (qq < nvec) {
@@ -321,9 +430,60 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
             if (DENSE) d.load_global_hint(yrow + (size_t)(qq + kRowThreads) * 8, pol_drop);
           }
         };
-        load_pair(q, z0, z1, y0, y1);
-        for (; q < nvec; q += 2 * kRowThreads) {
-          load_pair(q + 2 * kRowThreads, nz0, nz1, ny0, ny1);
+        {  // fast loop: whole pairs, alternating register sets, no predicates (see sweep 1)
+          struct Set {
+            Vec8<TZ> z0, z1;
+            Vec8<TY> y0, y1;
+          };
+          auto load_full = [&](Set& p, int qq, int i) {
+            if (kStash && i < n_stash) {  // this thread's own copy from sweep 1 (CTA-uniform branch)
+              const uint8_t* sz = stash_z + (size_t)i * kSetBytes;
+              const uint8_t* sy = stash_y + (size_t)i * kSetBytes;
+              p.z0.load_shared(reinterpret_cast<const TZ*>(sz));
+              p.z1.load_shared(reinterpret_cast<const TZ*>(sz + kRowThreads * sizeof(Vec8<TZ>)));
+              p.y0.load_shared(reinterpret_cast<const TY*>(sy));
+              p.y1.load_shared(reinterpret_cast<const TY*>(sy + kRowThreads * sizeof(Vec8<TY>)));
+              return;
+            }
+            p.z0.load_global_hint(zrow + (size_t)qq * 8, pol_drop);
+            p.z1.load_global_hint(zrow + (size_t)(qq + kRowThreads) * 8, pol_drop);
+            if (DENSE) {
+              p.y0.load_global_hint(yrow + (size_t)qq * 8, pol_drop);
+              p.y1.load_global_hint(yrow + (size_t)(qq + kRowThreads) * 8, pol_drop);
+            }
+          };
+          auto emit = [&](const Set& p, int qq) {
+            float fz[8], fy[8], g[8];
+            Vec8<TZ> vo;
+            p.z0.unpack(fz);
+            if (DENSE) p.y0.unpack(fy);
+            grad8(fz, fy, qq * 8, 8, g);
+            vo.pack(g);
+            vo.store_global(out_row + (size_t)qq * 8);
+            p.z1.unpack(fz);
+            if (DENSE) p.y1.unpack(fy);
+            grad8(fz, fy, (qq + kRowThreads) * 8, 8, g);
+            vo.pack(g);
+            vo.store_global(out_row + (size_t)(qq + kRowThreads) * 8);
+          };
+          if (q + kRowThreads < nvec) {  // the same control flow as sweep 1: the stashed sets are the same ones
+            Set a, b;
+            int si = 0;
+            load_full(a, q, 0);
+            while (q + 5 * kRowThreads < nvec) {
+              load_full(b, q + 2 * kRowThreads, si + 1);
+              emit(a, q);
+              load_full(a, q + 4 * kRowThreads, si + 2);
+              emit(b, q + 2 * kRowThreads);
+              q += 4 * kRowThreads;
+              si += 2;
+            }
+            emit(a, q);
+            q += 2 * kRowThreads;
+          }
+        }
+        for (; q < nvec; q += 2 * kRowThreads) {  // the remainder: at most two pairs, possibly partial
+          load_pair(q, z0, z1, y0, y1);
           float fz[8], fy[8], g[8];
           z0.unpack(fz);
           if (DENSE) y0.unpack(fy);
@@ -338,8 +498,6 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
             vo.pack(g);
             vo.store_global(out_row + (size_t)(q + kRowThreads) * 8);
           }
-          z0 = nz0; z1 = nz1;
-          if (DENSE) { y0 = ny0; y1 = ny1; }
         }
         for (int i = nvec * 8 + tid; i < V; i += kRowThreads) {
           float fz[8], fy[8], g[8];
@@ -490,35 +648,19 @@ __global__ void kd_zero_rows_kernel(T* __restrict__ x, int64_t n) {
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxClusters = 1024;
 
-static int stream_row_threads() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("KD_STREAM_THREADS");
-    v = e ? atoi(e) : 512;  // measured: 512 (126 registers, no spills) > 768 > 1024 (64 registers, spills)
-    if (v != 1024 && v != 768 && v != 256) v = 512;
-  }
-  return v;
-}
-
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
 static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream, int ctas_per_sm = 1);
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD>
 static int launch_stream_rows(const StreamParams& p0, cudaStream_t stream) {
-  // KD_STREAM_THREADS = 768 / 1024: experiment knob, headline instantiation only
-  if (std::is_same<TZ, __nv_bfloat16>::value && std::is_same<TY, __nv_bfloat16>::value && DENSE && TAU2) {
-    const int t = stream_row_threads();
-    if (t == 1024) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 1024>(p0, stream);
-    if (t == 768) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 768>(p0, stream);
-    if (t == 256) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 256>(p0, stream);
-  }
-  // dense: 512 threads x 126 registers hold two row pieces of z and y in flight per thread without spilling;
-  // the top-k form has no teacher stream and is faster with 1024 x 64 (measured: 726 vs 862 us at configs[1] shape)
-  // forward only (no second sweep, nothing to keep in L2): two 256-thread CTAs per SM overlap one row's block
-  // reduction with the other's streaming (measured 551 vs 604 us at the configs[1] shape)
-  if (DENSE && !GRAD) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 256>(p0, stream, 2);
-  if (DENSE) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 512>(p0, stream);
-  return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 1024>(p0, stream);
+  // dense with gradient: 512 threads x 128 registers hold two sets of z and y per thread, one CTA per SM (the stash
+  // takes the shared memory); the top-k form has no teacher stream and is faster with 1024 x 64 (measured: 726 vs
+  // 862 us at configs[1] shape); forward only (no second sweep, nothing to keep in L2): two 256-thread CTAs per SM
+  // overlap one row's block reduction with the other's streaming (measured 551 vs 604 us at the configs[1] shape).
+  // (768 and 1024 threads for the dense form measured slower: fewer registers per thread, spills.)
+  if constexpr (DENSE && !GRAD) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 256>(p0, stream, 2);
+  else if constexpr (DENSE) return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 512>(p0, stream);
+  else return launch_stream_rows_t<TZ, TY, DENSE, TAU2, GRAD, 1024>(p0, stream);
 }
 
 template <typename TZ, typename TY, bool DENSE, bool TAU2, bool GRAD, int kRowThreads>
@@ -540,7 +682,47 @@ static int launch_stream_rows_t(const StreamParams& p0, cudaStream_t stream, int
   // the row counter sits behind the reduced record in the workspace
   int* counter = reinterpret_cast<int*>(p.partials + (size_t)(kMaxClusters + 1) * kNumPartialSlots);
   if (check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), stream), "row counter")) return 1;
-  const size_t dyn = DENSE ? 0 : (size_t)p.K * 8;
+  size_t dyn = DENSE ? 0 : (size_t)p.K * 8;
+  p.n_stash = 0;
+  {
+    static int ahead_env = -2;  // KD_STREAM_L2_AHEAD = sets (0 = no L2 prefetch)
+    if (ahead_env == -2) {
+      const char* e = getenv("KD_STREAM_L2_AHEAD");
+      ahead_env = e ? atoi(e) : 3;
+      if (ahead_env < 0 || ahead_env > 16) ahead_env = 3;
+    }
+    p.l2_ahead = p.vec_ok ? ahead_env : 0;
+  }
+  if (DENSE && GRAD && p.vec_ok) {
+    // shared-memory stash of the leading sets of every row (see the kernel): as many as fit beside the static part;
+    // KD_STREAM_STASH = n caps it (0 = every sweep-2 read comes from L2, the round-2 form; -1 = as many as fit)
+    static int stash_env = -2;
+    if (stash_env == -2) {
+      const char* e = getenv("KD_STREAM_STASH");
+      stash_env = e ? atoi(e) : 4;  // measured at the configs[1] shape: 4 sets 1021 us, 7 sets (all that fit) 1042, none 1095
+    }
+    static int max_dyn[kMaxDevices] = {};  // per instantiation and device
+    const int slot = current_device_slot();
+    if (max_dyn[slot] == 0) {
+      cudaFuncAttributes fa;
+      int optin = 0;
+      if (check_cuda(cudaFuncGetAttributes(&fa, kern), "kd_stream_row attributes")) return 1;
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, slot);
+      int avail = (per_sm > 1 ? (optin + 1024) / per_sm - 1024 : optin) - (int)fa.sharedSizeBytes;
+      if (avail < 0) avail = 0;
+      if (avail > 48 * 1024 &&
+          check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, avail), "kd_stream_row smem"))
+        return 1;
+      max_dyn[slot] = avail > 0 ? avail : -1;
+    }
+    const int set_bytes = kRowThreads * 2 * (int)(sizeof(Vec8<TZ>) + sizeof(Vec8<TY>));
+    int n = max_dyn[slot] > 0 ? max_dyn[slot] / set_bytes : 0;
+    const int whole_sets = (p.V / 8) / (2 * kRowThreads);
+    if (n > whole_sets) n = whole_sets;
+    if (stash_env >= 0 && n > stash_env) n = stash_env;
+    p.n_stash = n;
+    dyn = (size_t)n * set_bytes;
+  }
   kern<<<grid, kRowThreads, dyn, stream>>>(p, counter);
   if (check_launch("kd_stream_row launch")) return 1;
   return reduce_partials(p.partials, grid, p0.partials + (size_t)kMaxClusters * kNumPartialSlots, stream);

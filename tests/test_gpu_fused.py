@@ -142,6 +142,27 @@ def test_fused_matches_oracle(B, T, H, V, tau, alpha, y_dtype):
     assert eh <= max(eh_ref, 2.0 ** -9) and ew <= max(ew_ref, 2.0 ** -9), (eh, eh_ref, ew, ew_ref)
 
 
+@pytest.mark.parametrize("y_dtype", [torch.bfloat16, torch.float32])
+def test_fused_teacher_with_blocks_of_minus_inf(y_dtype):
+    """A teacher that masks whole vocabulary ranges with -inf (p = 0 there: xlogy semantics of nn.KLDivLoss,
+    distillation_loss.py:68).  The first columns of a row being all -inf is the case where a thread's running
+    teacher maximum starts out as the floor value."""
+    B, T, H, V = 2, 96, 128, 3000
+    h, W, y, labels = _case(13, B, T, H, V, y_dtype)
+    y[:, ::3, :700] = float("-inf")        # whole leading tiles of every third row
+    y[:, 1::3, 1000:1016] = float("-inf")  # one 16-column group
+    y[:, :, 2990:] = float("-inf")         # ragged tail
+    labels[labels >= 0] = labels[labels >= 0] % 250 + 720  # teacher monitor: never a -inf column
+    ref, gh_ref, gw_ref = O.fused_linear_reference(h.double(), W.double(), labels, teacher_logits=y.double(),
+                                                   temperature=2.0, alpha=0.5)
+    losses, gh, gw = _run_fused(h, W, y, labels, 2.0, 0.5)
+    assert all(np.isfinite(losses)), losses
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
+        assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
+    assert rel_err(gh.float().cpu().numpy(), gh_ref.numpy()) < 4e-3
+    assert rel_err(gw.float().cpu().numpy(), gw_ref.numpy()) < 4e-3
+
+
 def test_fused_equals_streaming_path():
     """K1 (no logits) and K2 (materialised logits) are two routes to the same numbers."""
     import speech_distill_b200 as K

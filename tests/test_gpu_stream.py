@@ -125,6 +125,42 @@ def test_sparse_matches_oracle(B, T, V, dtype, K, tau):
     assert rel_err(grad.float().cpu().numpy(), gref.numpy()) < tol
 
 
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense", "topk"])
+def test_many_rows_per_cta_through_the_ring(sparse):
+    """More scored rows than CTAs and several ring turns per row: every CTA re-fills the shared-memory stash and the
+    ring slots across rows (dense: 512-thread sets of 8192 logits, top-k: 1024-thread sets of 16384), with ignored
+    rows, a partial last set and -inf teacher entries in between."""
+    B, T, V, K = 4, 121, 8192 * 9 + 8 * 700, 32
+    g = torch.Generator().manual_seed(5)
+    z = (torch.randn(B, T, V, generator=g) * 2).bfloat16()
+    y = (torch.randn(B, T, V, generator=g) * 2).bfloat16()
+    y[:, ::7, 100:9000] = float("-inf")
+    labels = torch.randint(9000, V, (B, T), generator=g)  # never a -inf teacher column: the monitor CE stays finite
+    labels[:, 5::11] = -100
+    kw_ref, kw = {}, {}
+    if sparse:
+        v, i = torch.topk(torch.log_softmax(y.float(), -1), K, -1)
+        kw_ref = dict(teacher_top_k_v=v.half(), teacher_top_k_i=i.int())
+        kw = dict(teacher_top_k_v=v.half().cuda(), teacher_top_k_i=i.int().cuda())
+    else:
+        kw_ref = dict(teacher_logits=y.float())
+        kw = dict(teacher_logits=y.cuda())
+    ref, gref = O.reference_loss_and_grad(z.float(), labels, temperature=2.0, alpha=0.5, **kw_ref)
+    losses, grad = run_ours(z.cuda(), labels.cuda(), temperature=2.0, alpha=0.5, **kw)
+    for got, want in zip(losses, [float(x.detach()) for x in ref]):
+        assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (losses, ref)
+    assert rel_err(grad.float().cpu().numpy(), gref.numpy()) < 5e-3
+    # per-row check (a swapped or stale slot would hide in a global maximum): every row's gradient within bf16 rounding
+    d = (grad.float().cpu() - gref).abs().amax(-1)
+    scale = gref.abs().amax(-1).clamp_min(1e-12)
+    assert float((d / scale).max()) < 8e-3
+    import speech_distill_b200 as K2
+    with torch.no_grad():
+        fwd = K2.kd_loss_on_logits(z.cuda(), labels.cuda(), temperature=2.0, alpha=0.5, **kw)
+    for got, want in zip([float(o) for o in fwd], losses):
+        assert abs(got - want) <= 1e-5 * max(1.0, abs(want))
+
+
 def test_sparse_duplicate_indices_accumulate():
     c = _random_case(77, 1, 6, 512, torch.float32, K=8, mask=False)
     c["i"][..., 3] = c["i"][..., 1]  # duplicate index inside a row: gather backward adds both
