@@ -83,6 +83,8 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes
 }
 
 struct RowShared {
+  double acc_ce, acc_kl, acc_t;  // the CTA's sums over its rows: thread 0 alone reads and writes them, once per row
+  int acc_n, acc_hits;           // (in registers they were 8 live values per thread through both sweeps)
   Stats7 warp_stats[kRowThreadsMax / 32];
   Stats7 row_stats;
   float sp_lk;
@@ -117,8 +119,10 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
   }
   const float c1 = p.alpha * norm;
   const float c2 = (1.f - p.alpha) * p.tau * norm;
-  double acc_ce = 0.0, acc_kl = 0.0, acc_t = 0.0;
-  int acc_n = 0, acc_hits = 0;
+  if (tid == 0) {
+    sh.acc_ce = sh.acc_kl = sh.acc_t = 0.0;
+    sh.acc_n = sh.acc_hits = 0;
+  }
   // sweep 1 keeps the row's lines in L2 (evict_last) only when a second sweep will read them
   const uint64_t pol_keep = GRAD ? l2_policy_evict_last() : l2_policy_evict_first();
   const uint64_t pol_drop = l2_policy_evict_first();
@@ -352,10 +356,10 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
         // out of bounds: NaN is loud and needs no host sync
         const float zl = target < p.V ? Elem<TZ>::to_f(zrow[target]) : CUDART_NAN_F;
         const float yl = target < p.V ? Elem<TY>::to_f(yrow[target]) : CUDART_NAN_F;
-        acc_ce += (double)(lse1 - zl);
-        acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
-        acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
-        acc_n += 1;
+        sh.acc_ce += (double)(lse1 - zl);
+        sh.acc_kl += (double)(f.a * inv_tau / f.tt - lsett + lset);
+        sh.acc_t += (double)((f.mt + ln_acc(f.t1)) - yl);
+        sh.acc_n += 1;
       }
     } else if (warp == 0) {
       // KL_r = sum_k p_k (log p_k - z_{i_k}/tau) + LSE_tau ; monitor hits (distillation_loss.py:104-116)
@@ -380,11 +384,11 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
       hits = __reduce_add_sync(0xffffffffu, hits);
       if (lane == 0) {
         const float zl = target < p.V ? Elem<TZ>::to_f(zrow[target]) : CUDART_NAN_F;
-        acc_ce += (double)(lse1 - zl);
-        acc_kl += (double)(part + lset);
-        acc_t += (double)hsum;
-        acc_hits += hits;
-        acc_n += 1;
+        sh.acc_ce += (double)(lse1 - zl);
+        sh.acc_kl += (double)(part + lset);
+        sh.acc_t += (double)hsum;
+        sh.acc_hits += hits;
+        sh.acc_n += 1;
       }
     }
 
@@ -534,11 +538,11 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
   }
   if (tid == 0) {
     float* out = p.partials + (size_t)blockIdx.x * kNumPartialSlots;
-    out[0] = (float)acc_ce;
-    out[1] = (float)acc_kl;
-    out[2] = (float)acc_t;
-    out[3] = (float)acc_n;
-    out[4] = (float)acc_hits;
+    out[0] = (float)sh.acc_ce;
+    out[1] = (float)sh.acc_kl;
+    out[2] = (float)sh.acc_t;
+    out[3] = (float)sh.acc_n;
+    out[4] = (float)sh.acc_hits;
     out[5] = out[6] = out[7] = 0.f;
   }
 }
