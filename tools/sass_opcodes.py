@@ -4,7 +4,7 @@ the tracked evidence that the hot kernels are tcgen05 / TMEM / TMA code.
     python tools/sass_opcodes.py > profiles/sass_opcodes.txt
 
 Mnemonics (B200_PROFILING.md): UTCHMMA / UTCQMMA = tcgen05.mma (".2CTA" = cta_group::2), LDTM / STTM = tcgen05.ld / st
-(TMEM), UTCBAR = tcgen05.commit, UTMALDG / UTMASTG = TMA tensor load / store (cp.async.bulk.tensor), UBLKCP = cp.async.bulk,
+(TMEM), UTCBAR = tcgen05.commit, UTMALDG / UTMASTG = TMA tensor load / store (cp.async.bulk.tensor), UBLKCP = cp.async.bulk, UBLKPF = cp.async.bulk.prefetch.L2,
 SYNCS = mbarrier ops, LDGMC = multimem.ld_reduce (NVLS in-switch reduction), HMMA / IMMA = legacy mma.sync (must be absent
 from the GEMM kernels).
 """
@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "speech-distill_b200", "libkd_b200.so")
-KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UBLKRED", "SYNCS",
+KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UBLKPF", "UBLKRED", "SYNCS",
        "HMMA", "IMMA", "MUFU.EX2", "MUFU.LG2", "REDUX", "ATOMG", "ATOMS", "RED", "LDG", "STG", "LDS", "STS", "BAR", "MEMBAR",
        "ELECT", "FENCE", "CCTL", "UCGABAR", "ACQBULK", "CGAERRBAR", "LDGMC")
 
