@@ -224,9 +224,19 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
             p.y1.unpack(t8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) fy[8 + j] = t8[j];
-            // a finite student logit is all the unguarded cross term needs once the teacher is clamped; a student
-            // -inf gives inf / NaN here as it does in the reference (kl_div of a -inf log-probability)
-            teacher_update<TAU2, 16, !kPacked, true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
+            // The unguarded cross term (one subtract and one FMA per element) needs finite student logits once the
+            // teacher is clamped: a -inf (or NaN) student logit in the group - the largest unsigned 16-bit patterns,
+            // found with 7 packed maxima - sends the group through the guarded form, which keeps p = 0 entries at
+            // exactly 0 (logits masked with -inf on both sides) and gives inf where the reference does.
+            constexpr bool kFast = kPacked && std::is_same<TZ, __nv_bfloat16>::value;
+            bool plain = kFast;
+            if (kFast) {
+              const uint32_t u0 = __vmaxu2(__vmaxu2(p.z0.a.x, p.z0.a.y), __vmaxu2(p.z0.a.z, p.z0.a.w));
+              const uint32_t u1 = __vmaxu2(__vmaxu2(p.z1.a.x, p.z1.a.y), __vmaxu2(p.z1.a.z, p.z1.a.w));
+              plain = __vcmpgeu2(__vmaxu2(u0, u1), 0xFF80FF80u) == 0;
+            }
+            if (plain) teacher_update<TAU2, 16, false, true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
+            else teacher_update<TAU2, 16, true, true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
           }
         };
         // L2 prefetch: the loads of a set leave when the previous set is being reduced, i.e. 64 bytes per thread = 32 KB

@@ -222,6 +222,32 @@ def test_teacher_with_minus_inf_and_fill():
     assert rel_err(grad.cpu().numpy(), gref.numpy()) < 2e-5
 
 
+def test_student_logits_masked_with_minus_inf():
+    """bf16 hot loop (V large enough for whole register sets).  A vocabulary range masked with -inf on BOTH sides
+    counts as absent (p = 0 terms stay exactly 0: the same numbers as the reference on the remaining columns; the
+    reference itself returns NaN here, 0 * inf inside kl_div); a -inf student logit where the teacher has mass gives an
+    infinite KL, as the reference does."""
+    B, T, V = 1, 7, 20000
+    c = _random_case(21, B, T, V, torch.bfloat16, mask=False)
+    c["labels"].clamp_(max=9999)
+    z, y = c["z"].clone(), c["y"].clone()
+    z[..., 10000:14000] = float("-inf")
+    y[..., 10000:14000] = float("-inf")
+    keep = torch.ones(V, dtype=torch.bool)
+    keep[10000:14000] = False
+    ref, gref = O.reference_loss_and_grad(z[..., keep].float(), c["labels"], teacher_logits=y[..., keep].float())
+    losses, grad = run_ours(z.cuda(), c["labels"].cuda(), teacher_logits=y.cuda())
+    np.testing.assert_allclose(losses, [float(x.detach()) for x in ref], rtol=1e-3)
+    g = grad.float().cpu()
+    assert float(g[..., ~keep].abs().max()) == 0.0
+    assert rel_err(g[..., keep].numpy(), gref.numpy()) < 5e-3
+    y2 = c["y"].clone()  # teacher mass on columns the student excludes
+    ref2 = O.reference_loss(z.float(), c["labels"], teacher_logits=y2.float())
+    losses2, _ = run_ours(z.cuda(), c["labels"].cuda(), teacher_logits=y2.cuda())
+    assert float(ref2[2]) == float("inf") and losses2[2] == float("inf")
+    assert abs(losses2[1] - float(ref2[1])) <= 1e-3 * float(ref2[1])
+
+
 def test_linearity_property_full_size():
     """Size-independent property at BASELINE's V: the sums record is additive over row shards."""
     import speech_distill_b200 as K
