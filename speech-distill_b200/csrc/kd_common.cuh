@@ -317,10 +317,13 @@ __device__ __forceinline__ void student_add(const float (&f)[N], int nvalid, flo
   s1 += p1[0] + p1[1];
 }
 
-// GUARD = true keeps p == 0 terms at exactly 0 even when the student logit is -inf (user-supplied logits,
-// K2).  GUARD = false (fused path: finite student logits, teacher values already clamped to >= kTeacherFloor by the
-// caller, see clamp_neg_inf_bf16x2) runs the cross term as one subtract and one FMA per element.
-template <bool TAU2, int N, bool GUARD = true, bool FSQ = false>
+// GUARD = 1 keeps p == 0 terms at exactly 0 whatever the student logit is (K1's ragged vocabulary edge: the padding
+// columns hold -inf on both sides).  GUARD = 2 (K2, user-supplied logits) does so for finite student logits only: a
+// -inf student logit contributes what it does in the reference - inf where the teacher has mass, NaN (0 * inf inside
+// kl_div) where it has none.  GUARD = 0 (fused path and K2's hot loop: teacher values already clamped to >=
+// kTeacherFloor by the caller, see clamp_neg_inf_bf16x2) runs the cross term as one subtract and one FMA per element,
+// with the same results as GUARD = 2.
+template <bool TAU2, int N, int GUARD = 1, bool FSQ = false>
 __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float (&fz)[N], int nvalid, float inv_tau,
                                                float& mt, float& t1, float& tt, float& a) {
   float vm = -CUDART_INF_F;
@@ -350,7 +353,8 @@ __device__ __forceinline__ void teacher_update(const float (&fy)[N], const float
         // p = 0 contributes exactly 0 (xlogy semantics of nn.KLDivLoss, distillation_loss.py:68);
         // the clamp keeps 0 * (-inf - z) from producing NaN when the teacher holds -inf
         const float d = fmaxf(fy[i], kTeacherFloor) - fz[i];
-        pa[i & 1] = (et > 0.f) ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
+        const bool take = GUARD == 2 ? (et > 0.f || fz[i] == -CUDART_INF_F) : (et > 0.f);
+        pa[i & 1] = take ? fmaf(et, d, pa[i & 1]) : pa[i & 1];
       } else {
         pa[i & 1] = fmaf(et, fy[i] - fz[i], pa[i & 1]);
       }

@@ -224,19 +224,13 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
             p.y1.unpack(t8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) fy[8 + j] = t8[j];
-            // The unguarded cross term (one subtract and one FMA per element) needs finite student logits once the
-            // teacher is clamped: a -inf (or NaN) student logit in the group - the largest unsigned 16-bit patterns,
-            // found with 7 packed maxima - sends the group through the guarded form, which keeps p = 0 entries at
-            // exactly 0 (logits masked with -inf on both sides) and gives inf where the reference does.
-            constexpr bool kFast = kPacked && std::is_same<TZ, __nv_bfloat16>::value;
-            bool plain = kFast;
-            if (kFast) {
-              const uint32_t u0 = __vmaxu2(__vmaxu2(p.z0.a.x, p.z0.a.y), __vmaxu2(p.z0.a.z, p.z0.a.w));
-              const uint32_t u1 = __vmaxu2(__vmaxu2(p.z1.a.x, p.z1.a.y), __vmaxu2(p.z1.a.z, p.z1.a.w));
-              plain = __vcmpgeu2(__vmaxu2(u0, u1), 0xFF80FF80u) == 0;
-            }
-            if (plain) teacher_update<TAU2, 16, false, true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
-            else teacher_update<TAU2, 16, true, true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
+            // The unguarded cross term (one subtract and one FMA per element) is exact for finite student logits once
+            // the teacher is clamped.  A -inf student logit gives what the reference gives: inf where the teacher has
+            // mass, NaN where it has none (0 * inf inside kl_div: logits masked with -inf on both sides are NaN in the
+            // reference too); the guarded form used outside the hot loop (GUARD = 2) does the same.  (Detecting such
+            // groups with packed maxima and sending them through a form that returns 0 for the second case cost 6 % of
+            // the kernel: 957 -> 1017 us.)
+            teacher_update<TAU2, 16, (kPacked ? 0 : 2), true>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
           }
         };
         // L2 prefetch: the loads of a set leave when the previous set is being reduced, i.e. 64 bytes per thread = 32 KB
@@ -305,10 +299,10 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
         }
         if (two) {
           student_update<TAU2, 16>(fz, 16, inv_tau, s.m, s.s1, s.st);
-          if (DENSE) teacher_update<TAU2, 16>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
+          if (DENSE) teacher_update<TAU2, 16, 2>(fy, fz, 16, inv_tau, s.mt, s.t1, s.tt, s.a);
         } else {
           student_update<TAU2, 16>(fz, 8, inv_tau, s.m, s.s1, s.st);
-          if (DENSE) teacher_update<TAU2, 16>(fy, fz, 8, inv_tau, s.mt, s.t1, s.tt, s.a);
+          if (DENSE) teacher_update<TAU2, 16, 2>(fy, fz, 8, inv_tau, s.mt, s.t1, s.tt, s.a);
         }
       }
       for (int i = nvec * 8 + tid; i < V; i += kRowThreads) {  // scalar tail / unaligned rows
@@ -317,7 +311,7 @@ __global__ void __launch_bounds__(kRowThreads, kRowThreads <= 256 ? 2 : 1) kd_st
         student_update<TAU2, 8>(fz, 1, inv_tau, s.m, s.s1, s.st);
         if (DENSE) {
           fy[0] = Elem<TY>::to_f(yrow[i]);
-          teacher_update<TAU2, 8>(fy, fz, 1, inv_tau, s.mt, s.t1, s.tt, s.a);
+          teacher_update<TAU2, 8, 2>(fy, fz, 1, inv_tau, s.mt, s.t1, s.tt, s.a);
         }
       }
     }
