@@ -852,7 +852,10 @@ __device__ __forceinline__ void warp_pass1(const T* __restrict__ row, int V, uin
 // (Measured and not kept, configs[2] size on one B200: 64-element pieces with 4 loads per batch and three CTAs per SM -
 //  21 - 24 row-warps per SM instead of 16 - 717 us; a per-lane cp.async ring of 12 x 16 bytes in shared memory instead
 //  of the register double buffer 842 us; the configuration below 590 us.  More row-warps lengthen every row in
-//  proportion: the SM's XU / issue / load-path mix is saturated at ~0.11 rows per microsecond either way.)
+//  proportion: the SM's XU / issue / load-path mix is saturated at ~0.11 rows per microsecond either way.
+//  A bulk L2 prefetch (cp.async.bulk.prefetch.L2 by lane 0, 2 / 4 passes of 8 KB ahead of the register loads - the
+//  step that took 7 % off K2) measured 635 / 664 us against 623 us without it on the same box: with 14 row-warps of
+//  8 KB in flight each the loads are already deep enough, and the extra requests only compete with them.)
 template <typename T>
 __global__ void __launch_bounds__(32 * kWrWarps, sizeof(T) == 2 ? KD_TOPK_WARP_MINB : 2) kd_topk_warp_kernel(const T* __restrict__ logits, int64_t R, int V,
                                                                        int64_t row_stride, int k,
