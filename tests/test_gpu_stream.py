@@ -126,10 +126,10 @@ def test_sparse_matches_oracle(B, T, V, dtype, K, tau):
 
 
 @pytest.mark.parametrize("sparse", [False, True], ids=["dense", "topk"])
-def test_many_rows_per_cta_through_the_ring(sparse):
-    """More scored rows than CTAs and several ring turns per row: every CTA re-fills the shared-memory stash and the
-    ring slots across rows (dense: 512-thread sets of 8192 logits, top-k: 1024-thread sets of 16384), with ignored
-    rows, a partial last set and -inf teacher entries in between."""
+def test_many_rows_per_cta_through_the_stash(sparse):
+    """More scored rows than CTAs and many register sets per row: every CTA re-uses its shared-memory stash slots and
+    runs the bulk L2 prefetch across rows (dense: 512-thread sets of 8192 logits, top-k: 1024-thread sets of 16384),
+    with ignored rows, a partial last set and -inf teacher entries (whole leading groups of a thread) in between."""
     B, T, V, K = 4, 121, 8192 * 9 + 8 * 700, 32
     g = torch.Generator().manual_seed(5)
     z = (torch.randn(B, T, V, generator=g) * 2).bfloat16()
