@@ -78,6 +78,9 @@ int kd_finalize_losses(const float* sums, float tau, float alpha, int sparse, fl
  * kd_prepare_rows, or the all-reduced global N).  grad_scale: host scalar folded into dlogits.
  * dlogits: NULL (forward only: one sweep, 4 B/element for bf16) or a contiguous [B,T,V] buffer of
  * z's dtype that receives d(total)/dz * grad_scale for EVERY row (zeros on invalid rows).
+ * -inf entries: a -inf teacher logit has probability 0 and contributes 0 (xlogy convention of nn.KLDivLoss, :68);
+ * a -inf student logit gives what the reference gives - an infinite KL where the teacher has mass on that column,
+ * NaN where the teacher holds -inf there too - with CE, the teacher monitor and other rows' gradients unaffected.
  * workspace: kd_stream_workspace_bytes() bytes, 16-byte aligned. */
 size_t kd_stream_workspace_bytes(void);
 int kd_dense_fwd_bwd(const void* z, int z_dtype, int64_t z_stride_b, int64_t z_stride_t,
